@@ -1,0 +1,78 @@
+"""CPU: the numpy oracle (oracle/tempo_np.py) against fixtures produced by the
+UNMODIFIED reference (tests/golden/make_golden.py) and against the golden density
+matrices quoted from the reference's own tests."""
+import numpy as np
+import pytest
+
+from conftest import golden_callables, load_golden
+from oracle import tempo_np as onp
+
+PT_CASES = ["pt_k12_eps7_n30", "pt_k8_eps9_n24", "pt_refA", "pt_refC"]
+TEMPO_CASES = ["tempo_c1_k20_eps7_n60", "tempo_refA", "tempo_refC",
+               "tempo_nondiag"]
+
+
+def run_pt_oracle(g):
+    influence, propagators = golden_callables(g)
+    pt = onp.PtTempoOracle(int(g["dim"]), influence, int(g["num_steps"]),
+                           int(g["dkmax"]), float(g["epsrel"]))
+    pt.compute()
+    mpos = pt.mpo_tensors()
+    caps = onp.compute_caps(mpos, int(g["dim"]))
+    states = onp.compute_dynamics([mpos], [caps], propagators,
+                                  g["initial_state"])
+    return pt, mpos, caps, states
+
+
+@pytest.mark.parametrize("name", PT_CASES)
+def test_pt_oracle_matches_reference(name):
+    g = load_golden(name)
+    pt, mpos, caps, states = run_pt_oracle(g)
+    bonds = [1] + pt.bond_dimensions() + [1]
+    assert bonds == list(g["bond_dims"])
+    np.testing.assert_allclose(states, g["states"], atol=1e-10, rtol=0)
+    np.testing.assert_allclose(caps[0], g["cap_first"], atol=1e-10)
+    if "rho_golden" in g:   # the reference's own decimal=4 pin
+        np.testing.assert_almost_equal(states[-1], g["rho_golden"], decimal=4)
+
+
+@pytest.mark.parametrize("name", TEMPO_CASES)
+def test_tempo_oracle_matches_reference(name):
+    g = load_golden(name)
+    influence, propagators = golden_callables(g)
+    d2 = int(g["dim"]) ** 2
+    dkmax = None if int(g["dkmax"]) < 0 else int(g["dkmax"])
+    tb = onp.TempoOracle(g["initial_state"], influence, g["unitary"],
+                         propagators, np.ones(d2), np.ones(d2), dkmax,
+                         float(g["epsrel"]))
+    _, s0 = tb.initialize()
+    states = [s0]
+    for _ in range(int(g["num_steps"])):
+        states.append(tb.compute_step()[1])
+    d = int(g["dim"])
+    states = np.array(states).reshape(-1, d, d)
+    assert tb.bond_dimensions() == list(g["bond_dims"])
+    # TEMPO amplifies 1e-16 rounding differences (contraction order) to ~10*eps
+    # once the memory cut-off sets in: perturbing the influence matrices of the
+    # REFERENCE by 1e-15 relative moves its own states by 4e-8 (DESIGN.md,
+    # "reproducibility floor").  Hence eps-scaled tolerance + exact bond dims.
+    np.testing.assert_allclose(states, g["states"],
+                               atol=50 * float(g["epsrel"]), rtol=0)
+    k = min(10, len(states))
+    np.testing.assert_allclose(states[:k], g["states"][:k], atol=1e-9, rtol=0)
+    if "rho_golden" in g:
+        np.testing.assert_almost_equal(states[-1], g["rho_golden"], decimal=4)
+
+
+def test_truncation_rule_matches_in_repo_pin():
+    """oqupy/mps_mpo.py:452-457: chi = count_nonzero(cumsum(flip(s)^2) > (s0 eps)^2)."""
+    rng = np.random.default_rng(3)
+    for _ in range(20):
+        s = np.sort(10.0 ** rng.uniform(-12, 0, size=40))[::-1]
+        q1, _ = np.linalg.qr(rng.normal(size=(60, 40)) + 1j * rng.normal(size=(60, 40)))
+        q2, _ = np.linalg.qr(rng.normal(size=(40, 40)) + 1j * rng.normal(size=(40, 40)))
+        mat = (q1 * s) @ q2
+        eps = 10.0 ** rng.uniform(-9, -3)
+        chi = np.count_nonzero(np.cumsum(np.flip(s) ** 2) > (s[0] * eps) ** 2)
+        u, sk, vh, rest = onp.truncated_svd(mat, eps)
+        assert sk.size == chi and rest.size == 40 - chi
