@@ -1,0 +1,112 @@
+/* oqupy_b200 -- C-ABI of the B200-native TEMPO / PT-TEMPO engine.
+ *
+ * Plain pointers and sizes only (no torch types).  All tensor pointers are DEVICE
+ * pointers to complex128 (interleaved re,im doubles) unless stated otherwise;
+ * `stream` is a cudaStream_t passed as void*.  Every function returns 0 on success
+ * or a negative B200_E* code; b200_last_error() gives the message.
+ *
+ * The reference (OQuPy 0.5.0) is pure Python and has no FFI: its hot path reaches
+ * the arithmetic through the third-party `tensornetwork` calls listed below.  Each
+ * entry point names the reference call site(s) it replaces.
+ */
+#ifndef OQUPY_B200_H
+#define OQUPY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK 0
+#define B200_EINVAL (-1)
+#define B200_ECUDA (-2)
+#define B200_ENOCONV (-3)
+#define B200_ESIZE (-4)
+
+const char* b200_last_error(void);
+int b200_abi_version(void);
+/* number of kernel launches issued through this library since load */
+uint64_t b200_launch_count(void);
+
+/* ---------------------------------------------------------------------------
+ * Strided, doubly-batched complex GEMM with per-batch scale:
+ *   C[b1,b2][i,j] = scale[b1,b2] * sum_t opA(A[b1,b2])[i,t] * opB(B[b1,b2])[t,j]
+ * Every operand is addressed with ELEMENT strides (row, col, batch1, batch2), so
+ * the delta-structured influence MPO sites never have to be materialised.
+ * scale may be NULL (== 1).  conj_a / conj_b conjugate the operand elements.
+ * If accumulate != 0 the result is added to C.
+ *
+ * Replaces: tn.contractors.greedy([A_site, B_site, carry])  oqupy/backends/node_array.py:395,519
+ *           svh @ nodes[i+-1]                               oqupy/backends/node_array.py:272-273,295-296
+ *           node @ node in compute_dynamics                 oqupy/system_dynamics.py:638,649,697
+ *           SimpleProcessTensor.compute_caps                oqupy/process_tensor.py:398,403
+ */
+typedef struct {
+  const void* ptr;
+  int64_t row, col, b1, b2; /* element strides */
+  int conj;
+} b200_operand;
+
+int b200_zgemm_strided(void* stream, int m, int n, int k, int nb1, int nb2,
+                       const b200_operand* a, const b200_operand* b,
+                       void* c, int64_t c_row, int64_t c_col, int64_t c_b1,
+                       int64_t c_b2, const void* scale, int64_t s_b1,
+                       int64_t s_b2, int accumulate);
+
+/* ---------------------------------------------------------------------------
+ * eps-truncated SVD  (one-sided block-Jacobi, fp64 DMMA Gram/apply panels).
+ *
+ * b200_svd_factor: theta is an m x n matrix addressed theta[i*rs + j*cs].
+ *   Computes all singular triplets on the device, sorts them, applies the
+ *   reference's tail-norm rule
+ *       keep = #{ j : sqrt(sum_{i>=j} s_i^2) > eps * s_0 }      (eps < 0: keep all)
+ *   and asynchronously copies {keep, sweeps, status, rotations} (4 x int32) to
+ *   `info_host` (pinned host memory).  The caller synchronises the stream, reads
+ *   keep, allocates exact-size outputs and calls b200_svd_emit.
+ *   `work` must hold b200_svd_workspace_bytes(m, n) bytes of device memory.
+ *
+ * b200_svd_emit: writes U (m x keep) with the row index i split as
+ *   (i / u_na, i % u_na) -> address (i/u_na)*u_so + (i%u_na)*u_sa + j*u_sj, and
+ *   S*Vh (keep x n) row-major into svh.  Either output may be NULL.
+ *
+ * b200_svd_values: copies the min(m,n) sorted singular values (doubles) to s_out.
+ *
+ * Replaces: tn.split_node_full_svd(node, left_edges, right_edges,
+ *             max_truncation_err=eps, relative=True)   oqupy/backends/node_array.py:262,285,541
+ *           and `s @ vh` at node_array.py:272,295,552; truncation rule mirrored at
+ *           oqupy/mps_mpo.py:452-457.
+ */
+size_t b200_svd_workspace_bytes(int m, int n);
+int b200_svd_factor(void* stream, const void* theta, int m, int n, int64_t rs,
+                    int64_t cs, double eps, void* work, int32_t* info_host);
+int b200_svd_emit(void* stream, const void* work, int m, int n, int keep,
+                  void* u, int u_na, int64_t u_so, int64_t u_sa, int64_t u_sj,
+                  void* svh);
+int b200_svd_values(void* stream, const void* work, int m, int n, double* s_out);
+
+/* ---------------------------------------------------------------------------
+ * compute_dynamics step for ONE environment and `nvec` ensemble members that
+ * share the process tensor (oqupy/system_dynamics.py:631-700):
+ *   v'[e, r, j] = sum_x P2[e][j,x] * sum_l T[l, r, x] * (sum_i P1[e][x,i] v[e, l, i])
+ * T is the rank-3 PT-MPO site (chi_l, chi_r, d2) (oqupy/process_tensor.py:301-305),
+ * v (nvec, chi_l, d2), v_out (nvec, chi_r, d2), p1/p2 (nvec, d2, d2) row-major.
+ * If cap (chi_l) and rho_out (nvec, d2) are non-NULL, the read-out
+ *   rho[e, i] = sum_l cap[l] * v[e, l, i]          (system_dynamics.py:643-651)
+ * of the INPUT state is fused into the same pass.  `work` holds
+ * b200_dyn_workspace_bytes(...) bytes of device scratch.
+ */
+size_t b200_dyn_workspace_bytes(int nvec, int chi_l, int chi_r, int d2);
+int b200_dyn_step(void* stream, int nvec, int chi_l, int chi_r, int d2,
+                  const void* t, const void* p1, const void* p2, const void* v,
+                  void* v_out, const void* cap, void* rho_out, void* work);
+
+/* cap_k[l] = sum_{r,x} T[l,r,x] * cap_next[r] * tr2[x]   (oqupy/process_tensor.py:380-406) */
+int b200_caps_step(void* stream, int chi_l, int chi_r, int d2, const void* t,
+                   const void* cap_next, const void* tr2, void* cap_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OQUPY_B200_H */

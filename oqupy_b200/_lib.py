@@ -1,0 +1,219 @@
+"""ctypes binding of the C-ABI library ``liboqupy_b200.so`` (include/oqupy_b200.h).
+
+torch is used for device memory and streams only.  There is NO CPU fallback: if the
+shared library or a CUDA device is missing, constructing :class:`CudaOps` raises.
+"""
+import ctypes
+import os
+from ctypes import (POINTER, Structure, c_char_p, c_double, c_int, c_int32,
+                    c_int64, c_size_t, c_uint64, c_void_p)
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liboqupy_b200.so")
+
+EXPORTS = [
+    "b200_last_error", "b200_abi_version", "b200_launch_count",
+    "b200_zgemm_strided", "b200_svd_workspace_bytes", "b200_svd_factor",
+    "b200_svd_emit", "b200_svd_values", "b200_dyn_workspace_bytes",
+    "b200_dyn_step", "b200_caps_step",
+]
+
+
+class B200Error(RuntimeError):
+    """Raised when a C-ABI call returns a non-zero status."""
+
+
+class _Operand(Structure):
+    _fields_ = [("ptr", c_void_p), ("row", c_int64), ("col", c_int64),
+                ("b1", c_int64), ("b2", c_int64), ("conj", c_int)]
+
+
+_lib = None
+
+
+def load_library():
+    """Load (once) and return the ctypes handle; raises if the .so is missing."""
+    global _lib  # pylint: disable=global-statement
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B200Error(
+            f"{LIB_PATH} not found: build it with oqupy_b200/csrc/build.sh "
+            "(or __graft_entry__.build()). There is no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.b200_last_error.restype = c_char_p
+    lib.b200_abi_version.restype = c_int
+    lib.b200_launch_count.restype = c_uint64
+    lib.b200_zgemm_strided.restype = c_int
+    lib.b200_zgemm_strided.argtypes = [
+        c_void_p, c_int, c_int, c_int, c_int, c_int, POINTER(_Operand),
+        POINTER(_Operand), c_void_p, c_int64, c_int64, c_int64, c_int64,
+        c_void_p, c_int64, c_int64, c_int]
+    lib.b200_svd_workspace_bytes.restype = c_size_t
+    lib.b200_svd_workspace_bytes.argtypes = [c_int, c_int]
+    lib.b200_svd_factor.restype = c_int
+    lib.b200_svd_factor.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int64,
+                                    c_int64, c_double, c_void_p, c_void_p]
+    lib.b200_svd_emit.restype = c_int
+    lib.b200_svd_emit.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int,
+                                  c_void_p, c_int, c_int64, c_int64, c_int64,
+                                  c_void_p]
+    lib.b200_svd_values.restype = c_int
+    lib.b200_svd_values.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p]
+    lib.b200_dyn_workspace_bytes.restype = c_size_t
+    lib.b200_dyn_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
+    lib.b200_dyn_step.restype = c_int
+    lib.b200_dyn_step.argtypes = [c_void_p, c_int, c_int, c_int, c_int] + \
+        [c_void_p] * 8
+    lib.b200_caps_step.restype = c_int
+    lib.b200_caps_step.argtypes = [c_void_p, c_int, c_int, c_int] + \
+        [c_void_p] * 4
+    _lib = lib
+    return lib
+
+
+class View:
+    """Strided 2-D (+ two batch strides) view of a complex128 tensor, in elements."""
+    __slots__ = ("t", "row", "col", "b1", "b2", "off", "conj")
+
+    def __init__(self, t, row=0, col=0, b1=0, b2=0, off=0, conj=False):
+        self.t, self.row, self.col = t, int(row), int(col)
+        self.b1, self.b2, self.off, self.conj = int(b1), int(b2), int(off), conj
+
+
+class SvdHandle:
+    """Result of svd_factor: keeps the device workspace alive until emit."""
+    __slots__ = ("work", "m", "n", "keep", "sweeps", "status", "rotations")
+
+
+class CudaOps:
+    """The product ops object: every method is a C-ABI call on ``cuda:device``."""
+
+    name = "cuda"
+
+    def __init__(self, device=0):
+        if not torch.cuda.is_available():
+            raise B200Error("oqupy_b200 needs a CUDA device (no CPU fallback).")
+        self.lib = load_library()
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        self._info = torch.zeros(4, dtype=torch.int32).pin_memory()
+        self._info_np = self._info.numpy()
+        self._work = None
+        self.one = torch.ones(1, dtype=torch.complex128, device=self.device)
+        self.svd_log = None       # optional list: (m, n, keep, sweeps)
+
+    # -- memory ---------------------------------------------------------------
+    def empty(self, *shape):
+        return torch.empty(shape, dtype=torch.complex128, device=self.device)
+
+    def from_host(self, array):
+        a = np.ascontiguousarray(np.asarray(array, dtype=np.complex128))
+        return torch.from_numpy(a).to(self.device)
+
+    def to_host(self, tensor):
+        return tensor.cpu().numpy()
+
+    def _stream(self):
+        return c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _check(self, code, what):
+        if code != 0:
+            raise B200Error(f"{what} failed ({code}): "
+                            f"{self.lib.b200_last_error().decode()}")
+
+    @staticmethod
+    def _ptr(t, off=0):
+        return t.data_ptr() + 16 * off
+
+    # -- kernels --------------------------------------------------------------
+    def gemm(self, m, n, k, a, b, c, nb1=1, nb2=1, scale=None, accumulate=False):
+        oa = _Operand(self._ptr(a.t, a.off), a.row, a.col, a.b1, a.b2,
+                      1 if a.conj else 0)
+        ob = _Operand(self._ptr(b.t, b.off), b.row, b.col, b.b1, b.b2,
+                      1 if b.conj else 0)
+        if scale is None:
+            sp, s1, s2 = None, 0, 0
+        else:
+            sp, s1, s2 = self._ptr(scale.t, scale.off), scale.b1, scale.b2
+        code = self.lib.b200_zgemm_strided(
+            self._stream(), m, n, k, nb1, nb2, ctypes.byref(oa),
+            ctypes.byref(ob), self._ptr(c.t, c.off), c.row, c.col, c.b1, c.b2,
+            sp, s1, s2, 1 if accumulate else 0)
+        self._check(code, "b200_zgemm_strided")
+
+    def svd_factor(self, theta, m, n, rs, cs, eps, off=0):
+        nbytes = self.lib.b200_svd_workspace_bytes(m, n)
+        work = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        code = self.lib.b200_svd_factor(
+            self._stream(), self._ptr(theta, off), m, n, rs, cs,
+            -1.0 if eps is None else float(eps), work.data_ptr(),
+            self._info.data_ptr())
+        self._check(code, "b200_svd_factor")
+        torch.cuda.current_stream(self.device).synchronize()
+        h = SvdHandle()
+        h.work, h.m, h.n = work, m, n
+        h.keep, h.sweeps, h.status, h.rotations = (int(x) for x in self._info_np)
+        if h.status != 0:
+            raise B200Error(f"Jacobi SVD did not converge ({m}x{n}, "
+                            f"{h.sweeps} sweeps)")
+        if self.svd_log is not None:
+            self.svd_log.append((m, n, h.keep, h.sweeps))
+        return h
+
+    def svd_emit(self, h, u=None, u_na=1, u_so=0, u_sa=0, u_sj=0, svh=None):
+        code = self.lib.b200_svd_emit(
+            self._stream(), h.work.data_ptr(), h.m, h.n, h.keep,
+            None if u is None else u.data_ptr(), u_na, u_so, u_sa, u_sj,
+            None if svh is None else svh.data_ptr())
+        self._check(code, "b200_svd_emit")
+
+    def svd_values(self, h):
+        k = min(h.m, h.n)
+        out = torch.empty(k, dtype=torch.float64, device=self.device)
+        code = self.lib.b200_svd_values(self._stream(), h.work.data_ptr(), h.m,
+                                        h.n, out.data_ptr())
+        self._check(code, "b200_svd_values")
+        return out.cpu().numpy()
+
+    def dyn_step(self, nvec, chi_l, chi_r, d2, t, p1, p2, v, v_out, cap=None,
+                 rho_out=None):
+        nbytes = self.lib.b200_dyn_workspace_bytes(nvec, chi_l, chi_r, d2)
+        if self._work is None or self._work.numel() < nbytes:
+            self._work = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8,
+                                     device=self.device)
+        code = self.lib.b200_dyn_step(
+            self._stream(), nvec, chi_l, chi_r, d2, t.data_ptr(), p1.data_ptr(),
+            p2.data_ptr(), v.data_ptr(), v_out.data_ptr(),
+            None if cap is None else cap.data_ptr(),
+            None if rho_out is None else rho_out.data_ptr(),
+            self._work.data_ptr())
+        self._check(code, "b200_dyn_step")
+
+    def caps_step(self, chi_l, chi_r, d2, t, cap_next, tr2, cap_out):
+        code = self.lib.b200_caps_step(
+            self._stream(), chi_l, chi_r, d2, t.data_ptr(), cap_next.data_ptr(),
+            tr2.data_ptr(), cap_out.data_ptr())
+        self._check(code, "b200_caps_step")
+
+    def launch_count(self):
+        return int(self.lib.b200_launch_count())
+
+    def synchronize(self):
+        torch.cuda.synchronize(self.device)
+
+
+_default_ops = None
+
+
+def default_ops():
+    """The process-wide CudaOps (raises without CUDA / the built library)."""
+    global _default_ops  # pylint: disable=global-statement
+    if _default_ops is None:
+        dev = int(os.environ.get("LOCAL_RANK", "0")) if torch.cuda.is_available() \
+            and torch.cuda.device_count() > 1 else 0
+        _default_ops = CudaOps(dev)
+    return _default_ops

@@ -1,0 +1,655 @@
+// eps-truncated complex128 SVD on the device: one-sided BLOCK Jacobi.
+//
+// Replaces tn.split_node_full_svd(max_truncation_err=eps, relative=True)
+// (reference call sites oqupy/backends/node_array.py:262,285,541).
+//
+// Algorithm (B200-first, not LAPACK's bidiagonalisation):
+//   * X = theta (m >= n) or theta^H (m < n), p x q with p >= q, stored as PANELS of
+//     4 columns: panel j holds X[:, 4j:4j+4] as [row][4] complex128 (64 B per row),
+//     so a panel streams through L2/shared memory fully coalesced.  A q x q matrix W
+//     (initially I) accumulates the right rotations in the same panel layout.
+//   * Hestenes one-sided Jacobi on panel pairs, round-robin tournament ordering:
+//     per stage every CTA owns a pair (I, J) = 8 columns, stages them in shared
+//     memory, forms their 8x8 Gram matrix on the fp64 tensor cores (DMMA.8x8x4),
+//     diagonalises it with a warp-parallel two-sided Jacobi eigensolver, and applies
+//     the 8x8 rotation to the 8 columns of X and of W, again with DMMA.
+//     grid.sync() separates stages (cooperative persistent kernel).
+//   * Convergence: a full sweep in which no pair had |g_ij| > tol*sqrt(g_ii g_jj).
+//   * sigma_j = ||y_j||; sort; reference tail-norm rule picks `keep`; emit kernel
+//     writes U[:, :keep] and S*Vh[:keep] in the layouts the MPS engine asks for.
+#include <cooperative_groups.h>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+using b200::dmma884;
+
+namespace {
+
+constexpr int PC = 4;            // columns per panel
+constexpr int JT = 512;          // threads of the Jacobi kernel
+constexpr int JW = JT / 32;      // warps
+constexpr int MAX_SWEEPS = 40;
+constexpr int INNER_SWEEPS = 3;
+constexpr int SMEM_STAGE_LIMIT = 200 * 1024;  // bytes of panel data staged per CTA
+
+struct Header {        // lives at the start of the workspace (device)
+  int m, n, p, q, npan, nb, transposed, keep;
+  int sweeps, status, rotations, pad;
+  double eps, s0;
+};
+
+struct Layout {
+  size_t header, xp, wp, sig2, sval, perm, flags, total;
+  int p, q, npan, nb, transposed;
+};
+
+__host__ __device__ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+__host__ Layout make_layout(int m, int n) {
+  Layout L;
+  L.transposed = (m < n) ? 1 : 0;
+  L.p = L.transposed ? n : m;
+  L.q = L.transposed ? m : n;
+  L.npan = (L.q + PC - 1) / PC;
+  L.nb = (L.npan & 1) ? L.npan + 1 : L.npan;   // even number of panels
+  if (L.nb < 2) L.nb = 2;
+  size_t off = 0;
+  L.header = off; off = align256(off + sizeof(Header));
+  L.xp = off;   off = align256(off + (size_t)L.nb * L.p * PC * sizeof(cplx));
+  L.wp = off;   off = align256(off + (size_t)L.nb * L.q * PC * sizeof(cplx));
+  L.sig2 = off; off = align256(off + (size_t)L.nb * PC * sizeof(double));
+  L.sval = off; off = align256(off + (size_t)L.nb * PC * sizeof(double));
+  L.perm = off; off = align256(off + (size_t)L.nb * PC * sizeof(int));
+  L.flags = off; off = align256(off + 64 * sizeof(int));
+  L.total = off;
+  return L;
+}
+
+// ------------------------------------------------------------------ load / init
+__global__ void svd_load_kernel(const cplx* __restrict__ theta, long long rs,
+                                long long cs, int m, int n, int p, int q, int nb,
+                                int transposed, cplx* __restrict__ xp,
+                                cplx* __restrict__ wp) {
+  const long long total_x = (long long)nb * p * PC;
+  const long long total_w = (long long)nb * q * PC;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+       e < total_x + total_w; e += (long long)gridDim.x * blockDim.x) {
+    if (e < total_x) {
+      const int c4 = (int)(e % PC);
+      const long long t = e / PC;
+      const int row = (int)(t % p);
+      const int pan = (int)(t / p);
+      const int col = pan * PC + c4;
+      cplx v = make_double2(0.0, 0.0);
+      if (col < q) {
+        if (!transposed) {
+          v = theta[row * rs + col * cs];
+        } else {           // X = theta^H : X[row][col] = conj(theta[col][row])
+          v = theta[col * rs + row * cs];
+          v.y = -v.y;
+        }
+      }
+      xp[e] = v;
+    } else {
+      const long long f = e - total_x;
+      const int c4 = (int)(f % PC);
+      const long long t = f / PC;
+      const int row = (int)(t % q);
+      const int pan = (int)(t / q);
+      const int col = pan * PC + c4;
+      wp[f] = make_double2((col == row) ? 1.0 : 0.0, 0.0);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ 8x8 helpers
+// Shared scratch of the Jacobi kernel (static part).
+struct JacobiShared {
+  double red[JW][128];   // per-warp partial Gram fragments (re: 0..63, im: 64..127)
+  double gr[8][8], gi[8][8];   // Gram / working Hermitian matrix
+  double vr[8][8], vi[8][8];   // accumulated eigenvectors
+  double sr[8][8], si[8][8];   // sorted eigenvectors (the 8x8 rotation to apply)
+  double rot_c[4], rot_sr[4], rot_si[4];
+  int rot_i[4], rot_j[4];
+  int need;                    // pair needs a rotation
+};
+
+// Gram matrix of the 8 columns [XI | XJ] (each [rows][4]) over `rows` rows.
+__device__ void gram8(const cplx* XI, const cplx* XJ, int rows, JacobiShared& S) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const cplx* src = (g < 4) ? (XI + g) : (XJ + (g - 4));
+  double r0 = 0.0, r1 = 0.0, i0 = 0.0, i1 = 0.0;
+  for (int base = warp * 4; base < rows; base += JW * 4) {
+    const int row = base + t;
+    cplx x = make_double2(0.0, 0.0);
+    if (row < rows) x = src[(size_t)row * PC];
+    // G = X^H X :  Gr = Xr^T Xr + Xi^T Xi ;  Gi = Xr^T Xi - Xi^T Xr
+    dmma884(r0, r1, x.x, x.x);
+    dmma884(r0, r1, x.y, x.y);
+    dmma884(i0, i1, x.x, x.y);
+    dmma884(i0, i1, -x.y, x.x);
+  }
+  S.red[warp][g * 8 + 2 * t] = r0;
+  S.red[warp][g * 8 + 2 * t + 1] = r1;
+  S.red[warp][64 + g * 8 + 2 * t] = i0;
+  S.red[warp][64 + g * 8 + 2 * t + 1] = i1;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    double acc = 0.0;
+#pragma unroll
+    for (int w = 0; w < JW; ++w) acc += S.red[w][threadIdx.x];
+    const int e = threadIdx.x & 63;
+    if (threadIdx.x < 64) S.gr[e >> 3][e & 7] = acc;
+    else S.gi[e >> 3][e & 7] = acc;
+  }
+  __syncthreads();
+}
+
+// Warp 0: decide whether the pair needs work; if so diagonalise the 8x8 Hermitian
+// Gram matrix (cyclic two-sided Jacobi, 4 disjoint rotations per round) and leave
+// the eigenvector matrix, columns sorted by DESCENDING eigenvalue, in S.sr/S.si.
+__device__ void eig8_warp0(JacobiShared& S, double tol2) {
+  const int lane = threadIdx.x;   // caller guarantees threadIdx.x < 32
+  // --- convergence test on the raw Gram matrix
+  double worst = 0.0;
+  for (int e = lane; e < 64; e += 32) {
+    const int i = e >> 3, j = e & 7;
+    if (i < j) {
+      const double a = S.gr[i][i], b = S.gr[j][j];
+      const double g2 = S.gr[i][j] * S.gr[i][j] + S.gi[i][j] * S.gi[i][j];
+      if (a > 0.0 && b > 0.0 && g2 > tol2 * a * b) worst = 1.0;
+    }
+  }
+  const unsigned any = __ballot_sync(0xffffffffu, worst > 0.0);
+  if (lane == 0) S.need = any ? 1 : 0;
+  if (!any) { __syncwarp(); return; }
+
+  // symmetrise exactly + V = I
+  for (int e = lane; e < 64; e += 32) {
+    const int i = e >> 3, j = e & 7;
+    S.vr[i][j] = (i == j) ? 1.0 : 0.0;
+    S.vi[i][j] = 0.0;
+  }
+  __syncwarp();
+  for (int e = lane; e < 64; e += 32) {
+    const int i = e >> 3, j = e & 7;
+    if (i > j) { S.gr[i][j] = S.gr[j][i]; S.gi[i][j] = -S.gi[j][i]; }
+    if (i == j) S.gi[i][j] = 0.0;
+  }
+  __syncwarp();
+
+  const int pr = lane >> 3, tt = lane & 7;
+  for (int sweep = 0; sweep < INNER_SWEEPS; ++sweep) {
+    for (int round = 0; round < 7; ++round) {
+      if (lane < 4) {
+        // round-robin tournament on 8 players: position k -> player
+        const int ka = lane, kb = 7 - lane;
+        int i = (ka == 0) ? 0 : 1 + ((ka - 1 + round) % 7);
+        int j = 1 + ((kb - 1 + round) % 7);
+        if (i > j) { const int s = i; i = j; j = s; }
+        const double a = S.gr[i][i], b = S.gr[j][j];
+        const double xr = S.gr[i][j], xi = S.gi[i][j];
+        const double mag2 = xr * xr + xi * xi;
+        double c = 1.0, sr_ = 0.0, si_ = 0.0;
+        if (mag2 > 0.0 && mag2 > 1e-34 * fabs(a * b)) {
+          const double mag = sqrt(mag2);
+          const double zeta = (b - a) / (2.0 * mag);
+          const double tq = ((zeta >= 0.0) ? 1.0 : -1.0) /
+                            (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          c = 1.0 / sqrt(1.0 + tq * tq);
+          const double s = tq * c;
+          // s * e^{i phi},  e^{i phi} = g_ij / |g_ij|
+          sr_ = s * xr / mag;
+          si_ = s * xi / mag;
+        }
+        S.rot_i[lane] = i; S.rot_j[lane] = j;
+        S.rot_c[lane] = c; S.rot_sr[lane] = sr_; S.rot_si[lane] = si_;
+      }
+      __syncwarp();
+      const int i = S.rot_i[pr], j = S.rot_j[pr];
+      const double c = S.rot_c[pr], sr_ = S.rot_sr[pr], si_ = S.rot_si[pr];
+      // R = [[c, s e^{i phi}], [-s e^{-i phi}, c]] on columns (i, j)
+      {  // G <- G R   (row tt)
+        const double air = S.gr[tt][i], aii = S.gi[tt][i];
+        const double ajr = S.gr[tt][j], aji = S.gi[tt][j];
+        // new_i = c*a_i - conj(se)*a_j ; conj(se) = (sr_, -si_)
+        S.gr[tt][i] = c * air - (sr_ * ajr + si_ * aji);
+        S.gi[tt][i] = c * aii - (sr_ * aji - si_ * ajr);
+        // new_j = se*a_i + c*a_j
+        S.gr[tt][j] = (sr_ * air - si_ * aii) + c * ajr;
+        S.gi[tt][j] = (sr_ * aii + si_ * air) + c * aji;
+        // V <- V R
+        const double vir = S.vr[tt][i], vii = S.vi[tt][i];
+        const double vjr = S.vr[tt][j], vji = S.vi[tt][j];
+        S.vr[tt][i] = c * vir - (sr_ * vjr + si_ * vji);
+        S.vi[tt][i] = c * vii - (sr_ * vji - si_ * vjr);
+        S.vr[tt][j] = (sr_ * vir - si_ * vii) + c * vjr;
+        S.vi[tt][j] = (sr_ * vii + si_ * vir) + c * vji;
+      }
+      __syncwarp();
+      {  // G <- R^H G  (column tt):  R^H = [[c, -s e^{i phi}], [s e^{-i phi}, c]]
+        const double air = S.gr[i][tt], aii = S.gi[i][tt];
+        const double ajr = S.gr[j][tt], aji = S.gi[j][tt];
+        // new_i = c*a_i - se*a_j
+        S.gr[i][tt] = c * air - (sr_ * ajr - si_ * aji);
+        S.gi[i][tt] = c * aii - (sr_ * aji + si_ * ajr);
+        // new_j = conj(se)*a_i + c*a_j
+        S.gr[j][tt] = (sr_ * air + si_ * aii) + c * ajr;
+        S.gi[j][tt] = (sr_ * aii - si_ * air) + c * aji;
+      }
+      __syncwarp();
+      if (lane < 4) {   // clean the annihilated entries
+        const int ii = S.rot_i[lane], jj = S.rot_j[lane];
+        if (S.rot_sr[lane] != 0.0 || S.rot_si[lane] != 0.0) {
+          S.gr[ii][jj] = 0.0; S.gi[ii][jj] = 0.0;
+          S.gr[jj][ii] = 0.0; S.gi[jj][ii] = 0.0;
+        }
+        S.gi[ii][ii] = 0.0; S.gi[jj][jj] = 0.0;
+      }
+      __syncwarp();
+    }
+  }
+  // --- sort eigenvectors by descending eigenvalue
+  if (lane < 8) {
+    const double lam = S.gr[lane][lane];
+    int rank = 0;
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      const double lo = S.gr[o][o];
+      if (lo > lam || (lo == lam && o < lane)) ++rank;
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      S.sr[r][rank] = S.vr[r][lane];
+      S.si[r][rank] = S.vi[r][lane];
+    }
+  }
+  __syncwarp();
+}
+
+// [XI | XJ] <- [XI | XJ] * R  over `rows` rows, R = S.sr + i S.si (8x8), in place.
+__device__ void apply8(cplx* XI, cplx* XJ, int rows, const JacobiShared& S) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  // B fragments: B[k][col] with k = kstep*4 + t, col = g
+  const double b0r = S.sr[t][g], b0i = S.si[t][g];
+  const double b1r = S.sr[4 + t][g], b1i = S.si[4 + t][g];
+  for (int base = warp * 8; base < rows; base += JW * 8) {
+    const int row = base + g;
+    cplx a0 = make_double2(0.0, 0.0), a1 = a0;
+    if (row < rows) {
+      a0 = XI[(size_t)row * PC + t];
+      a1 = XJ[(size_t)row * PC + t];
+    }
+    double dr0 = 0.0, dr1 = 0.0, di0 = 0.0, di1 = 0.0;
+    dmma884(dr0, dr1, a0.x, b0r);
+    dmma884(dr0, dr1, -a0.y, b0i);
+    dmma884(di0, di1, a0.x, b0i);
+    dmma884(di0, di1, a0.y, b0r);
+    dmma884(dr0, dr1, a1.x, b1r);
+    dmma884(dr0, dr1, -a1.y, b1i);
+    dmma884(di0, di1, a1.x, b1i);
+    dmma884(di0, di1, a1.y, b1r);
+    __syncwarp();
+    if (row < rows) {
+      // D[g][2t], D[g][2t+1]: columns 0..3 -> XI, 4..7 -> XJ
+      cplx* dst = (t < 2) ? (XI + (size_t)row * PC + 2 * t)
+                          : (XJ + (size_t)row * PC + 2 * (t - 2));
+      dst[0] = make_double2(dr0, di0);
+      dst[1] = make_double2(dr1, di1);
+    }
+  }
+}
+
+__device__ __forceinline__ void copy_panel(cplx* dst, const cplx* src, int rows) {
+  const double2* s = src;
+  double2* d = dst;
+  const int total = rows * PC;
+  for (int e = threadIdx.x; e < total; e += JT) d[e] = s[e];
+}
+
+// ------------------------------------------------------------------ Jacobi kernel
+__global__ void __launch_bounds__(JT, 1)
+jacobi_kernel(cplx* __restrict__ xp, cplx* __restrict__ wp, int p, int q, int nb,
+              int staged, double tol2, int* __restrict__ flags,
+              Header* __restrict__ hdr) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  __shared__ JacobiShared S;
+  cg::grid_group grid = cg::this_grid();
+
+  cplx* sI = reinterpret_cast<cplx*>(dyn_smem);
+  cplx* sJ = sI + (size_t)p * PC;
+  const int npairs = nb / 2;
+  const size_t xpan = (size_t)p * PC, wpan = (size_t)q * PC;
+
+  int sweeps_done = 0;
+  int total_rot = 0;
+  int status = 1;   // 1 = not converged
+  for (int sweep = 0; sweep < MAX_SWEEPS; ++sweep) {
+    int my_rot = 0;
+    for (int stage = 0; stage < nb - 1; ++stage) {
+      for (int idx = blockIdx.x; idx < npairs; idx += gridDim.x) {
+        const int ka = idx, kb = nb - 1 - idx;
+        int pa = (ka == 0) ? 0 : 1 + ((ka - 1 + stage) % (nb - 1));
+        int pb = 1 + ((kb - 1 + stage) % (nb - 1));
+        if (pa > pb) { const int s = pa; pa = pb; pb = s; }
+        cplx* gI = xp + pa * xpan;
+        cplx* gJ = xp + pb * xpan;
+        cplx* XI = gI;
+        cplx* XJ = gJ;
+        if (staged) {
+          copy_panel(sI, gI, p);
+          copy_panel(sJ, gJ, p);
+          XI = sI; XJ = sJ;
+          __syncthreads();
+        }
+        gram8(XI, XJ, p, S);
+        if (threadIdx.x < 32) eig8_warp0(S, tol2);
+        __syncthreads();
+        if (S.need) {
+          ++my_rot;
+          apply8(XI, XJ, p, S);
+          apply8(wp + pa * wpan, wp + pb * wpan, q, S);
+          if (staged) {
+            __syncthreads();
+            copy_panel(gI, sI, p);
+            copy_panel(gJ, sJ, p);
+          }
+        }
+        __syncthreads();
+      }
+      grid.sync();
+    }
+    // convergence vote: flags[sweep] counts pairs rotated in this sweep
+    if (threadIdx.x == 0 && my_rot) atomicAdd(&flags[sweep], my_rot);
+    grid.sync();
+    const int rot = *((volatile int*)&flags[sweep]);
+    total_rot += rot;
+    sweeps_done = sweep + 1;
+    if (rot == 0) { status = 0; break; }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    hdr->sweeps = sweeps_done;
+    hdr->status = status;
+    hdr->rotations = total_rot;
+  }
+}
+
+// ------------------------------------------------------------------ finalize
+// sigma_j^2 = ||X[:, j]||^2 ; one warp per panel.
+__global__ void colnorm_kernel(const cplx* __restrict__ xp, int p, int nb,
+                               double* __restrict__ sig2) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= nb) return;
+  const cplx* X = xp + (size_t)warp * p * PC;
+  double acc[PC] = {0.0, 0.0, 0.0, 0.0};
+  for (int row = lane; row < p; row += 32) {
+#pragma unroll
+    for (int c = 0; c < PC; ++c) {
+      const cplx v = X[(size_t)row * PC + c];
+      acc[c] = fma(v.x, v.x, acc[c]);
+      acc[c] = fma(v.y, v.y, acc[c]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < PC; ++c) {
+    double v = acc[c];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sig2[warp * PC + c] = v;
+  }
+}
+
+// Sort (descending), apply the tail-norm rule, publish keep.  One CTA.
+__global__ void __launch_bounds__(1024)
+rank_kernel(const double* __restrict__ sig2, int ncols, int q, int minmn,
+            double eps, double* __restrict__ sval, int* __restrict__ perm,
+            Header* __restrict__ hdr, int32_t* __restrict__ info) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  int npow = 1;
+  while (npow < ncols) npow <<= 1;
+  double* key = reinterpret_cast<double*>(dyn_smem);
+  int* idx = reinterpret_cast<int*>(key + npow);
+  for (int e = threadIdx.x; e < npow; e += blockDim.x) {
+    // padded / dummy columns sort to the end
+    key[e] = (e < q) ? sig2[e] : -1.0;
+    idx[e] = e;
+  }
+  __syncthreads();
+  // bitonic sort, descending
+  for (int k = 2; k <= npow; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int e = threadIdx.x; e < npow; e += blockDim.x) {
+        const int o = e ^ j;
+        if (o > e) {
+          const bool desc = ((e & k) == 0);
+          const double a = key[e], b = key[o];
+          const int ia = idx[e], ib = idx[o];
+          const bool a_first = (a > b) || (a == b && ia < ib);
+          if (desc ? !a_first : a_first) {
+            key[e] = b; key[o] = a;
+            idx[e] = ib; idx[o] = ia;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int e = threadIdx.x; e < q; e += blockDim.x) {
+    sval[e] = sqrt(fmax(key[e], 0.0));
+    perm[e] = idx[e];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // keep = #{ j : sqrt(sum_{i>=j} s_i^2) > eps*s_0 }, accumulated from the
+    // smallest value upwards exactly like numpy.cumsum(s[::-1]**2).
+    const int r = minmn;            // number of genuine singular values
+    int keep = r;
+    const double s0 = (r > 0) ? sqrt(fmax(key[0], 0.0)) : 0.0;
+    if (eps >= 0.0) {
+      const double thr = eps * s0;
+      double tail = 0.0;
+      keep = 0;
+      for (int j = r - 1; j >= 0; --j) {
+        const double s = sqrt(fmax(key[j], 0.0));
+        tail += s * s;
+        if (sqrt(tail) > thr) ++keep;
+      }
+    }
+    hdr->keep = keep;
+    hdr->s0 = s0;
+    info[0] = keep;
+    info[1] = hdr->sweeps;
+    info[2] = hdr->status;
+    info[3] = hdr->rotations;
+  }
+}
+
+// ------------------------------------------------------------------ emit
+__global__ void emit_kernel(const cplx* __restrict__ xp, const cplx* __restrict__ wp,
+                            const double* __restrict__ sval,
+                            const int* __restrict__ perm, int m, int n, int p, int q,
+                            int transposed, int keep, cplx* __restrict__ u, int u_na,
+                            long long u_so, long long u_sa, long long u_sj,
+                            cplx* __restrict__ svh) {
+  // element space: [0, m*keep) -> U ; [m*keep, (m+n)*keep) -> SVh
+  const long long nu = (long long)m * keep, nv = (long long)n * keep;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < nu + nv;
+       e += (long long)gridDim.x * blockDim.x) {
+    if (e < nu) {
+      if (!u) continue;
+      const int j = (int)(e % keep);
+      const int i = (int)(e / keep);
+      const int c = perm[j];
+      const size_t pan = c / PC, c4 = c % PC;
+      cplx v;
+      if (!transposed) {         // U = Y / sigma
+        v = xp[(pan * p + i) * PC + c4];
+        const double s = sval[j];
+        const double inv = (s > 0.0) ? 1.0 / s : 0.0;
+        v.x *= inv; v.y *= inv;
+      } else {                   // U = W
+        v = wp[(pan * q + i) * PC + c4];
+      }
+      u[(long long)(i / u_na) * u_so + (long long)(i % u_na) * u_sa + j * u_sj] = v;
+    } else {
+      if (!svh) continue;
+      const long long f = e - nu;
+      const int col = (int)(f % n);
+      const int j = (int)(f / n);
+      const int c = perm[j];
+      const size_t pan = c / PC, c4 = c % PC;
+      cplx v;
+      if (!transposed) {         // S Vh[j, col] = sigma_j * conj(W[col, c])
+        v = wp[(pan * q + col) * PC + c4];
+        const double s = sval[j];
+        v = make_double2(v.x * s, -v.y * s);
+      } else {                   // S Vh[j, col] = conj(Y[col, c])
+        v = xp[(pan * p + col) * PC + c4];
+        v.y = -v.y;
+      }
+      svh[(long long)j * n + col] = v;
+    }
+  }
+}
+
+}  // namespace
+
+// ============================================================================ C-ABI
+extern "C" size_t b200_svd_workspace_bytes(int m, int n) {
+  if (m <= 0 || n <= 0) return 0;
+  return make_layout(m, n).total;
+}
+
+extern "C" int b200_svd_factor(void* stream_, const void* theta, int m, int n,
+                               int64_t rs, int64_t cs, double eps, void* work,
+                               int32_t* info_host) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!theta || !work || !info_host || m <= 0 || n <= 0) {
+    b200::set_error("b200_svd_factor: invalid argument");
+    return B200_EINVAL;
+  }
+  const Layout L = make_layout(m, n);
+  if (L.nb * PC > 16384) {
+    b200::set_error("b200_svd_factor: min(m,n)=%d exceeds 16384", L.q);
+    return B200_ESIZE;
+  }
+  unsigned char* base = (unsigned char*)work;
+  Header* hdr = (Header*)(base + L.header);
+  cplx* xp = (cplx*)(base + L.xp);
+  cplx* wp = (cplx*)(base + L.wp);
+  double* sig2 = (double*)(base + L.sig2);
+  double* sval = (double*)(base + L.sval);
+  int* perm = (int*)(base + L.perm);
+  int* flags = (int*)(base + L.flags);
+
+  Header h;
+  h.m = m; h.n = n; h.p = L.p; h.q = L.q; h.npan = L.npan; h.nb = L.nb;
+  h.transposed = L.transposed; h.keep = 0; h.sweeps = 0; h.status = 1;
+  h.rotations = 0; h.pad = 0; h.eps = eps; h.s0 = 0.0;
+  B200_CUDA_CHECK(cudaMemcpyAsync(hdr, &h, sizeof(h), cudaMemcpyHostToDevice, stream));
+  B200_CUDA_CHECK(cudaMemsetAsync(flags, 0, 64 * sizeof(int), stream));
+
+  {
+    const long long total = (long long)L.nb * (L.p + L.q) * PC;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    svd_load_kernel<<<blocks, 256, 0, stream>>>((const cplx*)theta, rs, cs, m, n,
+                                                L.p, L.q, L.nb, L.transposed, xp, wp);
+    B200_LAUNCH_CHECK();
+  }
+  {
+    static int dev_sms = 0;
+    if (!dev_sms) {
+      int dev = 0;
+      B200_CUDA_CHECK(cudaGetDevice(&dev));
+      B200_CUDA_CHECK(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, dev));
+      B200_CUDA_CHECK(cudaFuncSetAttribute(
+          jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+          SMEM_STAGE_LIMIT));
+    }
+    const size_t stage_bytes = (size_t)2 * L.p * PC * sizeof(cplx);
+    int staged = stage_bytes <= (size_t)SMEM_STAGE_LIMIT ? 1 : 0;
+    size_t dyn = staged ? stage_bytes : 0;
+    int per_sm = 0;
+    B200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+        &per_sm, jacobi_kernel, JT, dyn));
+    if (per_sm < 1) {
+      b200::set_error("b200_svd_factor: Jacobi kernel cannot be resident (dyn smem %zu)", dyn);
+      return B200_ECUDA;
+    }
+    int grid = L.nb / 2;
+    const int cap = per_sm * dev_sms;
+    if (grid > cap) grid = cap;
+    int p = L.p, q = L.q, nb = L.nb;
+    const double tol = 2.0 * sqrt((double)L.p) * 2.220446049250313e-16;
+    double tol2 = tol * tol;
+    void* args[] = {&xp, &wp, &p, &q, &nb, &staged, &tol2, &flags, &hdr};
+    B200_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)jacobi_kernel, dim3(grid),
+                                                dim3(JT), args, dyn, stream));
+    b200::count_launch();
+  }
+  {
+    const int warps = L.nb;
+    const int blocks = (warps * 32 + 255) / 256;
+    colnorm_kernel<<<blocks, 256, 0, stream>>>(xp, L.p, L.nb, sig2);
+    B200_LAUNCH_CHECK();
+  }
+  {
+    static bool attr_set = false;
+    if (!attr_set) {
+      B200_CUDA_CHECK(cudaFuncSetAttribute(
+          rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 12));
+      attr_set = true;
+    }
+    const int ncols = L.nb * PC;
+    int npow = 1;
+    while (npow < ncols) npow <<= 1;
+    const size_t dyn = (size_t)npow * (sizeof(double) + sizeof(int));
+    const int minmn = (m < n) ? m : n;
+    // info is written to device-visible pinned host memory directly
+    rank_kernel<<<1, 1024, dyn, stream>>>(sig2, ncols, L.q, minmn, eps, sval, perm,
+                                          hdr, info_host);
+    B200_LAUNCH_CHECK();
+  }
+  return B200_OK;
+}
+
+extern "C" int b200_svd_emit(void* stream_, const void* work, int m, int n, int keep,
+                             void* u, int u_na, int64_t u_so, int64_t u_sa,
+                             int64_t u_sj, void* svh) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!work || m <= 0 || n <= 0 || keep < 0 || u_na < 1) {
+    b200::set_error("b200_svd_emit: invalid argument");
+    return B200_EINVAL;
+  }
+  if (keep == 0) return B200_OK;
+  const Layout L = make_layout(m, n);
+  const unsigned char* base = (const unsigned char*)work;
+  const long long total = (long long)(m + n) * keep;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  emit_kernel<<<blocks, 256, 0, stream>>>(
+      (const cplx*)(base + L.xp), (const cplx*)(base + L.wp),
+      (const double*)(base + L.sval), (const int*)(base + L.perm), m, n, L.p, L.q,
+      L.transposed, keep, (cplx*)u, u_na, u_so, u_sa, u_sj, (cplx*)svh);
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+extern "C" int b200_svd_values(void* stream_, const void* work, int m, int n,
+                               double* s_out) {
+  if (!work || !s_out || m <= 0 || n <= 0) {
+    b200::set_error("b200_svd_values: invalid argument");
+    return B200_EINVAL;
+  }
+  const Layout L = make_layout(m, n);
+  const int minmn = (m < n) ? m : n;
+  B200_CUDA_CHECK(cudaMemcpyAsync(
+      s_out, (const unsigned char*)work + L.sval, sizeof(double) * minmn,
+      cudaMemcpyDeviceToDevice, (cudaStream_t)stream_));
+  return B200_OK;
+}

@@ -1,0 +1,88 @@
+"""CPU: host-side index logic of the engine (oqupy_b200/chain.py, backends.py,
+process_tensor.py) against the oracle and the reference-generated fixtures, using
+the test-only strided-view model of the C-ABI (tests/host_model_ops.py)."""
+import numpy as np
+import pytest
+
+from conftest import golden_callables, load_golden
+from host_model_ops import HostModelOps
+from oracle import tempo_np as onp
+import oqupy_b200 as ob
+
+PT_CASES = ["pt_k12_eps7_n30", "pt_k8_eps9_n24", "pt_refA", "pt_refC"]
+TEMPO_CASES = ["tempo_c1_k20_eps7_n60", "tempo_refA", "tempo_refC",
+               "tempo_nondiag"]
+
+
+def build_pt(g, ops):
+    influence, propagators = golden_callables(g)
+    d = int(g["dim"])
+    pt = ob.DeviceProcessTensor(d, dt=float(g["dt"]), ops=ops)
+    be = ob.PtTempoBackend(d, influence, pt, np.ones(d * d), np.ones(d * d),
+                           int(g["num_steps"]), int(g["dkmax"]),
+                           float(g["epsrel"]), ops=ops)
+    be.initialize()
+    while be.compute_step():
+        pass
+    be.update_process_tensor()
+    return be, pt, propagators
+
+
+@pytest.mark.parametrize("name", PT_CASES)
+def test_pt_backend_host_logic(name):
+    g = load_golden(name)
+    ops = HostModelOps()
+    be, pt, propagators = build_pt(g, ops)
+    assert list(pt.get_bond_dimensions()) == list(g["bond_dims"])
+    states = ob.dynamics_device(pt, propagators, g["initial_state"], ops=ops)
+    np.testing.assert_allclose(states, g["states"], atol=1e-10, rtol=0)
+    np.testing.assert_allclose(pt.get_cap_tensor(0), g["cap_first"], atol=1e-10)
+
+
+def test_dynamics_ensemble_host_logic():
+    g = load_golden("pt_k12_eps7_n30")
+    ops = HostModelOps()
+    _, pt, propagators = build_pt(g, ops)
+    rng = np.random.default_rng(0)
+    p1, p2 = propagators(0)
+    e = 5
+    p1s = np.array([p1 * (1 + 0.01 * k) for k in range(e)])
+    p2s = np.array([p2] * e)
+    rho0 = np.array([g["initial_state"]] * e)
+    out = ob.dynamics_device(pt, lambda s: (p1s, p2s), rho0, ops=ops)
+    mpos = [pt.get_mpo_tensor(k) for k in range(len(pt))]
+    caps = [pt.get_cap_tensor(k) for k in range(len(pt) + 1)]
+    for k in range(e):
+        ref = onp.compute_dynamics([mpos], [caps], lambda s: (p1s[k], p2s[k]),
+                                   g["initial_state"])
+        np.testing.assert_allclose(out[k], ref, atol=1e-12, rtol=0)
+    del rng
+
+
+@pytest.mark.parametrize("name", TEMPO_CASES)
+def test_tempo_backend_host_logic(name):
+    g = load_golden(name)
+    influence, propagators = golden_callables(g)
+    d = int(g["dim"])
+    d2 = d * d
+    dkmax = None if int(g["dkmax"]) < 0 else int(g["dkmax"])
+    ops = HostModelOps()
+    be = ob.TempoBackend(g["initial_state"], influence, g["unitary"],
+                         propagators, np.ones(d2), np.ones(d2), dkmax,
+                         float(g["epsrel"]), ops=ops)
+    _, s0 = be.initialize()
+    states = [s0]
+    for _ in range(int(g["num_steps"])):
+        states.append(be.compute_step()[1])
+    states = np.array(states).reshape(-1, d, d)
+    assert be.get_bond_dimensions() == list(g["bond_dims"])
+    np.testing.assert_allclose(states, g["states"],
+                               atol=50 * float(g["epsrel"]), rtol=0)
+    np.testing.assert_allclose(states[:5], g["states"][:5], atol=1e-9, rtol=0)
+
+
+def test_unique_is_rejected_loudly():
+    with pytest.raises(NotImplementedError):
+        ob.PtTempoBackend(2, lambda k: None, None, np.ones(4), np.ones(4), 10, 5,
+                          1e-6, degeneracy_maps=[np.arange(4), np.arange(4)],
+                          ops=HostModelOps())
