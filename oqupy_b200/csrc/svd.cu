@@ -30,14 +30,16 @@ namespace {
 constexpr int PC = 4;            // columns per panel
 constexpr int JT = 512;          // threads of the Jacobi kernel
 constexpr int JW = JT / 32;      // warps
-constexpr int MAX_SWEEPS = 40;
-constexpr int INNER_SWEEPS = 3;
+constexpr int MAX_SWEEPS = 120;    // <= NFLAGS
+constexpr int NFLAGS = 128;
+constexpr int FLOOR_GROW_AFTER = 90;
+constexpr int INNER_SWEEPS = 4;    // upper bound; the inner solver stops early
 constexpr int SMEM_STAGE_LIMIT = 200 * 1024;  // bytes of panel data staged per CTA
 
 struct Header {        // lives at the start of the workspace (device)
   int m, n, p, q, npan, nb, transposed, keep;
   int sweeps, status, rotations, pad;
-  double eps, s0;
+  double eps, s0, fro2, pad2;
 };
 
 struct Layout {
@@ -62,7 +64,7 @@ __host__ Layout make_layout(int m, int n) {
   L.sig2 = off; off = align256(off + (size_t)L.nb * PC * sizeof(double));
   L.sval = off; off = align256(off + (size_t)L.nb * PC * sizeof(double));
   L.perm = off; off = align256(off + (size_t)L.nb * PC * sizeof(int));
-  L.flags = off; off = align256(off + 64 * sizeof(int));
+  L.flags = off; off = align256(off + NFLAGS * sizeof(int));
   L.total = off;
   return L;
 }
@@ -71,7 +73,8 @@ __host__ Layout make_layout(int m, int n) {
 __global__ void svd_load_kernel(const cplx* __restrict__ theta, long long rs,
                                 long long cs, int m, int n, int p, int q, int nb,
                                 int transposed, cplx* __restrict__ xp,
-                                cplx* __restrict__ wp) {
+                                cplx* __restrict__ wp, double* __restrict__ fro2) {
+  double local = 0.0;
   const long long total_x = (long long)nb * p * PC;
   const long long total_w = (long long)nb * q * PC;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -92,6 +95,8 @@ __global__ void svd_load_kernel(const cplx* __restrict__ theta, long long rs,
         }
       }
       xp[e] = v;
+      local = fma(v.x, v.x, local);
+      local = fma(v.y, v.y, local);
     } else {
       const long long f = e - total_x;
       const int c4 = (int)(f % PC);
@@ -101,6 +106,16 @@ __global__ void svd_load_kernel(const cplx* __restrict__ theta, long long rs,
       const int col = pan * PC + c4;
       wp[f] = make_double2((col == row) ? 1.0 : 0.0, 0.0);
     }
+  }
+  // ||X||_F^2: the scale of the absolute noise floor used by the convergence test
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  __shared__ double part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += part[w];
+    if (tot != 0.0) atomicAdd(fro2, tot);
   }
 }
 
@@ -151,7 +166,19 @@ __device__ void gram8(const cplx* XI, const cplx* XJ, int rows, JacobiShared& S)
 // Warp 0: decide whether the pair needs work; if so diagonalise the 8x8 Hermitian
 // Gram matrix (cyclic two-sided Jacobi, 4 disjoint rotations per round) and leave
 // the eigenvector matrix, columns sorted by DESCENDING eigenvalue, in S.sr/S.si.
-__device__ void eig8_warp0(JacobiShared& S, double tol2) {
+// A pair (i, j) counts as orthogonal when
+//   |g_ij| <= sqrt(max(a,b)) * (tol*sqrt(min(a,b)) + floor),  floor = kappa*eps*||X||_F:
+// the accumulated 8x8 rotations are accurate in the ABSOLUTE sense (eps*||X||), so
+// columns that have sunk to the rounding floor are left alone.
+__device__ __forceinline__ bool pair_converged(double a, double b, double g2,
+                                               double tol, double floor_) {
+  const double big = fmax(a, b), small = fmin(a, b);
+  if (big <= 0.0) return true;
+  const double thr = tol * sqrt(fmax(small, 0.0)) + floor_;
+  return g2 <= big * thr * thr;
+}
+
+__device__ void eig8_warp0(JacobiShared& S, double tol, double floor_) {
   const int lane = threadIdx.x;   // caller guarantees threadIdx.x < 32
   // --- convergence test on the raw Gram matrix
   double worst = 0.0;
@@ -160,7 +187,7 @@ __device__ void eig8_warp0(JacobiShared& S, double tol2) {
     if (i < j) {
       const double a = S.gr[i][i], b = S.gr[j][j];
       const double g2 = S.gr[i][j] * S.gr[i][j] + S.gi[i][j] * S.gi[i][j];
-      if (a > 0.0 && b > 0.0 && g2 > tol2 * a * b) worst = 1.0;
+      if (!pair_converged(a, b, g2, tol, floor_)) worst = 1.0;
     }
   }
   const unsigned any = __ballot_sync(0xffffffffu, worst > 0.0);
@@ -183,6 +210,7 @@ __device__ void eig8_warp0(JacobiShared& S, double tol2) {
 
   const int pr = lane >> 3, tt = lane & 7;
   for (int sweep = 0; sweep < INNER_SWEEPS; ++sweep) {
+    int rotated = 0;
     for (int round = 0; round < 7; ++round) {
       if (lane < 4) {
         // round-robin tournament on 8 players: position k -> player
@@ -194,7 +222,7 @@ __device__ void eig8_warp0(JacobiShared& S, double tol2) {
         const double xr = S.gr[i][j], xi = S.gi[i][j];
         const double mag2 = xr * xr + xi * xi;
         double c = 1.0, sr_ = 0.0, si_ = 0.0;
-        if (mag2 > 0.0 && mag2 > 1e-34 * fabs(a * b)) {
+        if (mag2 > 0.0 && !pair_converged(a, b, mag2, 1e-14, 0.25 * floor_)) {
           const double mag = sqrt(mag2);
           const double zeta = (b - a) / (2.0 * mag);
           const double tq = ((zeta >= 0.0) ? 1.0 : -1.0) /
@@ -204,6 +232,7 @@ __device__ void eig8_warp0(JacobiShared& S, double tol2) {
           // s * e^{i phi},  e^{i phi} = g_ij / |g_ij|
           sr_ = s * xr / mag;
           si_ = s * xi / mag;
+          rotated = 1;
         }
         S.rot_i[lane] = i; S.rot_j[lane] = j;
         S.rot_c[lane] = c; S.rot_sr[lane] = sr_; S.rot_si[lane] = si_;
@@ -251,6 +280,7 @@ __device__ void eig8_warp0(JacobiShared& S, double tol2) {
       }
       __syncwarp();
     }
+    if (__ballot_sync(0xffffffffu, rotated != 0) == 0u) break;
   }
   // --- sort eigenvectors by descending eigenvalue
   if (lane < 8) {
@@ -314,7 +344,7 @@ __device__ __forceinline__ void copy_panel(cplx* dst, const cplx* src, int rows)
 // ------------------------------------------------------------------ Jacobi kernel
 __global__ void __launch_bounds__(JT, 1)
 jacobi_kernel(cplx* __restrict__ xp, cplx* __restrict__ wp, int p, int q, int nb,
-              int staged, double tol2, int* __restrict__ flags,
+              int staged, double tol, int* __restrict__ flags,
               Header* __restrict__ hdr) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ JacobiShared S;
@@ -328,8 +358,14 @@ jacobi_kernel(cplx* __restrict__ xp, cplx* __restrict__ wp, int p, int q, int nb
   int sweeps_done = 0;
   int total_rot = 0;
   int status = 1;   // 1 = not converged
+  const double fro = sqrt(hdr->fro2);
   for (int sweep = 0; sweep < MAX_SWEEPS; ++sweep) {
     int my_rot = 0;
+    // absolute floor: 8 eps ||X||_F, doubled every sweep after FLOOR_GROW_AFTER so that the
+    // iteration always terminates
+    double kappa = 8.0;
+    for (int k = FLOOR_GROW_AFTER; k < sweep; ++k) kappa *= 2.0;
+    const double floor_ = kappa * 2.220446049250313e-16 * fro;
     for (int stage = 0; stage < nb - 1; ++stage) {
       for (int idx = blockIdx.x; idx < npairs; idx += gridDim.x) {
         const int ka = idx, kb = nb - 1 - idx;
@@ -347,7 +383,7 @@ jacobi_kernel(cplx* __restrict__ xp, cplx* __restrict__ wp, int p, int q, int nb
           __syncthreads();
         }
         gram8(XI, XJ, p, S);
-        if (threadIdx.x < 32) eig8_warp0(S, tol2);
+        if (threadIdx.x < 32) eig8_warp0(S, tol, floor_);
         __syncthreads();
         if (S.need) {
           ++my_rot;
@@ -549,16 +585,17 @@ extern "C" int b200_svd_factor(void* stream_, const void* theta, int m, int n,
   Header h;
   h.m = m; h.n = n; h.p = L.p; h.q = L.q; h.npan = L.npan; h.nb = L.nb;
   h.transposed = L.transposed; h.keep = 0; h.sweeps = 0; h.status = 1;
-  h.rotations = 0; h.pad = 0; h.eps = eps; h.s0 = 0.0;
+  h.rotations = 0; h.pad = 0; h.eps = eps; h.s0 = 0.0; h.fro2 = 0.0; h.pad2 = 0.0;
   B200_CUDA_CHECK(cudaMemcpyAsync(hdr, &h, sizeof(h), cudaMemcpyHostToDevice, stream));
-  B200_CUDA_CHECK(cudaMemsetAsync(flags, 0, 64 * sizeof(int), stream));
+  B200_CUDA_CHECK(cudaMemsetAsync(flags, 0, NFLAGS * sizeof(int), stream));
 
   {
     const long long total = (long long)L.nb * (L.p + L.q) * PC;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
     svd_load_kernel<<<blocks, 256, 0, stream>>>((const cplx*)theta, rs, cs, m, n,
-                                                L.p, L.q, L.nb, L.transposed, xp, wp);
+                                                L.p, L.q, L.nb, L.transposed, xp, wp,
+                                                &hdr->fro2);
     B200_LAUNCH_CHECK();
   }
   {
@@ -585,9 +622,11 @@ extern "C" int b200_svd_factor(void* stream_, const void* theta, int m, int n,
     const int cap = per_sm * dev_sms;
     if (grid > cap) grid = cap;
     int p = L.p, q = L.q, nb = L.nb;
-    const double tol = 2.0 * sqrt((double)L.p) * 2.220446049250313e-16;
-    double tol2 = tol * tol;
-    void* args[] = {&xp, &wp, &p, &q, &nb, &staged, &tol2, &flags, &hdr};
+    // relative orthogonality target |cos| <= 1e-11 (singular values are second order in
+    // it); never tighter than the rounding level of a length-p dot product
+    double tol = 2.0 * sqrt((double)L.p) * 2.220446049250313e-16;
+    if (tol < 1e-11) tol = 1e-11;
+    void* args[] = {&xp, &wp, &p, &q, &nb, &staged, &tol, &flags, &hdr};
     B200_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)jacobi_kernel, dim3(grid),
                                                 dim3(JT), args, dyn, stream));
     b200::count_launch();

@@ -1,0 +1,146 @@
+"""GPU: every C-ABI kernel against a plain torch complex128 reference of the same op."""
+import numpy as np
+import pytest
+import torch
+
+from oqupy_b200._lib import View, default_ops
+
+pytestmark = pytest.mark.gpu
+
+
+def rnd(rng, *shape):
+    return rng.normal(size=shape) + 1j * rng.normal(size=shape)
+
+
+@pytest.mark.parametrize("m,n,k", [(1, 1, 1), (5, 7, 3), (64, 64, 8), (130, 67, 45),
+                                   (257, 300, 129)])
+def test_zgemm_plain(m, n, k):
+    ops = default_ops()
+    rng = np.random.default_rng(m * 1000 + n)
+    a, b = rnd(rng, m, k), rnd(rng, k, n)
+    da, db = ops.from_host(a), ops.from_host(b)
+    c = ops.empty(m, n)
+    ops.gemm(m, n, k, View(da, row=k, col=1), View(db, row=n, col=1),
+             View(c, row=n, col=1))
+    np.testing.assert_allclose(ops.to_host(c), a @ b, atol=1e-11 * k)
+    # transposed / conjugated operands and accumulate
+    c2 = ops.from_host(np.ones((n, m)))
+    ops.gemm(n, m, k, View(db, row=1, col=n, conj=True),
+             View(da, row=1, col=k), View(c2, row=m, col=1), accumulate=True)
+    np.testing.assert_allclose(ops.to_host(c2), 1 + b.conj().T @ a.T,
+                               atol=1e-11 * k)
+
+
+def test_zgemm_zip_layout():
+    """The PT zip-up contraction: Theta[k,y,l,e] = M[e,y] sum_r C[k,r,e] A[l,y,r]."""
+    ops = default_ops()
+    rng = np.random.default_rng(5)
+    nk, nr, nl, d2 = 37, 29, 41, 4
+    carry, a, mat = rnd(rng, nk, nr, d2), rnd(rng, nl, d2, nr), rnd(rng, d2, d2)
+    dc, da, dm = ops.from_host(carry), ops.from_host(a), ops.from_host(mat)
+    theta = ops.empty(nk, d2, nl, d2)
+    ops.gemm(nk, nl, nr, View(dc, row=nr * d2, col=d2, b2=1),
+             View(da, row=1, col=d2 * nr, b1=nr),
+             View(theta, row=d2 * nl * d2, col=d2, b1=nl * d2, b2=1),
+             nb1=d2, nb2=d2, scale=View(dm, b1=1, b2=d2))
+    ref = np.einsum("ey,kre,lyr->kyle", mat, carry, a)
+    np.testing.assert_allclose(ops.to_host(theta), ref, atol=1e-10)
+
+
+def graded(rng, m, n, lo=-14.0):
+    k = min(m, n)
+    s = np.sort(10.0 ** rng.uniform(lo, 0.0, size=k))[::-1]
+    s[0] = 1.0
+    q1, _ = np.linalg.qr(rnd(rng, m, k))
+    q2, _ = np.linalg.qr(rnd(rng, n, k))
+    return (q1 * s) @ q2.conj().T, s
+
+
+def ref_keep(s, eps):
+    tail = np.sqrt(np.cumsum(np.square(s[::-1])))
+    return int(np.count_nonzero(tail > eps * s[0]))
+
+
+@pytest.mark.parametrize("m,n", [(4, 4), (4, 16), (16, 4), (3, 5), (9, 7), (33, 33),
+                                 (64, 48), (48, 130), (200, 96), (96, 200),
+                                 (260, 260), (520, 130)])
+@pytest.mark.parametrize("eps", [1e-7, None])
+def test_trunc_svd(m, n, eps):
+    ops = default_ops()
+    rng = np.random.default_rng(m * 7919 + n)
+    mat, _ = graded(rng, m, n)
+    dm = ops.from_host(mat)
+    h = ops.svd_factor(dm, m, n, n, 1, eps)
+    s_ref = np.linalg.svd(mat, compute_uv=False)
+    s = ops.svd_values(h)
+    # absolute accuracy relative to s0 (what the truncation rule needs)
+    np.testing.assert_allclose(s, s_ref, atol=2e-13 * s_ref[0], rtol=1e-9)
+    k = h.keep
+    assert k == (min(m, n) if eps is None else ref_keep(s_ref, eps))
+    u, svh = ops.empty(m, k), ops.empty(k, n)
+    ops.svd_emit(h, u=u, u_na=1, u_so=k, u_sj=1, svh=svh)
+    u, svh = ops.to_host(u), ops.to_host(svh)
+    # kept columns with sigma ~ eps*s0 are orthogonal to the rest only down to the
+    # absolute rounding floor (~1e-14 s0), i.e. to ~1e-14/sigma relative
+    otol = 1e-12 if eps is None else 1e-5
+    if eps is not None:
+        np.testing.assert_allclose(u.conj().T @ u, np.eye(k), atol=otol)
+    ur, sr, vhr = np.linalg.svd(mat, full_matrices=False)
+    best = (ur[:, :k] * sr[:k]) @ vhr[:k]
+    np.testing.assert_allclose(u @ svh, best, atol=2e-13)
+    # rows of S Vh are orthogonal with norms s
+    g = svh @ svh.conj().T
+    np.testing.assert_allclose(g, np.diag(s[:k] ** 2), atol=1e-12)
+
+
+def test_trunc_svd_strided_and_emit_layout():
+    """Transposed input view and the (j, y, k) site layout used by the PT zip-up."""
+    ops = default_ops()
+    rng = np.random.default_rng(11)
+    nk, ny, n = 13, 4, 40
+    mat, _ = graded(rng, nk * ny, n, lo=-9.0)
+    dt = ops.from_host(np.ascontiguousarray(mat.T))      # stored transposed
+    h = ops.svd_factor(dt, nk * ny, n, 1, nk * ny, 1e-6)
+    k = h.keep
+    site, svh = ops.empty(k, ny, nk), ops.empty(k, n)
+    ops.svd_emit(h, u=site, u_na=ny, u_so=1, u_sa=nk, u_sj=ny * nk, svh=svh)
+    site, svh = ops.to_host(site), ops.to_host(svh)
+    u = site.transpose(2, 1, 0).reshape(nk * ny, k)
+    ur, sr, vhr = np.linalg.svd(mat, full_matrices=False)
+    np.testing.assert_allclose(u @ svh, (ur[:, :k] * sr[:k]) @ vhr[:k], atol=1e-12)
+
+
+def test_trunc_svd_rank_deficient_and_zero_columns():
+    ops = default_ops()
+    rng = np.random.default_rng(2)
+    a = rnd(rng, 60, 5) @ rnd(rng, 5, 44)          # exact rank 5
+    a[:, 7] = 0.0
+    h = ops.svd_factor(ops.from_host(a), 60, 44, 44, 1, 1e-9)
+    assert h.keep == 5
+    s = ops.svd_values(h)
+    np.testing.assert_allclose(s[:5], np.linalg.svd(a, compute_uv=False)[:5],
+                               rtol=1e-12)
+
+
+def test_dyn_and_caps():
+    ops = default_ops()
+    rng = np.random.default_rng(8)
+    for nvec, cl, cr, d2 in [(1, 1, 4, 4), (1, 57, 63, 4), (6, 130, 90, 4),
+                             (3, 20, 33, 9)]:
+        t, v = rnd(rng, cl, cr, d2), rnd(rng, nvec, cl, d2)
+        p1, p2 = rnd(rng, nvec, d2, d2), rnd(rng, nvec, d2, d2)
+        cap, capn, tr2 = rnd(rng, cl), rnd(rng, cr), rnd(rng, d2)
+        dv_out, drho, dcap = ops.empty(nvec, cr, d2), ops.empty(nvec, d2), ops.empty(cl)
+        dt = ops.from_host(t)
+        ops.dyn_step(nvec, cl, cr, d2, dt, ops.from_host(p1), ops.from_host(p2),
+                     ops.from_host(v), dv_out, cap=ops.from_host(cap), rho_out=drho)
+        u = np.einsum("exi,eli->elx", p1, v)
+        w = np.einsum("lrx,elx->erx", t, u)
+        np.testing.assert_allclose(ops.to_host(dv_out),
+                                   np.einsum("ejx,erx->erj", p2, w), atol=1e-10)
+        np.testing.assert_allclose(ops.to_host(drho),
+                                   np.einsum("l,eli->ei", cap, v), atol=1e-11)
+        ops.caps_step(cl, cr, d2, dt, ops.from_host(capn), ops.from_host(tr2), dcap)
+        np.testing.assert_allclose(ops.to_host(dcap),
+                                   np.einsum("lrx,r,x->l", t, capn, tr2), atol=1e-10)
+    assert ops.launch_count() > 0
