@@ -1,0 +1,330 @@
+"""bench.py -- PT-TEMPO steps/s at (dkmax=200, epsrel=1e-9) on B200 (BASELINE.json metric).
+
+A "step" is one ``PtTempoBackend.compute_step`` (one column of the PT-TEMPO network:
+201 influence-MPO x MPS site contractions + 201 truncated SVDs in the zip-up, then
+the truncated-SVD sweep) of BASELINE.json configs[1]: spin-boson process tensor,
+ohmic alpha=0.08, wc=4, T=1.6, dt=0.05, dkmax=200, epsrel=1e-9, N=1000.  A run is
+time-sequential: W warm-up steps follow ``initialize()``, then EXACTLY K steps are
+timed (steps W+2 .. W+K+1 of the build; bond dimensions keep growing in that window).
+Inputs are the reference's own influence matrices (tests/golden/c2_operands.npz).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N > 1 (torchrun): one process per GPU, each builds an independent ensemble member
+(coupling alpha_r = 0.08*(1+0.05 r)); no data-path collective ("weak" scaling), NCCL
+only gathers the per-rank bond dimensions after the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = ("spin-boson PT-TEMPO process tensor build, ohmic alpha=0.08 wc=4 T=1.6, "
+            "dt=0.05, dkmax=200, epsrel=1e-9, N=1000 (BASELINE configs[1])")
+
+
+def load_operands(rank=0):
+    with np.load(os.path.join(ROOT, "tests", "golden", "c2_operands.npz")) as f:
+        g = {k: f[k] for k in f.files}
+    infl = g["influences"]
+    if rank:
+        # influence = exp(-(eta ...)) with eta proportional to alpha: another coupling
+        # strength is an element-wise power of the fixture (tempo.py:1008-1015)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            infl = np.where(infl == 0, 0, np.exp(np.log(infl) * (1.0 + 0.05 * rank)))
+    return g, infl
+
+
+def influence_fn(infl):
+    def influence(dk):
+        return None if dk < 0 else infl[dk]
+    return influence
+
+
+# ------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.samples, self.proc, self.thread, self.index = [], None, None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi missing"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                 "sw_power_cap"]
+        for s in self.samples:
+            if len(s) < 7:
+                continue
+            try:
+                sm.append(float(s[0]))
+                smax.append(float(s[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, s[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ CPU arm (oracle)
+def run_cpu(steps, warmup, budget_s, infl):
+    """The oracle port (numpy/LAPACK restatement of the reference path) on the host
+    cores: same step window; stops early when the time budget is exhausted."""
+    from oracle import tempo_np as onp
+    pt = onp.PtTempoOracle(2, influence_fn(infl), 1000, 200, 1e-9)
+    pt.initialize()
+    for _ in range(warmup):
+        pt.compute_step()
+    done, t0 = 0, time.perf_counter()
+    for _ in range(steps):
+        pt.compute_step()
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return done, dt, pt.bond_dimensions()
+
+
+def host_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+        return int(n)
+    except Exception:  # pylint: disable=broad-except
+        return os.cpu_count() or 1
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    _, infl = load_operands(0)
+    done, dt, _ = run_cpu(args.steps, args.warmup, args.cpu_budget, infl)
+    val = done / dt
+    cores = host_threads()
+    sample = (f"oracle port (numpy/LAPACK gesdd restatement of the reference path), "
+              f"steps {args.warmup + 2}..{args.warmup + 1 + done} of the same build "
+              f"({done} of {args.steps} requested, {dt:.1f} s)")
+    line = {
+        "impl": "reference", "metric": "PT-TEMPO steps/s at dkmax=200, epsrel=1e-9",
+        "value": val, "unit": "steps/s", "n_gpus": args.gpus, "steps": done,
+        "warmup": args.warmup, "ms_per_step": 1e3 / val, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "timed_steps":
+                   [args.warmup + 2, args.warmup + 1 + done]},
+        "cpu_baseline": {"value": val, "unit": "steps/s", "cores": cores,
+                         "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ GPU arm
+def fp64_gemm_peak(torch, device):
+    """cuBLAS DGEMM 4096^3 burst, the FP64 (DMMA) denominator: MEASURED_PEAKS.json has
+    no fp64 entry (SURVEY 8d asks to measure it on the box)."""
+    n = 4096
+    a = torch.randn(n, n, dtype=torch.float64, device=device)
+    b = torch.randn(n, n, dtype=torch.float64, device=device)
+    torch.matmul(a, b)
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(5):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import oqupy_b200 as ob
+    from oqupy_b200._lib import CudaOps
+    ops = CudaOps(local)
+    dev = ops.device
+    _, infl = load_operands(rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    be = ob.PtTempoBackend(2, influence_fn(infl), None, np.ones(4), np.ones(4),
+                           1000, 200, 1e-9, ops=ops)
+    be.initialize()
+    for _ in range(args.warmup):
+        be.compute_step()
+    ops.profile_enable(True)
+    ops.profile_read()
+    ops.svd_log = []
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0, h0, d0 = ops.launch_count(), ops.h2d_bytes, ops.d2h_bytes
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        be.compute_step()
+    e1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ops.launch_count() - l0
+    h2d, d2h = ops.h2d_bytes - h0, ops.d2h_bytes - d0
+    k_ms, k_flops, k_launches, k_sweeps = ops.profile_read()
+    ops.profile_enable(False)
+    svd_log = ops.svd_log
+    ops.svd_log = None
+
+    t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([launches], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        # the only collective of the design: gather per-member results (NCCL)
+        bonds = torch.zeros(1024, dtype=torch.int64, device=dev)
+        b = be.get_bond_dimensions()
+        bonds[:len(b)] = torch.tensor(b, device=dev)
+        gathered = [torch.zeros_like(bonds) for _ in range(world)]
+        dist.all_gather(gathered, bonds)
+    dev_ms, wall_ms = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak = fp64_gemm_peak(torch, dev)
+    value = world * args.steps / (dev_ms * 1e-3)
+    e2e = world * args.steps / (wall_ms * 1e-3)
+    achieved = k_flops / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_jacobi_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    big = max(svd_log, key=lambda x: x[0] * x[1]) if svd_log else None
+
+    # bounded CPU baseline on this box's host cores (oracle port), same step window
+    cdone, cdt, _ = run_cpu(args.steps, args.warmup, args.cpu_budget,
+                            load_operands(0)[1]) if not args.no_cpu else (0, 1.0, None)
+    cpu_val = cdone / cdt if cdone else None
+
+    line = {
+        "metric": "PT-TEMPO steps/s at dkmax=200, epsrel=1e-9",
+        "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "c128", "data": "synthetic",
+        "config": {
+            "workload": WORKLOAD,
+            "timed_steps": [args.warmup + 2, args.warmup + 1 + args.steps],
+            "parallelism": f"{world} independent ensemble members, one per GPU",
+            "l2": ("time-sequential build: every SVD operand is new data produced by "
+                   "the previous kernel; no repeated iteration, no L2 flush needed"),
+            "largest_svd": None if big is None else [big[0], big[1], big[2]],
+            "svds_per_step": len(svd_log) / args.steps if svd_log else None,
+        },
+        "e2e": {"value": e2e, "unit": "steps/s",
+                "h2d_bytes_per_step": h2d / args.steps,
+                "d2h_bytes_per_step": d2h / args.steps,
+                "note": ("wall clock around PtTempoBackend.compute_step() (public "
+                         "API): host influence callback + H2D of its operands and "
+                         "the per-bond rank read-back (D2H) happen inside every step")},
+        "gpu_launches": int(cnt[0]),
+        "clocks": clocks,
+        "roofline": {
+            "kernel": "jacobi_kernel (block-Jacobi truncated SVD, fp64 DMMA)",
+            "bound": "tensor", "achieved": achieved, "peak": peak,
+            "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+            "traffic": traffic,
+            "peak_source": ("fp64 cuBLAS DGEMM 4096^3 measured in this run "
+                            "(MEASURED_PEAKS.json carries no fp64 figure)"),
+            "kernel_ms": k_ms, "kernel_share_of_step": k_ms / dev_ms,
+            "launches": int(k_launches), "jacobi_sweeps": int(k_sweeps),
+            "algorithmic_flops": k_flops,
+        },
+        "cpu_baseline": None if cpu_val is None else {
+            "value": cpu_val, "unit": "steps/s", "cores": host_threads(),
+            "kind": "port",
+            "sample": (f"oracle port (numpy/LAPACK), steps {args.warmup + 2}.."
+                       f"{args.warmup + 1 + cdone} of the same build, {cdt:.1f} s")},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--cpu-budget", type=float, default=30.0,
+                    help="seconds of host time for the CPU baseline sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        if args.cpu_budget == 30.0:
+            args.cpu_budget = 150.0
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

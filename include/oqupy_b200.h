@@ -30,6 +30,16 @@ int b200_abi_version(void);
 /* number of kernel launches issued through this library since load */
 uint64_t b200_launch_count(void);
 
+/* Live per-kernel timing for the roofline report (bench.py): when enabled, every
+ * launch of the dominant kernel (the block-Jacobi SVD sweep kernel) is bracketed by
+ * CUDA events on its own stream.  b200_profile_read synchronises the device, adds
+ * up the finished launches and returns: total kernel milliseconds, total
+ * ALGORITHMIC flops (4*(14 m n^2 + 8 n^3), m >= n, per truncated SVD),
+ * number of launches and total Jacobi sweeps; then resets the counters. */
+int b200_profile_enable(int on);
+int b200_profile_read(double* kernel_ms, double* algorithmic_flops,
+                      uint64_t* launches, uint64_t* sweeps);
+
 /* ---------------------------------------------------------------------------
  * Strided, doubly-batched complex GEMM with per-batch scale:
  *   C[b1,b2][i,j] = scale[b1,b2] * sum_t opA(A[b1,b2])[i,t] * opB(B[b1,b2])[t,j]
@@ -69,7 +79,9 @@ int b200_zgemm_strided(void* stream, int m, int n, int k, int nb1, int nb2,
  *
  * b200_svd_emit: writes U (m x keep) with the row index i split as
  *   (i / u_na, i % u_na) -> address (i/u_na)*u_so + (i%u_na)*u_sa + j*u_sj, and
- *   S*Vh (keep x n) row-major into svh.  Either output may be NULL.
+ *   S*Vh (keep x n) row-major into svh.  Either output may be NULL.  `theta`, rs, cs
+ *   are the same matrix as given to b200_svd_factor (reserved; the right factor is
+ *   taken from the accumulated rotations, so theta may already have been reused).
  *
  * b200_svd_values: copies the min(m,n) sorted singular values (doubles) to s_out.
  *
@@ -81,9 +93,9 @@ int b200_zgemm_strided(void* stream, int m, int n, int k, int nb1, int nb2,
 size_t b200_svd_workspace_bytes(int m, int n);
 int b200_svd_factor(void* stream, const void* theta, int m, int n, int64_t rs,
                     int64_t cs, double eps, void* work, int32_t* info_host);
-int b200_svd_emit(void* stream, const void* work, int m, int n, int keep,
-                  void* u, int u_na, int64_t u_so, int64_t u_sa, int64_t u_sj,
-                  void* svh);
+int b200_svd_emit(void* stream, const void* work, const void* theta, int m, int n,
+                  int64_t rs, int64_t cs, int keep, void* u, int u_na, int64_t u_so,
+                  int64_t u_sa, int64_t u_sj, void* svh);
 int b200_svd_values(void* stream, const void* work, int m, int n, double* s_out);
 
 /* ---------------------------------------------------------------------------

@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "liboqupy_b200.so")
 
 EXPORTS = [
     "b200_last_error", "b200_abi_version", "b200_launch_count",
+    "b200_profile_enable", "b200_profile_read",
     "b200_zgemm_strided", "b200_svd_workspace_bytes", "b200_svd_factor",
     "b200_svd_emit", "b200_svd_values", "b200_dyn_workspace_bytes",
     "b200_dyn_step", "b200_caps_step",
@@ -47,6 +48,11 @@ def load_library():
     lib.b200_last_error.restype = c_char_p
     lib.b200_abi_version.restype = c_int
     lib.b200_launch_count.restype = c_uint64
+    lib.b200_profile_enable.restype = c_int
+    lib.b200_profile_enable.argtypes = [c_int]
+    lib.b200_profile_read.restype = c_int
+    lib.b200_profile_read.argtypes = [POINTER(c_double), POINTER(c_double),
+                                      POINTER(c_uint64), POINTER(c_uint64)]
     lib.b200_zgemm_strided.restype = c_int
     lib.b200_zgemm_strided.argtypes = [
         c_void_p, c_int, c_int, c_int, c_int, c_int, POINTER(_Operand),
@@ -58,9 +64,9 @@ def load_library():
     lib.b200_svd_factor.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int64,
                                     c_int64, c_double, c_void_p, c_void_p]
     lib.b200_svd_emit.restype = c_int
-    lib.b200_svd_emit.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int,
-                                  c_void_p, c_int, c_int64, c_int64, c_int64,
-                                  c_void_p]
+    lib.b200_svd_emit.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                  c_int64, c_int64, c_int, c_void_p, c_int,
+                                  c_int64, c_int64, c_int64, c_void_p]
     lib.b200_svd_values.restype = c_int
     lib.b200_svd_values.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p]
     lib.b200_dyn_workspace_bytes.restype = c_size_t
@@ -86,7 +92,8 @@ class View:
 
 class SvdHandle:
     """Result of svd_factor: keeps the device workspace alive until emit."""
-    __slots__ = ("work", "m", "n", "keep", "sweeps", "status", "rotations")
+    __slots__ = ("work", "m", "n", "keep", "sweeps", "status", "rotations",
+                 "theta", "theta_ptr", "rs", "cs")
 
 
 class CudaOps:
@@ -105,6 +112,8 @@ class CudaOps:
         self._work = None
         self.one = torch.ones(1, dtype=torch.complex128, device=self.device)
         self.svd_log = None       # optional list: (m, n, keep, sweeps)
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
 
     # -- memory ---------------------------------------------------------------
     def empty(self, *shape):
@@ -112,9 +121,11 @@ class CudaOps:
 
     def from_host(self, array):
         a = np.ascontiguousarray(np.asarray(array, dtype=np.complex128))
+        self.h2d_bytes += a.nbytes
         return torch.from_numpy(a).to(self.device)
 
     def to_host(self, tensor):
+        self.d2h_bytes += tensor.numel() * tensor.element_size()
         return tensor.cpu().numpy()
 
     def _stream(self):
@@ -156,7 +167,9 @@ class CudaOps:
         torch.cuda.current_stream(self.device).synchronize()
         h = SvdHandle()
         h.work, h.m, h.n = work, m, n
+        h.theta, h.theta_ptr, h.rs, h.cs = theta, self._ptr(theta, off), rs, cs
         h.keep, h.sweeps, h.status, h.rotations = (int(x) for x in self._info_np)
+        self.d2h_bytes += 16
         if h.status != 0:
             raise B200Error(f"Jacobi SVD did not converge ({m}x{n}, "
                             f"{h.sweeps} sweeps)")
@@ -166,8 +179,8 @@ class CudaOps:
 
     def svd_emit(self, h, u=None, u_na=1, u_so=0, u_sa=0, u_sj=0, svh=None):
         code = self.lib.b200_svd_emit(
-            self._stream(), h.work.data_ptr(), h.m, h.n, h.keep,
-            None if u is None else u.data_ptr(), u_na, u_so, u_sa, u_sj,
+            self._stream(), h.work.data_ptr(), h.theta_ptr, h.m, h.n, h.rs, h.cs,
+            h.keep, None if u is None else u.data_ptr(), u_na, u_so, u_sa, u_sj,
             None if svh is None else svh.data_ptr())
         self._check(code, "b200_svd_emit")
 
@@ -201,6 +214,18 @@ class CudaOps:
 
     def launch_count(self):
         return int(self.lib.b200_launch_count())
+
+    def profile_enable(self, on=True):
+        self.lib.b200_profile_enable(1 if on else 0)
+
+    def profile_read(self):
+        """(kernel_ms, algorithmic_flops, launches, sweeps) of the SVD sweep kernel."""
+        ms, fl = c_double(0.0), c_double(0.0)
+        n, sw = c_uint64(0), c_uint64(0)
+        self._check(self.lib.b200_profile_read(ctypes.byref(ms), ctypes.byref(fl),
+                                               ctypes.byref(n), ctypes.byref(sw)),
+                    "b200_profile_read")
+        return ms.value, fl.value, n.value, sw.value
 
     def synchronize(self):
         torch.cuda.synchronize(self.device)

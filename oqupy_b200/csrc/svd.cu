@@ -33,17 +33,19 @@ constexpr int JW = JT / 32;      // warps
 constexpr int MAX_SWEEPS = 120;    // <= NFLAGS
 constexpr int NFLAGS = 128;
 constexpr int FLOOR_GROW_AFTER = 90;
-constexpr int INNER_SWEEPS = 4;    // upper bound; the inner solver stops early
+constexpr int INNER_SWEEPS = 3;    // upper bound; the inner solver stops early
 constexpr int SMEM_STAGE_LIMIT = 200 * 1024;  // bytes of panel data staged per CTA
 
 struct Header {        // lives at the start of the workspace (device)
   int m, n, p, q, npan, nb, transposed, keep;
   int sweeps, status, rotations, pad;
   double eps, s0, fro2, pad2;
+  const void* theta;          // original matrix (needed by emit when W is not kept)
+  long long rs, cs;
 };
 
 struct Layout {
-  size_t header, xp, wp, sig2, sval, perm, flags, total;
+  size_t header, xp, wp, ucont, sig2, sval, perm, flags, total;
   int p, q, npan, nb, transposed;
 };
 
@@ -60,7 +62,11 @@ __host__ Layout make_layout(int m, int n) {
   size_t off = 0;
   L.header = off; off = align256(off + sizeof(Header));
   L.xp = off;   off = align256(off + (size_t)L.nb * L.p * PC * sizeof(cplx));
+  // W accumulates the right rotations.  (Forming S*Vh as U^H*theta instead is NOT an
+  // option: columns of U are orthogonal only down to the absolute rounding floor, and
+  // the projection would amplify that by sigma_0/sigma_j.)
   L.wp = off;   off = align256(off + (size_t)L.nb * L.q * PC * sizeof(cplx));
+  L.ucont = off;
   L.sig2 = off; off = align256(off + (size_t)L.nb * PC * sizeof(double));
   L.sval = off; off = align256(off + (size_t)L.nb * PC * sizeof(double));
   L.perm = off; off = align256(off + (size_t)L.nb * PC * sizeof(int));
@@ -76,7 +82,7 @@ __global__ void svd_load_kernel(const cplx* __restrict__ theta, long long rs,
                                 cplx* __restrict__ wp, double* __restrict__ fro2) {
   double local = 0.0;
   const long long total_x = (long long)nb * p * PC;
-  const long long total_w = (long long)nb * q * PC;
+  const long long total_w = wp ? (long long)nb * q * PC : 0;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
        e < total_x + total_w; e += (long long)gridDim.x * blockDim.x) {
     if (e < total_x) {
@@ -123,11 +129,11 @@ __global__ void svd_load_kernel(const cplx* __restrict__ theta, long long rs,
 // Shared scratch of the Jacobi kernel (static part).
 struct JacobiShared {
   double red[JW][128];   // per-warp partial Gram fragments (re: 0..63, im: 64..127)
-  double gr[8][8], gi[8][8];   // Gram / working Hermitian matrix
-  double vr[8][8], vi[8][8];   // accumulated eigenvectors
+  double gr[2][8][8], gi[2][8][8];   // Gram / working Hermitian matrix (double-buffered)
+  double vr[2][8][8], vi[2][8][8];   // accumulated eigenvectors (double-buffered)
   double sr[8][8], si[8][8];   // sorted eigenvectors (the 8x8 rotation to apply)
-  double rot_c[4], rot_sr[4], rot_si[4];
-  int rot_i[4], rot_j[4];
+  double al[8], ber[8], bei[8];      // per index: alpha (real), beta (complex)
+  int partner[8], rot[8];
   int need;                    // pair needs a rotation
 };
 
@@ -157,8 +163,8 @@ __device__ void gram8(const cplx* XI, const cplx* XJ, int rows, JacobiShared& S)
 #pragma unroll
     for (int w = 0; w < JW; ++w) acc += S.red[w][threadIdx.x];
     const int e = threadIdx.x & 63;
-    if (threadIdx.x < 64) S.gr[e >> 3][e & 7] = acc;
-    else S.gi[e >> 3][e & 7] = acc;
+    if (threadIdx.x < 64) S.gr[0][e >> 3][e & 7] = acc;
+    else S.gi[0][e >> 3][e & 7] = acc;
   }
   __syncthreads();
 }
@@ -185,8 +191,8 @@ __device__ void eig8_warp0(JacobiShared& S, double tol, double floor_) {
   for (int e = lane; e < 64; e += 32) {
     const int i = e >> 3, j = e & 7;
     if (i < j) {
-      const double a = S.gr[i][i], b = S.gr[j][j];
-      const double g2 = S.gr[i][j] * S.gr[i][j] + S.gi[i][j] * S.gi[i][j];
+      const double a = S.gr[0][i][i], b = S.gr[0][j][j];
+      const double g2 = S.gr[0][i][j] * S.gr[0][i][j] + S.gi[0][i][j] * S.gi[0][i][j];
       if (!pair_converged(a, b, g2, tol, floor_)) worst = 1.0;
     }
   }
@@ -194,107 +200,107 @@ __device__ void eig8_warp0(JacobiShared& S, double tol, double floor_) {
   if (lane == 0) S.need = any ? 1 : 0;
   if (!any) { __syncwarp(); return; }
 
-  // symmetrise exactly + V = I
+  // exact Hermitian symmetry + V = I   (buffer 0)
   for (int e = lane; e < 64; e += 32) {
     const int i = e >> 3, j = e & 7;
-    S.vr[i][j] = (i == j) ? 1.0 : 0.0;
-    S.vi[i][j] = 0.0;
+    S.vr[0][i][j] = (i == j) ? 1.0 : 0.0;
+    S.vi[0][i][j] = 0.0;
   }
   __syncwarp();
   for (int e = lane; e < 64; e += 32) {
     const int i = e >> 3, j = e & 7;
-    if (i > j) { S.gr[i][j] = S.gr[j][i]; S.gi[i][j] = -S.gi[j][i]; }
-    if (i == j) S.gi[i][j] = 0.0;
+    if (i > j) { S.gr[0][i][j] = S.gr[0][j][i]; S.gi[0][i][j] = -S.gi[0][j][i]; }
+    if (i == j) S.gi[0][i][j] = 0.0;
   }
   __syncwarp();
 
-  const int pr = lane >> 3, tt = lane & 7;
+  // Cyclic two-sided Jacobi, 4 disjoint rotations per round, all 64 entries of
+  // G' = R^H G R and V' = V R recomputed in ONE pass from the previous buffer
+  // (double buffering: two __syncwarp per round).  With pi(x) the partner of index x:
+  //   column op  T(x,y)  = al_y G[x][y] + be_y G[x][pi y]
+  //   row op     G'[x][y] = al_x T(x,y) + conj(be_x) T(pi x, y)
+  // where (al, be) = (c, -conj(se)) for the first index of a pair, (c, se) for the
+  // second, R = [[c, se], [-conj(se), c]].
+  int cur = 0;
   for (int sweep = 0; sweep < INNER_SWEEPS; ++sweep) {
     int rotated = 0;
     for (int round = 0; round < 7; ++round) {
       if (lane < 4) {
-        // round-robin tournament on 8 players: position k -> player
         const int ka = lane, kb = 7 - lane;
         int i = (ka == 0) ? 0 : 1 + ((ka - 1 + round) % 7);
         int j = 1 + ((kb - 1 + round) % 7);
-        if (i > j) { const int s = i; i = j; j = s; }
-        const double a = S.gr[i][i], b = S.gr[j][j];
-        const double xr = S.gr[i][j], xi = S.gi[i][j];
+        if (i > j) { const int t = i; i = j; j = t; }
+        const double a = S.gr[cur][i][i], b = S.gr[cur][j][j];
+        const double xr = S.gr[cur][i][j], xi = S.gi[cur][i][j];
         const double mag2 = xr * xr + xi * xi;
         double c = 1.0, sr_ = 0.0, si_ = 0.0;
+        int rot = 0;
         if (mag2 > 0.0 && !pair_converged(a, b, mag2, 1e-14, 0.25 * floor_)) {
-          const double mag = sqrt(mag2);
-          const double zeta = (b - a) / (2.0 * mag);
-          const double tq = ((zeta >= 0.0) ? 1.0 : -1.0) /
-                            (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-          c = 1.0 / sqrt(1.0 + tq * tq);
-          const double s = tq * c;
-          // s * e^{i phi},  e^{i phi} = g_ij / |g_ij|
-          sr_ = s * xr / mag;
-          si_ = s * xi / mag;
+          // cos(2t) = |h|/r, c = sqrt((1+cos 2t)/2), s e^{i phi} = sign(h) g/(2 r c)
+          const double h = 0.5 * (b - a);
+          const double inv_r = rsqrt(h * h + mag2);
+          c = sqrt(0.5 + 0.5 * fabs(h) * inv_r);
+          const double k = ((h >= 0.0) ? 0.5 : -0.5) * inv_r / c;
+          sr_ = xr * k;
+          si_ = xi * k;
+          rot = 1;
           rotated = 1;
         }
-        S.rot_i[lane] = i; S.rot_j[lane] = j;
-        S.rot_c[lane] = c; S.rot_sr[lane] = sr_; S.rot_si[lane] = si_;
+        S.partner[i] = j; S.partner[j] = i;
+        S.al[i] = c; S.al[j] = c;
+        S.ber[i] = -sr_; S.bei[i] = si_;     // -conj(se)
+        S.ber[j] = sr_;  S.bei[j] = si_;     //  se
+        S.rot[i] = rot; S.rot[j] = rot;
       }
       __syncwarp();
-      const int i = S.rot_i[pr], j = S.rot_j[pr];
-      const double c = S.rot_c[pr], sr_ = S.rot_sr[pr], si_ = S.rot_si[pr];
-      // R = [[c, s e^{i phi}], [-s e^{-i phi}, c]] on columns (i, j)
-      {  // G <- G R   (row tt)
-        const double air = S.gr[tt][i], aii = S.gi[tt][i];
-        const double ajr = S.gr[tt][j], aji = S.gi[tt][j];
-        // new_i = c*a_i - conj(se)*a_j ; conj(se) = (sr_, -si_)
-        S.gr[tt][i] = c * air - (sr_ * ajr + si_ * aji);
-        S.gi[tt][i] = c * aii - (sr_ * aji - si_ * ajr);
-        // new_j = se*a_i + c*a_j
-        S.gr[tt][j] = (sr_ * air - si_ * aii) + c * ajr;
-        S.gi[tt][j] = (sr_ * aii + si_ * air) + c * aji;
-        // V <- V R
-        const double vir = S.vr[tt][i], vii = S.vi[tt][i];
-        const double vjr = S.vr[tt][j], vji = S.vi[tt][j];
-        S.vr[tt][i] = c * vir - (sr_ * vjr + si_ * vji);
-        S.vi[tt][i] = c * vii - (sr_ * vji - si_ * vjr);
-        S.vr[tt][j] = (sr_ * vir - si_ * vii) + c * vjr;
-        S.vi[tt][j] = (sr_ * vii + si_ * vir) + c * vji;
+      const int nxt = cur ^ 1;
+#pragma unroll
+      for (int rep = 0; rep < 2; ++rep) {
+        const int e = lane + 32 * rep;
+        const int x = e >> 3, y = e & 7;
+        const int px = S.partner[x], py = S.partner[y];
+        const double aly = S.al[y], byr = S.ber[y], byi = S.bei[y];
+        const double alx = S.al[x], bxr = S.ber[x], bxi = -S.bei[x];   // conj(be_x)
+        // T(x,y)
+        const double g00r = S.gr[cur][x][y], g00i = S.gi[cur][x][y];
+        const double g01r = S.gr[cur][x][py], g01i = S.gi[cur][x][py];
+        const double t0r = aly * g00r + (byr * g01r - byi * g01i);
+        const double t0i = aly * g00i + (byr * g01i + byi * g01r);
+        // T(pi x, y)
+        const double g10r = S.gr[cur][px][y], g10i = S.gi[cur][px][y];
+        const double g11r = S.gr[cur][px][py], g11i = S.gi[cur][px][py];
+        const double t1r = aly * g10r + (byr * g11r - byi * g11i);
+        const double t1i = aly * g10i + (byr * g11i + byi * g11r);
+        double nr = alx * t0r + (bxr * t1r - bxi * t1i);
+        double ni = alx * t0i + (bxr * t1i + bxi * t1r);
+        if (x == y) ni = 0.0;
+        if (y == px && S.rot[x]) { nr = 0.0; ni = 0.0; }   // annihilated entry
+        S.gr[nxt][x][y] = nr;
+        S.gi[nxt][x][y] = ni;
+        // V' = V R
+        const double v0r = S.vr[cur][x][y], v0i = S.vi[cur][x][y];
+        const double v1r = S.vr[cur][x][py], v1i = S.vi[cur][x][py];
+        S.vr[nxt][x][y] = aly * v0r + (byr * v1r - byi * v1i);
+        S.vi[nxt][x][y] = aly * v0i + (byr * v1i + byi * v1r);
       }
       __syncwarp();
-      {  // G <- R^H G  (column tt):  R^H = [[c, -s e^{i phi}], [s e^{-i phi}, c]]
-        const double air = S.gr[i][tt], aii = S.gi[i][tt];
-        const double ajr = S.gr[j][tt], aji = S.gi[j][tt];
-        // new_i = c*a_i - se*a_j
-        S.gr[i][tt] = c * air - (sr_ * ajr - si_ * aji);
-        S.gi[i][tt] = c * aii - (sr_ * aji + si_ * ajr);
-        // new_j = conj(se)*a_i + c*a_j
-        S.gr[j][tt] = (sr_ * air + si_ * aii) + c * ajr;
-        S.gi[j][tt] = (sr_ * aii - si_ * air) + c * aji;
-      }
-      __syncwarp();
-      if (lane < 4) {   // clean the annihilated entries
-        const int ii = S.rot_i[lane], jj = S.rot_j[lane];
-        if (S.rot_sr[lane] != 0.0 || S.rot_si[lane] != 0.0) {
-          S.gr[ii][jj] = 0.0; S.gi[ii][jj] = 0.0;
-          S.gr[jj][ii] = 0.0; S.gi[jj][ii] = 0.0;
-        }
-        S.gi[ii][ii] = 0.0; S.gi[jj][jj] = 0.0;
-      }
-      __syncwarp();
+      cur = nxt;
     }
     if (__ballot_sync(0xffffffffu, rotated != 0) == 0u) break;
   }
   // --- sort eigenvectors by descending eigenvalue
   if (lane < 8) {
-    const double lam = S.gr[lane][lane];
+    const double lam = S.gr[cur][lane][lane];
     int rank = 0;
 #pragma unroll
     for (int o = 0; o < 8; ++o) {
-      const double lo = S.gr[o][o];
+      const double lo = S.gr[cur][o][o];
       if (lo > lam || (lo == lam && o < lane)) ++rank;
     }
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-      S.sr[r][rank] = S.vr[r][lane];
-      S.si[r][rank] = S.vi[r][lane];
+      S.sr[r][rank] = S.vr[cur][r][lane];
+      S.si[r][rank] = S.vi[cur][r][lane];
     }
   }
   __syncwarp();
@@ -388,7 +394,7 @@ jacobi_kernel(cplx* __restrict__ xp, cplx* __restrict__ wp, int p, int q, int nb
         if (S.need) {
           ++my_rot;
           apply8(XI, XJ, p, S);
-          apply8(wp + pa * wpan, wp + pb * wpan, q, S);
+          if (wp) apply8(wp + pa * wpan, wp + pb * wpan, q, S);
           if (staged) {
             __syncthreads();
             copy_panel(gI, sI, p);
@@ -510,13 +516,13 @@ __global__ void emit_kernel(const cplx* __restrict__ xp, const cplx* __restrict_
                             const int* __restrict__ perm, int m, int n, int p, int q,
                             int transposed, int keep, cplx* __restrict__ u, int u_na,
                             long long u_so, long long u_sa, long long u_sj,
-                            cplx* __restrict__ svh) {
+                            cplx* __restrict__ svh, cplx* __restrict__ ucont) {
   // element space: [0, m*keep) -> U ; [m*keep, (m+n)*keep) -> SVh
   const long long nu = (long long)m * keep, nv = (long long)n * keep;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < nu + nv;
        e += (long long)gridDim.x * blockDim.x) {
     if (e < nu) {
-      if (!u) continue;
+      if (!u && !ucont) continue;
       const int j = (int)(e % keep);
       const int i = (int)(e / keep);
       const int c = perm[j];
@@ -530,7 +536,8 @@ __global__ void emit_kernel(const cplx* __restrict__ xp, const cplx* __restrict_
       } else {                   // U = W
         v = wp[(pan * q + i) * PC + c4];
       }
-      u[(long long)(i / u_na) * u_so + (long long)(i % u_na) * u_sa + j * u_sj] = v;
+      if (u) u[(long long)(i / u_na) * u_so + (long long)(i % u_na) * u_sa + j * u_sj] = v;
+      if (ucont) ucont[(long long)i * keep + j] = v;
     } else {
       if (!svh) continue;
       const long long f = e - nu;
@@ -586,11 +593,12 @@ extern "C" int b200_svd_factor(void* stream_, const void* theta, int m, int n,
   h.m = m; h.n = n; h.p = L.p; h.q = L.q; h.npan = L.npan; h.nb = L.nb;
   h.transposed = L.transposed; h.keep = 0; h.sweeps = 0; h.status = 1;
   h.rotations = 0; h.pad = 0; h.eps = eps; h.s0 = 0.0; h.fro2 = 0.0; h.pad2 = 0.0;
+  h.theta = theta; h.rs = rs; h.cs = cs;
   B200_CUDA_CHECK(cudaMemcpyAsync(hdr, &h, sizeof(h), cudaMemcpyHostToDevice, stream));
   B200_CUDA_CHECK(cudaMemsetAsync(flags, 0, NFLAGS * sizeof(int), stream));
 
   {
-    const long long total = (long long)L.nb * (L.p + L.q) * PC;
+    const long long total = (long long)L.nb * (L.p + (wp ? L.q : 0)) * PC;
     int blocks = (int)((total + 255) / 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
     svd_load_kernel<<<blocks, 256, 0, stream>>>((const cplx*)theta, rs, cs, m, n,
@@ -627,9 +635,15 @@ extern "C" int b200_svd_factor(void* stream_, const void* theta, int m, int n,
     double tol = 2.0 * sqrt((double)L.p) * 2.220446049250313e-16;
     if (tol < 1e-11) tol = 1e-11;
     void* args[] = {&xp, &wp, &p, &q, &nb, &staged, &tol, &flags, &hdr};
+    b200::profile_begin(stream);
     B200_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)jacobi_kernel, dim3(grid),
                                                 dim3(JT), args, dyn, stream));
     b200::count_launch();
+    {   // SURVEY 8d convention: 4*(14 m n^2 + 8 n^3) with m >= n
+      const double mm = (double)L.p, nn = (double)L.q;
+      b200::profile_end(stream, 4.0 * (14.0 * mm * nn * nn + 8.0 * nn * nn * nn),
+                        &hdr->sweeps);
+    }
   }
   {
     const int warps = L.nb;
@@ -657,9 +671,9 @@ extern "C" int b200_svd_factor(void* stream_, const void* theta, int m, int n,
   return B200_OK;
 }
 
-extern "C" int b200_svd_emit(void* stream_, const void* work, int m, int n, int keep,
-                             void* u, int u_na, int64_t u_so, int64_t u_sa,
-                             int64_t u_sj, void* svh) {
+extern "C" int b200_svd_emit(void* stream_, const void* work, const void* theta, int m,
+                             int n, int64_t rs, int64_t cs, int keep, void* u, int u_na,
+                             int64_t u_so, int64_t u_sa, int64_t u_sj, void* svh) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!work || m <= 0 || n <= 0 || keep < 0 || u_na < 1) {
     b200::set_error("b200_svd_emit: invalid argument");
@@ -671,10 +685,12 @@ extern "C" int b200_svd_emit(void* stream_, const void* work, int m, int n, int 
   const long long total = (long long)(m + n) * keep;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
+  cplx* ucont = nullptr;
+  (void)theta; (void)rs; (void)cs;
   emit_kernel<<<blocks, 256, 0, stream>>>(
       (const cplx*)(base + L.xp), (const cplx*)(base + L.wp),
       (const double*)(base + L.sval), (const int*)(base + L.perm), m, n, L.p, L.q,
-      L.transposed, keep, (cplx*)u, u_na, u_so, u_sa, u_sj, (cplx*)svh);
+      L.transposed, keep, (cplx*)u, u_na, u_so, u_sa, u_sj, (cplx*)svh, ucont);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }
