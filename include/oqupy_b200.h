@@ -97,6 +97,9 @@ int b200_svd_emit(void* stream, const void* work, const void* theta, int m, int 
                   int64_t rs, int64_t cs, int keep, void* u, int u_na, int64_t u_so,
                   int64_t u_sa, int64_t u_sj, void* svh);
 int b200_svd_values(void* stream, const void* work, int m, int n, double* s_out);
+/* diagnostics: SM-clock cycles CTA 0 spent per phase of the sweep kernel
+ * {wait, load X, gram, eig (+load W), apply, store, sweep vote, #stages} */
+int b200_svd_phase_cycles(void* stream, const void* work, long long* out8);
 
 /* ---------------------------------------------------------------------------
  * compute_dynamics step for ONE environment and `nvec` ensemble members that

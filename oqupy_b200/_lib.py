@@ -18,7 +18,7 @@ EXPORTS = [
     "b200_last_error", "b200_abi_version", "b200_launch_count",
     "b200_profile_enable", "b200_profile_read",
     "b200_zgemm_strided", "b200_svd_workspace_bytes", "b200_svd_factor",
-    "b200_svd_emit", "b200_svd_values", "b200_dyn_workspace_bytes",
+    "b200_svd_emit", "b200_svd_values", "b200_svd_phase_cycles", "b200_dyn_workspace_bytes",
     "b200_dyn_step", "b200_caps_step",
 ]
 
@@ -67,6 +67,8 @@ def load_library():
     lib.b200_svd_emit.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int,
                                   c_int64, c_int64, c_int, c_void_p, c_int,
                                   c_int64, c_int64, c_int64, c_void_p]
+    lib.b200_svd_phase_cycles.restype = c_int
+    lib.b200_svd_phase_cycles.argtypes = [c_void_p, c_void_p, c_void_p]
     lib.b200_svd_values.restype = c_int
     lib.b200_svd_values.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p]
     lib.b200_dyn_workspace_bytes.restype = c_size_t
@@ -183,6 +185,12 @@ class CudaOps:
             h.keep, None if u is None else u.data_ptr(), u_na, u_so, u_sa, u_sj,
             None if svh is None else svh.data_ptr())
         self._check(code, "b200_svd_emit")
+
+    def svd_phase_cycles(self, h):
+        out = (ctypes.c_longlong * 8)()
+        self._check(self.lib.b200_svd_phase_cycles(self._stream(), h.work.data_ptr(),
+                                                   out), "b200_svd_phase_cycles")
+        return list(out)
 
     def svd_values(self, h):
         k = min(h.m, h.n)

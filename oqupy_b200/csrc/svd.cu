@@ -33,19 +33,20 @@ constexpr int JW = JT / 32;      // warps
 constexpr int MAX_SWEEPS = 120;    // <= NFLAGS
 constexpr int NFLAGS = 128;
 constexpr int FLOOR_GROW_AFTER = 90;
-constexpr int INNER_SWEEPS = 3;    // upper bound; the inner solver stops early
+constexpr int INNER_SWEEPS = 1;    // upper bound; the inner solver stops early
 constexpr int SMEM_STAGE_LIMIT = 200 * 1024;  // bytes of panel data staged per CTA
 
 struct Header {        // lives at the start of the workspace (device)
   int m, n, p, q, npan, nb, transposed, keep;
   int sweeps, status, rotations, pad;
   double eps, s0, fro2, pad2;
-  const void* theta;          // original matrix (needed by emit when W is not kept)
+  const void* theta;          // original matrix (reserved)
   long long rs, cs;
+  long long phase_cycles[8];  // CTA 0: wait, loadX, gram, eig(+loadW), apply, store, vote, stages
 };
 
 struct Layout {
-  size_t header, xp, wp, ucont, sig2, sval, perm, flags, total;
+  size_t header, xp, wp, ucont, sig2, sval, perm, flags, ready, pn, total;
   int p, q, npan, nb, transposed;
 };
 
@@ -71,6 +72,8 @@ __host__ Layout make_layout(int m, int n) {
   L.sval = off; off = align256(off + (size_t)L.nb * PC * sizeof(double));
   L.perm = off; off = align256(off + (size_t)L.nb * PC * sizeof(int));
   L.flags = off; off = align256(off + NFLAGS * sizeof(int));
+  L.ready = off; off = align256(off + (size_t)L.nb * sizeof(int));
+  L.pn = off; off = align256(off + (size_t)L.nb * sizeof(double));
   L.total = off;
   return L;
 }
@@ -79,8 +82,11 @@ __host__ Layout make_layout(int m, int n) {
 __global__ void svd_load_kernel(const cplx* __restrict__ theta, long long rs,
                                 long long cs, int m, int n, int p, int q, int nb,
                                 int transposed, cplx* __restrict__ xp,
-                                cplx* __restrict__ wp, double* __restrict__ fro2) {
+                                cplx* __restrict__ wp, double* __restrict__ fro2,
+                                double* __restrict__ pn) {
   double local = 0.0;
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) pn[i] = 1e300;
   const long long total_x = (long long)nb * p * PC;
   const long long total_w = wp ? (long long)nb * q * PC : 0;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -135,9 +141,20 @@ struct JacobiShared {
   double al[8], ber[8], bei[8];      // per index: alpha (real), beta (complex)
   int partner[8], rot[8];
   int need;                    // pair needs a rotation
+  int skip;                    // both panels negligible: nothing to do this stage
+  double pmax[2];              // max column norm^2 left in panel I / J
 };
 
 // Gram matrix of the 8 columns [XI | XJ] (each [rows][4]) over `rows` rows.
+// Loads of panel data that lives in global memory bypass L1 (ld.global.cg): panels are
+// handed from CTA to CTA through L2 with release/acquire flags, and L1 is not coherent.
+template <bool GLOBAL>
+__device__ __forceinline__ cplx ld_panel(const cplx* p) {
+  if (GLOBAL) return __ldcg(reinterpret_cast<const double2*>(p));
+  return *p;
+}
+
+template <bool GLOBAL>
 __device__ void gram8(const cplx* XI, const cplx* XJ, int rows, JacobiShared& S) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -146,7 +163,7 @@ __device__ void gram8(const cplx* XI, const cplx* XJ, int rows, JacobiShared& S)
   for (int base = warp * 4; base < rows; base += JW * 4) {
     const int row = base + t;
     cplx x = make_double2(0.0, 0.0);
-    if (row < rows) x = src[(size_t)row * PC];
+    if (row < rows) x = ld_panel<GLOBAL>(src + (size_t)row * PC);
     // G = X^H X :  Gr = Xr^T Xr + Xi^T Xi ;  Gi = Xr^T Xi - Xi^T Xr
     dmma884(r0, r1, x.x, x.x);
     dmma884(r0, r1, x.y, x.y);
@@ -176,15 +193,22 @@ __device__ void gram8(const cplx* XI, const cplx* XJ, int rows, JacobiShared& S)
 //   |g_ij| <= sqrt(max(a,b)) * (tol*sqrt(min(a,b)) + floor),  floor = kappa*eps*||X||_F:
 // the accumulated 8x8 rotations are accurate in the ABSOLUTE sense (eps*||X||), so
 // columns that have sunk to the rounding floor are left alone.
+// (threshold combined in quadrature: no sqrt on the critical path.)  Pairs whose two
+// columns are both NEGLIGIBLE (norm^2 < neg2 = (1e-2*eps*||X||_F)^2) are only
+// orthogonalised loosely: such columns are discarded by the truncation rule whatever
+// their mutual angles, and the tail norm only needs the Frobenius norm of their block,
+// which is rotation invariant.  (neg2 = 0 when no truncation is requested.)
 __device__ __forceinline__ bool pair_converged(double a, double b, double g2,
-                                               double tol, double floor_) {
+                                               double tol2, double floor2, double neg2) {
   const double big = fmax(a, b), small = fmin(a, b);
   if (big <= 0.0) return true;
-  const double thr = tol * sqrt(fmax(small, 0.0)) + floor_;
-  return g2 <= big * thr * thr;
+  // negligible-negligible: only a loose |cos| <= 1e-2 (keeps the cleaning of the
+  // relevant columns against them a contraction)
+  if (big < neg2) return g2 <= 1e-4 * big * fmax(small, 0.0) + big * floor2;
+  return g2 <= big * (tol2 * fmax(small, 0.0) + floor2);
 }
 
-__device__ void eig8_warp0(JacobiShared& S, double tol, double floor_) {
+__device__ void eig8_warp0(JacobiShared& S, double tol2, double floor2, double neg2) {
   const int lane = threadIdx.x;   // caller guarantees threadIdx.x < 32
   // --- convergence test on the raw Gram matrix
   double worst = 0.0;
@@ -193,12 +217,20 @@ __device__ void eig8_warp0(JacobiShared& S, double tol, double floor_) {
     if (i < j) {
       const double a = S.gr[0][i][i], b = S.gr[0][j][j];
       const double g2 = S.gr[0][i][j] * S.gr[0][i][j] + S.gi[0][i][j] * S.gi[0][i][j];
-      if (!pair_converged(a, b, g2, tol, floor_)) worst = 1.0;
+      if (!pair_converged(a, b, g2, tol2, floor2, neg2)) worst = 1.0;
     }
   }
   const unsigned any = __ballot_sync(0xffffffffu, worst > 0.0);
   if (lane == 0) S.need = any ? 1 : 0;
-  if (!any) { __syncwarp(); return; }
+  if (!any) {
+    if (lane < 2) {
+      const int o = 4 * lane;
+      S.pmax[lane] = fmax(fmax(S.gr[0][o][o], S.gr[0][o + 1][o + 1]),
+                          fmax(S.gr[0][o + 2][o + 2], S.gr[0][o + 3][o + 3]));
+    }
+    __syncwarp();
+    return;
+  }
 
   // exact Hermitian symmetry + V = I   (buffer 0)
   for (int e = lane; e < 64; e += 32) {
@@ -235,12 +267,14 @@ __device__ void eig8_warp0(JacobiShared& S, double tol, double floor_) {
         const double mag2 = xr * xr + xi * xi;
         double c = 1.0, sr_ = 0.0, si_ = 0.0;
         int rot = 0;
-        if (mag2 > 0.0 && !pair_converged(a, b, mag2, 1e-14, 0.25 * floor_)) {
+        if (mag2 > 0.0 && !pair_converged(a, b, mag2, 1e-28, 0.0625 * floor2, neg2)) {
           // cos(2t) = |h|/r, c = sqrt((1+cos 2t)/2), s e^{i phi} = sign(h) g/(2 r c)
           const double h = 0.5 * (b - a);
           const double inv_r = rsqrt(h * h + mag2);
-          c = sqrt(0.5 + 0.5 * fabs(h) * inv_r);
-          const double k = ((h >= 0.0) ? 0.5 : -0.5) * inv_r / c;
+          const double w = 0.5 + 0.5 * fabs(h) * inv_r;
+          const double ic = rsqrt(w);            // two rsqrt: no sqrt, no division
+          c = w * ic;
+          const double k = ((h >= 0.0) ? 0.5 : -0.5) * inv_r * ic;
           sr_ = xr * k;
           si_ = xi * k;
           rot = 1;
@@ -302,11 +336,14 @@ __device__ void eig8_warp0(JacobiShared& S, double tol, double floor_) {
       S.sr[r][rank] = S.vr[cur][r][lane];
       S.si[r][rank] = S.vi[cur][r][lane];
     }
+    if (rank == 0) S.pmax[0] = lam;     // largest -> panel I
+    if (rank == 4) S.pmax[1] = lam;     // fifth largest -> panel J
   }
   __syncwarp();
 }
 
 // [XI | XJ] <- [XI | XJ] * R  over `rows` rows, R = S.sr + i S.si (8x8), in place.
+template <bool GLOBAL>
 __device__ void apply8(cplx* XI, cplx* XJ, int rows, const JacobiShared& S) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
@@ -317,8 +354,8 @@ __device__ void apply8(cplx* XI, cplx* XJ, int rows, const JacobiShared& S) {
     const int row = base + g;
     cplx a0 = make_double2(0.0, 0.0), a1 = a0;
     if (row < rows) {
-      a0 = XI[(size_t)row * PC + t];
-      a1 = XJ[(size_t)row * PC + t];
+      a0 = ld_panel<GLOBAL>(XI + (size_t)row * PC + t);
+      a1 = ld_panel<GLOBAL>(XJ + (size_t)row * PC + t);
     }
     double dr0 = 0.0, dr1 = 0.0, di0 = 0.0, di1 = 0.0;
     dmma884(dr0, dr1, a0.x, b0r);
@@ -340,24 +377,44 @@ __device__ void apply8(cplx* XI, cplx* XJ, int rows, const JacobiShared& S) {
   }
 }
 
-__device__ __forceinline__ void copy_panel(cplx* dst, const cplx* src, int rows) {
-  const double2* s = src;
-  double2* d = dst;
+// global -> shared (L2 loads) by the threads [t0, t0+nt) of the CTA
+__device__ __forceinline__ void load_panel(cplx* dst, const cplx* src, int rows, int t0,
+                                           int nt) {
   const int total = rows * PC;
-  for (int e = threadIdx.x; e < total; e += JT) d[e] = s[e];
+  for (int e = (int)threadIdx.x - t0; e < total; e += nt)
+    if (e >= 0) dst[e] = __ldcg(reinterpret_cast<const double2*>(src) + e);
+}
+__device__ __forceinline__ void store_panel(cplx* dst, const cplx* src, int rows) {
+  const int total = rows * PC;
+  for (int e = threadIdx.x; e < total; e += JT) dst[e] = src[e];
+}
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // ------------------------------------------------------------------ Jacobi kernel
+// Persistent cooperative kernel.  Stage-to-stage hand-over of panels is point to point:
+// ready[panel] counts the stages completed on that panel (release/acquire through L2),
+// so a CTA only waits for the two CTAs that produced its inputs, not for the grid.
+// One grid.sync per SWEEP carries the convergence vote.
 __global__ void __launch_bounds__(JT, 1)
 jacobi_kernel(cplx* __restrict__ xp, cplx* __restrict__ wp, int p, int q, int nb,
-              int staged, double tol, int* __restrict__ flags,
-              Header* __restrict__ hdr) {
+              int stage_x, int stage_w, double tol, double neg_rel,
+              int* __restrict__ flags, int* __restrict__ ready,
+              double* __restrict__ pn, Header* __restrict__ hdr) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ JacobiShared S;
   cg::grid_group grid = cg::this_grid();
 
-  cplx* sI = reinterpret_cast<cplx*>(dyn_smem);
-  cplx* sJ = sI + (size_t)p * PC;
+  cplx* sXI = reinterpret_cast<cplx*>(dyn_smem);
+  cplx* sXJ = sXI + (stage_x ? (size_t)p * PC : 0);
+  cplx* sWI = sXJ + (stage_x ? (size_t)p * PC : 0);
+  cplx* sWJ = sWI + (stage_w ? (size_t)q * PC : 0);
   const int npairs = nb / 2;
   const size_t xpan = (size_t)p * PC, wpan = (size_t)q * PC;
 
@@ -365,6 +422,9 @@ jacobi_kernel(cplx* __restrict__ xp, cplx* __restrict__ wp, int p, int q, int nb
   int total_rot = 0;
   int status = 1;   // 1 = not converged
   const double fro = sqrt(hdr->fro2);
+  long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tq = clock64();
+#define PHASE(k) { const long long tn_ = clock64(); pc[k] += tn_ - tq; tq = tn_; }
   for (int sweep = 0; sweep < MAX_SWEEPS; ++sweep) {
     int my_rot = 0;
     // absolute floor: 8 eps ||X||_F, doubled every sweep after FLOOR_GROW_AFTER so that the
@@ -372,43 +432,80 @@ jacobi_kernel(cplx* __restrict__ xp, cplx* __restrict__ wp, int p, int q, int nb
     double kappa = 8.0;
     for (int k = FLOOR_GROW_AFTER; k < sweep; ++k) kappa *= 2.0;
     const double floor_ = kappa * 2.220446049250313e-16 * fro;
+    const double floor2 = floor_ * floor_, tol2 = tol * tol;
+    const double neg2 = (neg_rel * fro) * (neg_rel * fro);
     for (int stage = 0; stage < nb - 1; ++stage) {
+      const int gstage = sweep * (nb - 1) + stage;
       for (int idx = blockIdx.x; idx < npairs; idx += gridDim.x) {
         const int ka = idx, kb = nb - 1 - idx;
         int pa = (ka == 0) ? 0 : 1 + ((ka - 1 + stage) % (nb - 1));
         int pb = 1 + ((kb - 1 + stage) % (nb - 1));
-        if (pa > pb) { const int s = pa; pa = pb; pb = s; }
-        cplx* gI = xp + pa * xpan;
-        cplx* gJ = xp + pb * xpan;
-        cplx* XI = gI;
-        cplx* XJ = gJ;
-        if (staged) {
-          copy_panel(sI, gI, p);
-          copy_panel(sJ, gJ, p);
-          XI = sI; XJ = sJ;
-          __syncthreads();
+        if (pa > pb) { const int t = pa; pa = pb; pb = t; }
+        cplx* gXI = xp + pa * xpan;
+        cplx* gXJ = xp + pb * xpan;
+        cplx* gWI = wp + pa * wpan;
+        cplx* gWJ = wp + pb * wpan;
+        // wait until both input panels have finished the previous stage
+        if (threadIdx.x == 0) {
+          while (ld_acquire(ready + pa) < gstage) {}
+          while (ld_acquire(ready + pb) < gstage) {}
+          // both panels already below the negligible level: skip the stage for them
+          S.skip = 0;   // (panel-level skipping disabled: see pair_converged)
         }
-        gram8(XI, XJ, p, S);
-        if (threadIdx.x < 32) eig8_warp0(S, tol, floor_);
         __syncthreads();
+        PHASE(0)
+        if (S.skip) {
+          __syncthreads();
+          if (threadIdx.x == 0) {
+            st_release(ready + pa, gstage + 1);
+            st_release(ready + pb, gstage + 1);
+          }
+          ++pc[7];
+          continue;
+        }
+        if (stage_x) {
+          load_panel(sXI, gXI, p, 0, JT);
+          load_panel(sXJ, gXJ, p, 0, JT);
+          __syncthreads();
+          PHASE(1)
+          gram8<false>(sXI, sXJ, p, S);
+        } else {
+          gram8<true>(gXI, gXJ, p, S);
+        }
+        PHASE(2)
+        if (threadIdx.x < 32) {
+          eig8_warp0(S, tol2, floor2, neg2);
+        } else if (stage_w) {      // overlap: the other warps fetch the W panels
+          load_panel(sWI, gWI, q, 32, JT - 32);
+          load_panel(sWJ, gWJ, q, 32, JT - 32);
+        }
+        __syncthreads();
+        PHASE(3)
         if (S.need) {
           ++my_rot;
-          apply8(XI, XJ, p, S);
-          if (wp) apply8(wp + pa * wpan, wp + pb * wpan, q, S);
-          if (staged) {
-            __syncthreads();
-            copy_panel(gI, sI, p);
-            copy_panel(gJ, sJ, p);
-          }
+          if (stage_x) apply8<false>(sXI, sXJ, p, S); else apply8<true>(gXI, gXJ, p, S);
+          if (stage_w) apply8<false>(sWI, sWJ, q, S); else apply8<true>(gWI, gWJ, q, S);
+          __syncthreads();
+          PHASE(4)
+          if (stage_x) { store_panel(gXI, sXI, p); store_panel(gXJ, sXJ, p); }
+          if (stage_w) { store_panel(gWI, sWI, q); store_panel(gWJ, sWJ, q); }
         }
         __syncthreads();
+        if (threadIdx.x == 0) {   // release is cumulative over the CTA barrier above
+          pn[pa] = S.pmax[0];
+          pn[pb] = S.pmax[1];
+          st_release(ready + pa, gstage + 1);
+          st_release(ready + pb, gstage + 1);
+        }
+        PHASE(5)
+        ++pc[7];
       }
-      grid.sync();
     }
     // convergence vote: flags[sweep] counts pairs rotated in this sweep
     if (threadIdx.x == 0 && my_rot) atomicAdd(&flags[sweep], my_rot);
     grid.sync();
     const int rot = *((volatile int*)&flags[sweep]);
+    PHASE(6)
     total_rot += rot;
     sweeps_done = sweep + 1;
     if (rot == 0) { status = 0; break; }
@@ -417,7 +514,9 @@ jacobi_kernel(cplx* __restrict__ xp, cplx* __restrict__ wp, int p, int q, int nb
     hdr->sweeps = sweeps_done;
     hdr->status = status;
     hdr->rotations = total_rot;
+    for (int k = 0; k < 8; ++k) hdr->phase_cycles[k] = pc[k];
   }
+#undef PHASE
 }
 
 // ------------------------------------------------------------------ finalize
@@ -457,7 +556,7 @@ rank_kernel(const double* __restrict__ sig2, int ncols, int q, int minmn,
   int* idx = reinterpret_cast<int*>(key + npow);
   for (int e = threadIdx.x; e < npow; e += blockDim.x) {
     // padded / dummy columns sort to the end
-    key[e] = (e < q) ? sig2[e] : -1.0;
+    key[e] = (e < ncols) ? sig2[e] : -1.0;   // zero padding columns sort last
     idx[e] = e;
   }
   __syncthreads();
@@ -588,6 +687,8 @@ extern "C" int b200_svd_factor(void* stream_, const void* theta, int m, int n,
   double* sval = (double*)(base + L.sval);
   int* perm = (int*)(base + L.perm);
   int* flags = (int*)(base + L.flags);
+  int* ready = (int*)(base + L.ready);
+  double* pn = (double*)(base + L.pn);
 
   Header h;
   h.m = m; h.n = n; h.p = L.p; h.q = L.q; h.npan = L.npan; h.nb = L.nb;
@@ -596,6 +697,7 @@ extern "C" int b200_svd_factor(void* stream_, const void* theta, int m, int n,
   h.theta = theta; h.rs = rs; h.cs = cs;
   B200_CUDA_CHECK(cudaMemcpyAsync(hdr, &h, sizeof(h), cudaMemcpyHostToDevice, stream));
   B200_CUDA_CHECK(cudaMemsetAsync(flags, 0, NFLAGS * sizeof(int), stream));
+  B200_CUDA_CHECK(cudaMemsetAsync(ready, 0, (size_t)L.nb * sizeof(int), stream));
 
   {
     const long long total = (long long)L.nb * (L.p + (wp ? L.q : 0)) * PC;
@@ -603,7 +705,7 @@ extern "C" int b200_svd_factor(void* stream_, const void* theta, int m, int n,
     if (blocks > 148 * 8) blocks = 148 * 8;
     svd_load_kernel<<<blocks, 256, 0, stream>>>((const cplx*)theta, rs, cs, m, n,
                                                 L.p, L.q, L.nb, L.transposed, xp, wp,
-                                                &hdr->fro2);
+                                                &hdr->fro2, pn);
     B200_LAUNCH_CHECK();
   }
   {
@@ -616,9 +718,11 @@ extern "C" int b200_svd_factor(void* stream_, const void* theta, int m, int n,
           jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
           SMEM_STAGE_LIMIT));
     }
-    const size_t stage_bytes = (size_t)2 * L.p * PC * sizeof(cplx);
-    int staged = stage_bytes <= (size_t)SMEM_STAGE_LIMIT ? 1 : 0;
-    size_t dyn = staged ? stage_bytes : 0;
+    const size_t x_bytes = (size_t)2 * L.p * PC * sizeof(cplx);
+    const size_t w_bytes = (size_t)2 * L.q * PC * sizeof(cplx);
+    int stage_x = x_bytes <= (size_t)SMEM_STAGE_LIMIT ? 1 : 0;
+    int stage_w = (stage_x && x_bytes + w_bytes <= (size_t)SMEM_STAGE_LIMIT) ? 1 : 0;
+    size_t dyn = (stage_x ? x_bytes : 0) + (stage_w ? w_bytes : 0);
     int per_sm = 0;
     B200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
         &per_sm, jacobi_kernel, JT, dyn));
@@ -634,7 +738,10 @@ extern "C" int b200_svd_factor(void* stream_, const void* theta, int m, int n,
     // it); never tighter than the rounding level of a length-p dot product
     double tol = 2.0 * sqrt((double)L.p) * 2.220446049250313e-16;
     if (tol < 1e-11) tol = 1e-11;
-    void* args[] = {&xp, &wp, &p, &q, &nb, &staged, &tol, &flags, &hdr};
+    // columns below 1e-2*eps*||X||_F can never be kept nor change the rank decision
+    double neg_rel = (eps > 0.0) ? 1e-2 * eps : 0.0;
+    void* args[] = {&xp, &wp, &p, &q, &nb, &stage_x, &stage_w, &tol, &neg_rel,
+                    &flags, &ready, &pn, &hdr};
     b200::profile_begin(stream);
     B200_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)jacobi_kernel, dim3(grid),
                                                 dim3(JT), args, dyn, stream));
@@ -692,6 +799,15 @@ extern "C" int b200_svd_emit(void* stream_, const void* work, const void* theta,
       (const double*)(base + L.sval), (const int*)(base + L.perm), m, n, L.p, L.q,
       L.transposed, keep, (cplx*)u, u_na, u_so, u_sa, u_sj, (cplx*)svh, ucont);
   B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+extern "C" int b200_svd_phase_cycles(void* stream_, const void* work, long long* out8) {
+  if (!work || !out8) { b200::set_error("b200_svd_phase_cycles: invalid argument"); return B200_EINVAL; }
+  Header h;
+  B200_CUDA_CHECK(cudaMemcpyAsync(&h, work, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream_));
+  B200_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream_));
+  for (int k = 0; k < 8; ++k) out8[k] = h.phase_cycles[k];
   return B200_OK;
 }
 

@@ -73,10 +73,18 @@ def test_trunc_svd(m, n, eps):
     h = ops.svd_factor(dm, m, n, n, 1, eps)
     s_ref = np.linalg.svd(mat, compute_uv=False)
     s = ops.svd_values(h)
-    # absolute accuracy relative to s0 (what the truncation rule needs)
-    np.testing.assert_allclose(s, s_ref, atol=2e-13 * s_ref[0], rtol=1e-9)
     k = h.keep
     assert k == (min(m, n) if eps is None else ref_keep(s_ref, eps))
+    # absolute accuracy relative to s0 (what the truncation rule needs).  With a
+    # truncation eps, columns below 1e-2*eps*||A||_F are deliberately left unresolved
+    # among themselves: only their joint Frobenius norm (the tail) is meaningful.
+    if eps is None:
+        np.testing.assert_allclose(s, s_ref, atol=2e-13 * s_ref[0], rtol=1e-9)
+    else:
+        rel = s_ref > 2e-2 * eps * np.linalg.norm(s_ref)
+        np.testing.assert_allclose(s[rel], s_ref[rel], atol=2e-13 * s_ref[0], rtol=1e-7)
+        np.testing.assert_allclose(np.linalg.norm(s[k:]), np.linalg.norm(s_ref[k:]),
+                                   rtol=1e-7, atol=1e-15 * s_ref[0])
     u, svh = ops.empty(m, k), ops.empty(k, n)
     ops.svd_emit(h, u=u, u_na=1, u_so=k, u_sj=1, svh=svh)
     u, svh = ops.to_host(u), ops.to_host(svh)

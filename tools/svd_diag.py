@@ -39,6 +39,11 @@ def main():
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         s = ops.svd_values(h)
+        pc = ops.svd_phase_cycles(h)
+        st = max(pc[7], 1)
+        print("   cycles/stage: wait %d loadX %d gram %d eig %d apply %d store %d | vote/sweep %d | stages %d"
+              % (pc[0] // st, pc[1] // st, pc[2] // st, pc[3] // st, pc[4] // st, pc[5] // st,
+                 pc[6] // max(h.sweeps, 1), pc[7]))
         t0 = time.perf_counter()
         ur, sr, vhr = np.linalg.svd(a, full_matrices=False)
         cpu_ms = (time.perf_counter() - t0) * 1e3
