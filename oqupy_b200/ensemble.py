@@ -1,0 +1,80 @@
+"""Ensembles of independent runs sharded over the GPUs of one box.
+
+A single TEMPO / PT-TEMPO run is time-sequential and stays on one GPU.  Independent
+parameter points (couplings, temperatures, control perturbations) are assigned
+cyclically to ranks (``index % world_size``: balances the chi(alpha, T) cost gradient
+of a parameter grid); no data-path collective exists.  The ONLY collective is the
+final gather of the per-member dynamics (``all_gather_into_tensor``: NCCL over NVLink
+on GPUs, gloo in the CPU tests).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_indices(n_members, rank, world_size):
+    """Members owned by ``rank``: rank, rank + W, rank + 2W, ..."""
+    return list(range(rank, n_members, world_size))
+
+
+def run_ensemble(n_members, run_member, device=None, group=None):
+    """Run ``run_member(i)`` (-> real or complex ndarray, same shape for all i) for the
+    members of this rank and gather everything on every rank.
+
+    Returns an ndarray (n_members, *member_shape)."""
+    if dist.is_available() and dist.is_initialized():
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+    else:
+        world, rank = 1, 0
+    mine = shard_indices(n_members, rank, world)
+    results = [np.asarray(run_member(i)) for i in mine]
+    if world == 1:
+        return np.stack(results) if results else np.zeros((0,))
+    # every rank learns shape/dtype from rank 0 (which always owns member 0)
+    meta = [None]
+    if rank == 0:
+        meta = [(results[0].shape, results[0].dtype.str)]
+    dist.broadcast_object_list(meta, src=0, group=group)
+    shape, dtype = meta[0]
+    dtype = np.dtype(dtype)
+    per_rank = (n_members + world - 1) // world
+    buf = np.zeros((per_rank,) + tuple(shape), dtype=dtype)
+    for k, r in enumerate(results):
+        buf[k] = r
+    is_complex = np.iscomplexobj(buf)
+    flat = np.ascontiguousarray(buf).view(np.float64) if is_complex else \
+        np.ascontiguousarray(buf, dtype=np.float64)
+    send = torch.from_numpy(flat.reshape(-1).copy())
+    if device is not None:
+        send = send.to(device)
+    recv = torch.empty(world * send.numel(), dtype=send.dtype, device=send.device)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    allr = recv.cpu().numpy().reshape((world, per_rank) + flat.shape[1:])
+    if is_complex:
+        allr = allr.view(np.complex128).reshape((world, per_rank) + tuple(shape))
+    out = np.zeros((n_members,) + tuple(shape), dtype=dtype)
+    for r in range(world):
+        for k, i in enumerate(shard_indices(n_members, r, world)):
+            out[i] = allr[r, k]
+    return out
+
+
+def tempo_member(influences, propagators, initial_state, dkmax, epsrel, num_steps,
+                 unitary=None, ops=None):
+    """One TEMPO run on this rank's GPU; returns states (num_steps+1, d, d)."""
+    from .backends import TempoBackend  # pylint: disable=import-outside-toplevel
+    infl = np.asarray(influences)
+    rho0 = np.asarray(initial_state, dtype=np.complex128)
+    d = rho0.shape[0]
+    d2 = d * d
+
+    def influence(dk):
+        return None if dk < 0 else infl[dk]
+
+    be = TempoBackend(rho0, influence, np.eye(d) if unitary is None else unitary,
+                      propagators, np.ones(d2), np.ones(d2), dkmax, epsrel, ops=ops)
+    _, s0 = be.initialize()
+    states = [s0]
+    for _ in range(num_steps):
+        states.append(be.compute_step()[1])
+    return np.array(states).reshape(-1, d, d)
