@@ -1,393 +1,127 @@
-// eps-truncated complex128 SVD on the device: one-sided BLOCK Jacobi.
+// eps-truncated complex128 SVD on the device: one-sided BLOCK Jacobi, row-sliced.
 //
 // Replaces tn.split_node_full_svd(max_truncation_err=eps, relative=True)
 // (reference call sites oqupy/backends/node_array.py:262,285,541).
 //
-// Algorithm (B200-first, not LAPACK's bidiagonalisation):
-//   * X = theta (m >= n) or theta^H (m < n), p x q with p >= q, stored as PANELS of
-//     4 columns: panel j holds X[:, 4j:4j+4] as [row][4] complex128 (64 B per row),
-//     so a panel streams through L2/shared memory fully coalesced.  A q x q matrix W
-//     (initially I) accumulates the right rotations in the same panel layout.
-//   * Hestenes one-sided Jacobi on panel pairs, round-robin tournament ordering:
-//     per stage every CTA owns a pair (I, J) = 8 columns, stages them in shared
-//     memory, forms their 8x8 Gram matrix on the fp64 tensor cores (DMMA.8x8x4),
-//     diagonalises it with a warp-parallel two-sided Jacobi eigensolver, and applies
-//     the 8x8 rotation to the 8 columns of X and of W, again with DMMA.
-//     grid.sync() separates stages (cooperative persistent kernel).
-//   * Convergence: a full sweep in which no pair had |g_ij| > tol*sqrt(g_ii g_jj).
-//   * sigma_j = ||y_j||; sort; reference tail-norm rule picks `keep`; emit kernel
-//     writes U[:, :keep] and S*Vh[:keep] in the layouts the MPS engine asks for.
+// Algorithm (B200-first, not LAPACK's bidiagonalisation).  The SVDs of a TEMPO chain
+// are strictly sequential, so what matters is the LATENCY of one factorisation:
+//   * X = theta (m >= n) or theta^H (m < n), p x q with p >= q.  Y = [X ; W] stacks X
+//     on top of the q x q rotation accumulator W (initially I); T = p + q rows.  Y is
+//     stored in BLOCKS of 16 columns, block j = Y[:, 16j:16j+16] as [row][16]
+//     complex128 (256 B per row, fully coalesced).
+//   * Hestenes one-sided Jacobi on block pairs (32 columns), round-robin tournament.
+//     The grid is a 2-D decomposition: CTA (s, r) owns pair-slot s and ROW SLICE r of
+//     the stacked matrix.  Per stage it
+//       1. stages its slice of the two blocks in shared memory,
+//       2. forms the partial 32x32 Gram matrix of its X rows and publishes it,
+//       3. (slice 0 = leader) sums the partials in a fixed order (deterministic),
+//          runs ONE cyclic sweep of a two-sided Jacobi eigensolver on the 32x32
+//          Hermitian Gram matrix (cross-block pairs first, 2x2-block ownership: no
+//          buffer hazards), sorts the columns by descending norm and publishes the
+//          32x32 rotation J,
+//       4. applies J to its slice of [X ; W] and writes it back.
+//     Hand-over between stages is point to point through L2 (st.release / ld.acquire
+//     per (block, slice)); only the end of a sweep is a grid-wide barrier (the
+//     convergence vote).
+//   * Convergence: a full sweep in which no pair violated
+//       |g_ij|^2 <= max(a,b) * (tol^2 * min(a,b) + floor^2).
+//   * In the same launch: column norms -> sort -> the reference tail-norm rule picks
+//     `keep`, written straight to pinned host memory.  emit_kernel then writes
+//     U[:, :keep] and S*Vh[:keep] in the layouts the MPS engine asks for.
 #include <cooperative_groups.h>
 #include <math.h>
 
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
-using b200::dmma884;
 
 namespace {
 
-constexpr int PC = 4;            // columns per panel
-constexpr int JT = 512;          // threads of the Jacobi kernel
-constexpr int JW = JT / 32;      // warps
-constexpr int MAX_SWEEPS = 120;    // <= NFLAGS
+constexpr int BC = 16;            // columns per block
+constexpr int PB = 2 * BC;        // columns per block pair (the inner problem)
+constexpr int JT = 512;           // threads of the Jacobi kernel
+constexpr int MAX_SWEEPS = 120;   // <= NFLAGS
 constexpr int NFLAGS = 128;
 constexpr int FLOOR_GROW_AFTER = 90;
-constexpr int INNER_SWEEPS = 1;    // upper bound; the inner solver stops early
-constexpr int SMEM_STAGE_LIMIT = 200 * 1024;  // bytes of panel data staged per CTA
+constexpr int CHUNK_ROWS = 256;   // rows of a slice staged in shared memory at a time
+constexpr int MIN_SLICE_ROWS = 32;
+constexpr int GP = PB + 1;        // padded leading dimension of the 32x32 work matrices
 
 struct Header {        // lives at the start of the workspace (device)
-  int m, n, p, q, npan, nb, transposed, keep;
-  int sweeps, status, rotations, pad;
+  int m, n, p, q, nb, transposed, keep, sweeps;
+  int status, rotations, R, RS;
   double eps, s0, fro2, pad2;
-  const void* theta;          // original matrix (reserved)
-  long long rs, cs;
-  long long phase_cycles[8];  // CTA 0: wait, loadX, gram, eig(+loadW), apply, store, vote, stages
+  long long phase_cycles[8];  // CTA 0: wait, load, gram, solve/J-wait, apply+store, vote, -, stages
 };
 
 struct Layout {
-  size_t header, xp, wp, ucont, sig2, sval, perm, flags, ready, pn, total;
-  int p, q, npan, nb, transposed;
+  size_t header, ctrl, ctrl_bytes, sig2, sval, perm, gpart, jbuf, y, total;
+  int p, q, T, nb, S, R, RS, SE, transposed;
 };
 
 __host__ __device__ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+int device_sms() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        sms <= 0) {
+      (void)cudaGetLastError();
+      sms = 148;   // B200
+    }
+  }
+  return sms;
+}
+
+// ctrl region (ints, zeroed by one memset per factorisation):
+//   [0]            grid barrier counter
+//   [1]            spare
+//   [2 .. 2+NFLAGS)           rotated-stage count per sweep
+//   ready[nb*R]               stages completed per (block, slice)
+//   cnt[2*S]                  slices that published their partial Gram (double-buffered)
+//   flagj[S]                  2*(stage+1) + need, per slot
 __host__ Layout make_layout(int m, int n) {
   Layout L;
   L.transposed = (m < n) ? 1 : 0;
   L.p = L.transposed ? n : m;
   L.q = L.transposed ? m : n;
-  L.npan = (L.q + PC - 1) / PC;
-  L.nb = (L.npan & 1) ? L.npan + 1 : L.npan;   // even number of panels
+  L.T = L.p + L.q;
+  int nblk = (L.q + BC - 1) / BC;
+  L.nb = (nblk & 1) ? nblk + 1 : nblk;   // even number of blocks
   if (L.nb < 2) L.nb = 2;
+  L.S = L.nb / 2;
+  const int sms = device_sms();
+  int max_r = sms / L.S;
+  if (max_r < 1) max_r = 1;
+  int r = (L.T + MIN_SLICE_ROWS - 1) / MIN_SLICE_ROWS;
+  if (r > max_r) r = max_r;
+  int rs = (L.T + r - 1) / r;
+  rs = (rs + 3) & ~3;
+  L.RS = rs;
+  L.R = (L.T + rs - 1) / rs;
+  L.SE = L.S;                       // slots resident at once
+  if (L.SE * L.R > sms) L.SE = sms / L.R;
+  if (L.SE < 1) L.SE = 1;
   size_t off = 0;
   L.header = off; off = align256(off + sizeof(Header));
-  L.xp = off;   off = align256(off + (size_t)L.nb * L.p * PC * sizeof(cplx));
+  L.ctrl = off;
+  L.ctrl_bytes = sizeof(int) * (size_t)(2 + NFLAGS + (size_t)L.nb * L.R + 3 * (size_t)L.S);
+  off = align256(off + L.ctrl_bytes);
+  L.sig2 = off; off = align256(off + (size_t)L.nb * BC * sizeof(double));
+  L.sval = off; off = align256(off + (size_t)L.nb * BC * sizeof(double));
+  L.perm = off; off = align256(off + (size_t)L.nb * BC * sizeof(int));
+  L.gpart = off; off = align256(off + (size_t)2 * L.S * L.R * PB * PB * sizeof(cplx));
+  L.jbuf = off; off = align256(off + (size_t)2 * L.S * PB * PB * sizeof(cplx));
   // W accumulates the right rotations.  (Forming S*Vh as U^H*theta instead is NOT an
   // option: columns of U are orthogonal only down to the absolute rounding floor, and
   // the projection would amplify that by sigma_0/sigma_j.)
-  L.wp = off;   off = align256(off + (size_t)L.nb * L.q * PC * sizeof(cplx));
-  L.ucont = off;
-  L.sig2 = off; off = align256(off + (size_t)L.nb * PC * sizeof(double));
-  L.sval = off; off = align256(off + (size_t)L.nb * PC * sizeof(double));
-  L.perm = off; off = align256(off + (size_t)L.nb * PC * sizeof(int));
-  L.flags = off; off = align256(off + NFLAGS * sizeof(int));
-  L.ready = off; off = align256(off + (size_t)L.nb * sizeof(int));
-  L.pn = off; off = align256(off + (size_t)L.nb * sizeof(double));
+  L.y = off; off = align256(off + (size_t)L.nb * L.T * BC * sizeof(cplx));
   L.total = off;
   return L;
 }
 
-// ------------------------------------------------------------------ load / init
-__global__ void svd_load_kernel(const cplx* __restrict__ theta, long long rs,
-                                long long cs, int m, int n, int p, int q, int nb,
-                                int transposed, cplx* __restrict__ xp,
-                                cplx* __restrict__ wp, double* __restrict__ fro2,
-                                double* __restrict__ pn) {
-  double local = 0.0;
-  if (blockIdx.x == 0)
-    for (int i = threadIdx.x; i < nb; i += blockDim.x) pn[i] = 1e300;
-  const long long total_x = (long long)nb * p * PC;
-  const long long total_w = wp ? (long long)nb * q * PC : 0;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-       e < total_x + total_w; e += (long long)gridDim.x * blockDim.x) {
-    if (e < total_x) {
-      const int c4 = (int)(e % PC);
-      const long long t = e / PC;
-      const int row = (int)(t % p);
-      const int pan = (int)(t / p);
-      const int col = pan * PC + c4;
-      cplx v = make_double2(0.0, 0.0);
-      if (col < q) {
-        if (!transposed) {
-          v = theta[row * rs + col * cs];
-        } else {           // X = theta^H : X[row][col] = conj(theta[col][row])
-          v = theta[col * rs + row * cs];
-          v.y = -v.y;
-        }
-      }
-      xp[e] = v;
-      local = fma(v.x, v.x, local);
-      local = fma(v.y, v.y, local);
-    } else {
-      const long long f = e - total_x;
-      const int c4 = (int)(f % PC);
-      const long long t = f / PC;
-      const int row = (int)(t % q);
-      const int pan = (int)(t / q);
-      const int col = pan * PC + c4;
-      wp[f] = make_double2((col == row) ? 1.0 : 0.0, 0.0);
-    }
-  }
-  // ||X||_F^2: the scale of the absolute noise floor used by the convergence test
-  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
-  __shared__ double part[8];
-  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = local;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double tot = 0.0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += part[w];
-    if (tot != 0.0) atomicAdd(fro2, tot);
-  }
-}
-
-// ------------------------------------------------------------------ 8x8 helpers
-// Shared scratch of the Jacobi kernel (static part).
-struct JacobiShared {
-  double red[JW][128];   // per-warp partial Gram fragments (re: 0..63, im: 64..127)
-  double gr[2][8][8], gi[2][8][8];   // Gram / working Hermitian matrix (double-buffered)
-  double vr[2][8][8], vi[2][8][8];   // accumulated eigenvectors (double-buffered)
-  double sr[8][8], si[8][8];   // sorted eigenvectors (the 8x8 rotation to apply)
-  double al[8], ber[8], bei[8];      // per index: alpha (real), beta (complex)
-  int partner[8], rot[8];
-  int need;                    // pair needs a rotation
-  int skip;                    // both panels negligible: nothing to do this stage
-  double pmax[2];              // max column norm^2 left in panel I / J
-};
-
-// Gram matrix of the 8 columns [XI | XJ] (each [rows][4]) over `rows` rows.
-// Loads of panel data that lives in global memory bypass L1 (ld.global.cg): panels are
-// handed from CTA to CTA through L2 with release/acquire flags, and L1 is not coherent.
-template <bool GLOBAL>
-__device__ __forceinline__ cplx ld_panel(const cplx* p) {
-  if (GLOBAL) return __ldcg(reinterpret_cast<const double2*>(p));
-  return *p;
-}
-
-template <bool GLOBAL>
-__device__ void gram8(const cplx* XI, const cplx* XJ, int rows, JacobiShared& S) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int g = lane >> 2, t = lane & 3;
-  const cplx* src = (g < 4) ? (XI + g) : (XJ + (g - 4));
-  double r0 = 0.0, r1 = 0.0, i0 = 0.0, i1 = 0.0;
-  for (int base = warp * 4; base < rows; base += JW * 4) {
-    const int row = base + t;
-    cplx x = make_double2(0.0, 0.0);
-    if (row < rows) x = ld_panel<GLOBAL>(src + (size_t)row * PC);
-    // G = X^H X :  Gr = Xr^T Xr + Xi^T Xi ;  Gi = Xr^T Xi - Xi^T Xr
-    dmma884(r0, r1, x.x, x.x);
-    dmma884(r0, r1, x.y, x.y);
-    dmma884(i0, i1, x.x, x.y);
-    dmma884(i0, i1, -x.y, x.x);
-  }
-  S.red[warp][g * 8 + 2 * t] = r0;
-  S.red[warp][g * 8 + 2 * t + 1] = r1;
-  S.red[warp][64 + g * 8 + 2 * t] = i0;
-  S.red[warp][64 + g * 8 + 2 * t + 1] = i1;
-  __syncthreads();
-  if (threadIdx.x < 128) {
-    double acc = 0.0;
-#pragma unroll
-    for (int w = 0; w < JW; ++w) acc += S.red[w][threadIdx.x];
-    const int e = threadIdx.x & 63;
-    if (threadIdx.x < 64) S.gr[0][e >> 3][e & 7] = acc;
-    else S.gi[0][e >> 3][e & 7] = acc;
-  }
-  __syncthreads();
-}
-
-// Warp 0: decide whether the pair needs work; if so diagonalise the 8x8 Hermitian
-// Gram matrix (cyclic two-sided Jacobi, 4 disjoint rotations per round) and leave
-// the eigenvector matrix, columns sorted by DESCENDING eigenvalue, in S.sr/S.si.
-// A pair (i, j) counts as orthogonal when
-//   |g_ij| <= sqrt(max(a,b)) * (tol*sqrt(min(a,b)) + floor),  floor = kappa*eps*||X||_F:
-// the accumulated 8x8 rotations are accurate in the ABSOLUTE sense (eps*||X||), so
-// columns that have sunk to the rounding floor are left alone.
-// (threshold combined in quadrature: no sqrt on the critical path.)  Pairs whose two
-// columns are both NEGLIGIBLE (norm^2 < neg2 = (1e-2*eps*||X||_F)^2) are only
-// orthogonalised loosely: such columns are discarded by the truncation rule whatever
-// their mutual angles, and the tail norm only needs the Frobenius norm of their block,
-// which is rotation invariant.  (neg2 = 0 when no truncation is requested.)
-__device__ __forceinline__ bool pair_converged(double a, double b, double g2,
-                                               double tol2, double floor2, double neg2) {
-  const double big = fmax(a, b), small = fmin(a, b);
-  if (big <= 0.0) return true;
-  // negligible-negligible: only a loose |cos| <= 1e-2 (keeps the cleaning of the
-  // relevant columns against them a contraction)
-  if (big < neg2) return g2 <= 1e-4 * big * fmax(small, 0.0) + big * floor2;
-  return g2 <= big * (tol2 * fmax(small, 0.0) + floor2);
-}
-
-__device__ void eig8_warp0(JacobiShared& S, double tol2, double floor2, double neg2) {
-  const int lane = threadIdx.x;   // caller guarantees threadIdx.x < 32
-  // --- convergence test on the raw Gram matrix
-  double worst = 0.0;
-  for (int e = lane; e < 64; e += 32) {
-    const int i = e >> 3, j = e & 7;
-    if (i < j) {
-      const double a = S.gr[0][i][i], b = S.gr[0][j][j];
-      const double g2 = S.gr[0][i][j] * S.gr[0][i][j] + S.gi[0][i][j] * S.gi[0][i][j];
-      if (!pair_converged(a, b, g2, tol2, floor2, neg2)) worst = 1.0;
-    }
-  }
-  const unsigned any = __ballot_sync(0xffffffffu, worst > 0.0);
-  if (lane == 0) S.need = any ? 1 : 0;
-  if (!any) {
-    if (lane < 2) {
-      const int o = 4 * lane;
-      S.pmax[lane] = fmax(fmax(S.gr[0][o][o], S.gr[0][o + 1][o + 1]),
-                          fmax(S.gr[0][o + 2][o + 2], S.gr[0][o + 3][o + 3]));
-    }
-    __syncwarp();
-    return;
-  }
-
-  // exact Hermitian symmetry + V = I   (buffer 0)
-  for (int e = lane; e < 64; e += 32) {
-    const int i = e >> 3, j = e & 7;
-    S.vr[0][i][j] = (i == j) ? 1.0 : 0.0;
-    S.vi[0][i][j] = 0.0;
-  }
-  __syncwarp();
-  for (int e = lane; e < 64; e += 32) {
-    const int i = e >> 3, j = e & 7;
-    if (i > j) { S.gr[0][i][j] = S.gr[0][j][i]; S.gi[0][i][j] = -S.gi[0][j][i]; }
-    if (i == j) S.gi[0][i][j] = 0.0;
-  }
-  __syncwarp();
-
-  // Cyclic two-sided Jacobi, 4 disjoint rotations per round, all 64 entries of
-  // G' = R^H G R and V' = V R recomputed in ONE pass from the previous buffer
-  // (double buffering: two __syncwarp per round).  With pi(x) the partner of index x:
-  //   column op  T(x,y)  = al_y G[x][y] + be_y G[x][pi y]
-  //   row op     G'[x][y] = al_x T(x,y) + conj(be_x) T(pi x, y)
-  // where (al, be) = (c, -conj(se)) for the first index of a pair, (c, se) for the
-  // second, R = [[c, se], [-conj(se), c]].
-  int cur = 0;
-  for (int sweep = 0; sweep < INNER_SWEEPS; ++sweep) {
-    int rotated = 0;
-    for (int round = 0; round < 7; ++round) {
-      if (lane < 4) {
-        const int ka = lane, kb = 7 - lane;
-        int i = (ka == 0) ? 0 : 1 + ((ka - 1 + round) % 7);
-        int j = 1 + ((kb - 1 + round) % 7);
-        if (i > j) { const int t = i; i = j; j = t; }
-        const double a = S.gr[cur][i][i], b = S.gr[cur][j][j];
-        const double xr = S.gr[cur][i][j], xi = S.gi[cur][i][j];
-        const double mag2 = xr * xr + xi * xi;
-        double c = 1.0, sr_ = 0.0, si_ = 0.0;
-        int rot = 0;
-        if (mag2 > 0.0 && !pair_converged(a, b, mag2, 1e-28, 0.0625 * floor2, neg2)) {
-          // cos(2t) = |h|/r, c = sqrt((1+cos 2t)/2), s e^{i phi} = sign(h) g/(2 r c)
-          const double h = 0.5 * (b - a);
-          const double inv_r = rsqrt(h * h + mag2);
-          const double w = 0.5 + 0.5 * fabs(h) * inv_r;
-          const double ic = rsqrt(w);            // two rsqrt: no sqrt, no division
-          c = w * ic;
-          const double k = ((h >= 0.0) ? 0.5 : -0.5) * inv_r * ic;
-          sr_ = xr * k;
-          si_ = xi * k;
-          rot = 1;
-          rotated = 1;
-        }
-        S.partner[i] = j; S.partner[j] = i;
-        S.al[i] = c; S.al[j] = c;
-        S.ber[i] = -sr_; S.bei[i] = si_;     // -conj(se)
-        S.ber[j] = sr_;  S.bei[j] = si_;     //  se
-        S.rot[i] = rot; S.rot[j] = rot;
-      }
-      __syncwarp();
-      const int nxt = cur ^ 1;
-#pragma unroll
-      for (int rep = 0; rep < 2; ++rep) {
-        const int e = lane + 32 * rep;
-        const int x = e >> 3, y = e & 7;
-        const int px = S.partner[x], py = S.partner[y];
-        const double aly = S.al[y], byr = S.ber[y], byi = S.bei[y];
-        const double alx = S.al[x], bxr = S.ber[x], bxi = -S.bei[x];   // conj(be_x)
-        // T(x,y)
-        const double g00r = S.gr[cur][x][y], g00i = S.gi[cur][x][y];
-        const double g01r = S.gr[cur][x][py], g01i = S.gi[cur][x][py];
-        const double t0r = aly * g00r + (byr * g01r - byi * g01i);
-        const double t0i = aly * g00i + (byr * g01i + byi * g01r);
-        // T(pi x, y)
-        const double g10r = S.gr[cur][px][y], g10i = S.gi[cur][px][y];
-        const double g11r = S.gr[cur][px][py], g11i = S.gi[cur][px][py];
-        const double t1r = aly * g10r + (byr * g11r - byi * g11i);
-        const double t1i = aly * g10i + (byr * g11i + byi * g11r);
-        double nr = alx * t0r + (bxr * t1r - bxi * t1i);
-        double ni = alx * t0i + (bxr * t1i + bxi * t1r);
-        if (x == y) ni = 0.0;
-        if (y == px && S.rot[x]) { nr = 0.0; ni = 0.0; }   // annihilated entry
-        S.gr[nxt][x][y] = nr;
-        S.gi[nxt][x][y] = ni;
-        // V' = V R
-        const double v0r = S.vr[cur][x][y], v0i = S.vi[cur][x][y];
-        const double v1r = S.vr[cur][x][py], v1i = S.vi[cur][x][py];
-        S.vr[nxt][x][y] = aly * v0r + (byr * v1r - byi * v1i);
-        S.vi[nxt][x][y] = aly * v0i + (byr * v1i + byi * v1r);
-      }
-      __syncwarp();
-      cur = nxt;
-    }
-    if (__ballot_sync(0xffffffffu, rotated != 0) == 0u) break;
-  }
-  // --- sort eigenvectors by descending eigenvalue
-  if (lane < 8) {
-    const double lam = S.gr[cur][lane][lane];
-    int rank = 0;
-#pragma unroll
-    for (int o = 0; o < 8; ++o) {
-      const double lo = S.gr[cur][o][o];
-      if (lo > lam || (lo == lam && o < lane)) ++rank;
-    }
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      S.sr[r][rank] = S.vr[cur][r][lane];
-      S.si[r][rank] = S.vi[cur][r][lane];
-    }
-    if (rank == 0) S.pmax[0] = lam;     // largest -> panel I
-    if (rank == 4) S.pmax[1] = lam;     // fifth largest -> panel J
-  }
-  __syncwarp();
-}
-
-// [XI | XJ] <- [XI | XJ] * R  over `rows` rows, R = S.sr + i S.si (8x8), in place.
-template <bool GLOBAL>
-__device__ void apply8(cplx* XI, cplx* XJ, int rows, const JacobiShared& S) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int g = lane >> 2, t = lane & 3;
-  // B fragments: B[k][col] with k = kstep*4 + t, col = g
-  const double b0r = S.sr[t][g], b0i = S.si[t][g];
-  const double b1r = S.sr[4 + t][g], b1i = S.si[4 + t][g];
-  for (int base = warp * 8; base < rows; base += JW * 8) {
-    const int row = base + g;
-    cplx a0 = make_double2(0.0, 0.0), a1 = a0;
-    if (row < rows) {
-      a0 = ld_panel<GLOBAL>(XI + (size_t)row * PC + t);
-      a1 = ld_panel<GLOBAL>(XJ + (size_t)row * PC + t);
-    }
-    double dr0 = 0.0, dr1 = 0.0, di0 = 0.0, di1 = 0.0;
-    dmma884(dr0, dr1, a0.x, b0r);
-    dmma884(dr0, dr1, -a0.y, b0i);
-    dmma884(di0, di1, a0.x, b0i);
-    dmma884(di0, di1, a0.y, b0r);
-    dmma884(dr0, dr1, a1.x, b1r);
-    dmma884(dr0, dr1, -a1.y, b1i);
-    dmma884(di0, di1, a1.x, b1i);
-    dmma884(di0, di1, a1.y, b1r);
-    __syncwarp();
-    if (row < rows) {
-      // D[g][2t], D[g][2t+1]: columns 0..3 -> XI, 4..7 -> XJ
-      cplx* dst = (t < 2) ? (XI + (size_t)row * PC + 2 * t)
-                          : (XJ + (size_t)row * PC + 2 * (t - 2));
-      dst[0] = make_double2(dr0, di0);
-      dst[1] = make_double2(dr1, di1);
-    }
-  }
-}
-
-// global -> shared (L2 loads) by the threads [t0, t0+nt) of the CTA
-__device__ __forceinline__ void load_panel(cplx* dst, const cplx* src, int rows, int t0,
-                                           int nt) {
-  const int total = rows * PC;
-  for (int e = (int)threadIdx.x - t0; e < total; e += nt)
-    if (e >= 0) dst[e] = __ldcg(reinterpret_cast<const double2*>(src) + e);
-}
-__device__ __forceinline__ void store_panel(cplx* dst, const cplx* src, int rows) {
-  const int total = rows * PC;
-  for (int e = threadIdx.x; e < total; e += JT) dst[e] = src[e];
-}
 __device__ __forceinline__ int ld_acquire(const int* p) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -396,267 +130,634 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
 __device__ __forceinline__ void st_release(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void red_release_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ cplx ldcg(const cplx* p) {
+  return __ldcg(reinterpret_cast<const double2*>(p));
+}
+
+// grid-wide barrier on a monotonically increasing counter (cooperative launch
+// guarantees co-residency).  `epoch` counts the barriers this CTA has passed.
+__device__ __forceinline__ void grid_barrier(int* counter, int& epoch) {
+  __syncthreads();
+  ++epoch;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    red_release_add(counter, 1);
+    const int target = epoch * (int)gridDim.x;
+    while (ld_acquire(counter) < target) {}
+  }
+  __syncthreads();
+}
+
+// A pair (i, j) counts as orthogonal when
+//   |g_ij| <= sqrt(max(a,b)) * (tol*sqrt(min(a,b)) + floor),  floor = kappa*eps*||X||_F:
+// the accumulated rotations are accurate in the ABSOLUTE sense (eps*||X||), so columns
+// that have sunk to the rounding floor are left alone.  (threshold combined in
+// quadrature: no sqrt on the critical path.)  Pairs whose two columns are both
+// NEGLIGIBLE (norm^2 < neg2 = (1e-2*eps*||X||_F)^2) are only orthogonalised loosely:
+// such columns are discarded by the truncation rule whatever their mutual angles, and
+// the tail norm only needs the Frobenius norm of their block, which is rotation
+// invariant.  (neg2 = 0 when no truncation is requested.)
+__device__ __forceinline__ bool pair_converged(double a, double b, double g2,
+                                               double tol2, double floor2, double neg2) {
+  const double big = fmax(a, b), small = fmin(a, b);
+  if (big <= 0.0) return true;
+  if (big < neg2) return g2 <= 1e-4 * big * fmax(small, 0.0) + big * floor2;
+  return g2 <= big * (tol2 * fmax(small, 0.0) + floor2);
+}
+
+// Round-robin partner tables ---------------------------------------------------------
+// outer tournament over nb blocks (nb even), stage in [0, nb-1)
+__device__ __forceinline__ void outer_pair(int idx, int stage, int nb, int& pa, int& pb) {
+  const int ka = idx, kb = nb - 1 - idx;
+  pa = (ka == 0) ? 0 : 1 + ((ka - 1 + stage) % (nb - 1));
+  pb = 1 + ((kb - 1 + stage) % (nb - 1));
+  if (pa > pb) { const int t = pa; pa = pb; pb = t; }
+}
+// inner ordering over 32 columns, 31 rounds of 16 disjoint pairs: rounds 0..15 pair
+// every column of the first block with every column of the second (the pairs that have
+// never met), rounds 16..30 are two simultaneous 16-player tournaments inside the blocks.
+__device__ __forceinline__ void inner_pair(int round, int k, int& i, int& j) {
+  if (round < BC) {
+    i = k;
+    j = BC + ((k + round) & (BC - 1));
+  } else {
+    const int st = round - BC;          // 0..14
+    const int half = k >> 3, kk = k & 7;
+    const int ka = kk, kb = BC - 1 - kk;
+    int a = (ka == 0) ? 0 : 1 + ((ka - 1 + st) % (BC - 1));
+    int b = 1 + ((kb - 1 + st) % (BC - 1));
+    if (a > b) { const int t = a; a = b; b = t; }
+    i = half * BC + a;
+    j = half * BC + b;
+  }
+}
+
+struct InnerShared {
+  double gr[PB][GP], gi[PB][GP];   // Hermitian working matrix
+  double jr[PB][GP], ji[PB][GP];   // accumulated rotations
+  double rc[BC], rsr[BC], rsi[BC]; // per pair of the round: c, s e^{i phi}
+  int rp[BC], rq[BC], ract[BC];
+  int order[PB];
+  int need, flag;
+};
+
+// One cyclic sweep of two-sided Jacobi on the 32x32 Hermitian matrix S.gr + i S.gi,
+// accumulating J.  All JT threads participate.  Thread (a, b), a, b in [0,16), owns the
+// 2x2 block (rows of pair a) x (columns of pair b): G' = R_a^H G R_b touches only its
+// own four entries, so the update is in place.  Threads 256.. own two rows of J each.
+// R = [[c, se], [-conj(se), c]] acting on columns (p, q).
+__device__ void inner_sweep(InnerShared& S, double floor2, double neg2) {
+  const int t = threadIdx.x;
+  for (int round = 0; round < PB - 1; ++round) {
+    int act = 0;
+    if (t < BC) {
+      int i, j;
+      inner_pair(round, t, i, j);
+      const double a = S.gr[i][i], b = S.gr[j][j];
+      const double xr = S.gr[i][j], xi = S.gi[i][j];
+      const double mag2 = xr * xr + xi * xi;
+      double c = 1.0, sr_ = 0.0, si_ = 0.0;
+      if (mag2 > 0.0 && !pair_converged(a, b, mag2, 1e-28, 0.0625 * floor2, neg2)) {
+        // cos(2t) = |h|/r, c = sqrt((1+cos 2t)/2), s e^{i phi} = sign(h) g/(2 r c)
+        const double h = 0.5 * (b - a);
+        const double inv_r = rsqrt(h * h + mag2);
+        const double w = 0.5 + 0.5 * fabs(h) * inv_r;
+        const double ic = rsqrt(w);            // two rsqrt: no sqrt, no division
+        c = w * ic;
+        const double k = ((h >= 0.0) ? 0.5 : -0.5) * inv_r * ic;
+        sr_ = xr * k;
+        si_ = xi * k;
+        act = 1;
+      }
+      S.rp[t] = i; S.rq[t] = j; S.ract[t] = act;
+      S.rc[t] = c; S.rsr[t] = sr_; S.rsi[t] = si_;
+    }
+    if (!__syncthreads_or(act)) continue;
+    if (t < 256) {
+      const int a = t >> 4, b = t & 15;
+      const int aa = S.ract[a], ab = S.ract[b];
+      if (aa | ab) {
+        const int pa = S.rp[a], qa = S.rq[a], pb = S.rp[b], qb = S.rq[b];
+        const double ca = S.rc[a], sar = S.rsr[a], sai = S.rsi[a];
+        const double cb = S.rc[b], sbr = S.rsr[b], sbi = S.rsi[b];
+        const double g00r = S.gr[pa][pb], g00i = S.gi[pa][pb];
+        const double g01r = S.gr[pa][qb], g01i = S.gi[pa][qb];
+        const double g10r = S.gr[qa][pb], g10i = S.gi[qa][pb];
+        const double g11r = S.gr[qa][qb], g11i = S.gi[qa][qb];
+        // column op: T[:,0] = cb g[:,0] - conj(seb) g[:,1] ; T[:,1] = seb g[:,0] + cb g[:,1]
+        const double t00r = cb * g00r - (sbr * g01r + sbi * g01i);
+        const double t00i = cb * g00i - (sbr * g01i - sbi * g01r);
+        const double t01r = cb * g01r + (sbr * g00r - sbi * g00i);
+        const double t01i = cb * g01i + (sbr * g00i + sbi * g00r);
+        const double t10r = cb * g10r - (sbr * g11r + sbi * g11i);
+        const double t10i = cb * g10i - (sbr * g11i - sbi * g11r);
+        const double t11r = cb * g11r + (sbr * g10r - sbi * g10i);
+        const double t11i = cb * g11i + (sbr * g10i + sbi * g10r);
+        // row op: G'[0,:] = ca T[0,:] - sea T[1,:] ; G'[1,:] = conj(sea) T[0,:] + ca T[1,:]
+        double n00r = ca * t00r - (sar * t10r - sai * t10i);
+        double n00i = ca * t00i - (sar * t10i + sai * t10r);
+        double n01r = ca * t01r - (sar * t11r - sai * t11i);
+        double n01i = ca * t01i - (sar * t11i + sai * t11r);
+        double n10r = ca * t10r + (sar * t00r + sai * t00i);
+        double n10i = ca * t10i + (sar * t00i - sai * t00r);
+        double n11r = ca * t11r + (sar * t01r + sai * t01i);
+        double n11i = ca * t11i + (sar * t01i - sai * t01r);
+        if (a == b) {            // diagonal block: real diagonal, annihilated off-diagonal
+          n00i = 0.0; n11i = 0.0;
+          n01r = 0.0; n01i = 0.0; n10r = 0.0; n10i = 0.0;
+        }
+        S.gr[pa][pb] = n00r; S.gi[pa][pb] = n00i;
+        S.gr[pa][qb] = n01r; S.gi[pa][qb] = n01i;
+        S.gr[qa][pb] = n10r; S.gi[qa][pb] = n10i;
+        S.gr[qa][qb] = n11r; S.gi[qa][qb] = n11i;
+      }
+    } else {
+      const int u = t - 256;
+      const int b = u & 15, r0 = (u >> 4) * 2;
+      if (S.ract[b]) {
+        const int pb = S.rp[b], qb = S.rq[b];
+        const double cb = S.rc[b], sbr = S.rsr[b], sbi = S.rsi[b];
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          const int r = r0 + rr;
+          const double v0r = S.jr[r][pb], v0i = S.ji[r][pb];
+          const double v1r = S.jr[r][qb], v1i = S.ji[r][qb];
+          S.jr[r][pb] = cb * v0r - (sbr * v1r + sbi * v1i);
+          S.ji[r][pb] = cb * v0i - (sbr * v1i - sbi * v1r);
+          S.jr[r][qb] = cb * v1r + (sbr * v0r - sbi * v0i);
+          S.ji[r][qb] = cb * v1i + (sbr * v0i + sbi * v0r);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// Partial Gram matrix of `rows` rows of the staged tile ([row][32] complex) into
+// registers: thread (kh, oi, oj) accumulates the 2x2 block rows (2oi, 2oi+1), columns
+// (2oj, 2oj+1) of T^H T over the rows r = kh (mod 2).
+__device__ __forceinline__ void gram_accumulate(const cplx* tile, int rows, double acc[8]) {
+  const int t = threadIdx.x;
+  const int kh = t >> 8, oi = (t >> 4) & 15, oj = t & 15;
+  for (int r = kh; r < rows; r += 2) {
+    const cplx* row = tile + (size_t)r * PB;
+    const cplx a0 = row[2 * oi], a1 = row[2 * oi + 1];
+    const cplx b0 = row[2 * oj], b1 = row[2 * oj + 1];
+    // conj(a) * b
+    acc[0] = fma(a0.x, b0.x, acc[0]); acc[0] = fma(a0.y, b0.y, acc[0]);
+    acc[1] = fma(a0.x, b0.y, acc[1]); acc[1] = fma(-a0.y, b0.x, acc[1]);
+    acc[2] = fma(a0.x, b1.x, acc[2]); acc[2] = fma(a0.y, b1.y, acc[2]);
+    acc[3] = fma(a0.x, b1.y, acc[3]); acc[3] = fma(-a0.y, b1.x, acc[3]);
+    acc[4] = fma(a1.x, b0.x, acc[4]); acc[4] = fma(a1.y, b0.y, acc[4]);
+    acc[5] = fma(a1.x, b0.y, acc[5]); acc[5] = fma(-a1.y, b0.x, acc[5]);
+    acc[6] = fma(a1.x, b1.x, acc[6]); acc[6] = fma(a1.y, b1.y, acc[6]);
+    acc[7] = fma(a1.x, b1.y, acc[7]); acc[7] = fma(-a1.y, b1.x, acc[7]);
+  }
+}
+
+// out[row][:] = tile[row][:] * J  for `rows` rows; NR rows per thread.  Output columns
+// 0..15 go to block A, 16..31 to block B (both [row][16] in global memory).
+template <int NR>
+__device__ __forceinline__ void apply_tile(const cplx* tile, int rows, const cplx* sj,
+                                           cplx* outA, cplx* outB) {
+  const int t = threadIdx.x;
+  const int tx = t & 15, ty = t >> 4;     // 16 column pairs x 32 row groups
+  for (int rbase = ty * NR; rbase < rows; rbase += 32 * NR) {
+    double ar[NR][2], ai[NR][2];
+#pragma unroll
+    for (int x = 0; x < NR; ++x) { ar[x][0] = ar[x][1] = ai[x][0] = ai[x][1] = 0.0; }
+#pragma unroll 4
+    for (int k = 0; k < PB; ++k) {
+      const cplx j0 = sj[k * PB + 2 * tx], j1 = sj[k * PB + 2 * tx + 1];
+#pragma unroll
+      for (int x = 0; x < NR; ++x) {
+        const int r = (rbase + x < rows) ? rbase + x : rows - 1;
+        const cplx v = tile[(size_t)r * PB + k];
+        ar[x][0] = fma(v.x, j0.x, ar[x][0]); ar[x][0] = fma(-v.y, j0.y, ar[x][0]);
+        ai[x][0] = fma(v.x, j0.y, ai[x][0]); ai[x][0] = fma(v.y, j0.x, ai[x][0]);
+        ar[x][1] = fma(v.x, j1.x, ar[x][1]); ar[x][1] = fma(-v.y, j1.y, ar[x][1]);
+        ai[x][1] = fma(v.x, j1.y, ai[x][1]); ai[x][1] = fma(v.y, j1.x, ai[x][1]);
+      }
+    }
+#pragma unroll
+    for (int x = 0; x < NR; ++x) {
+      const int r = rbase + x;
+      if (r < rows) {
+        cplx* dst = (tx < 8) ? (outA + (size_t)r * BC + 2 * tx)
+                             : (outB + (size_t)r * BC + 2 * (tx - 8));
+        dst[0] = make_double2(ar[x][0], ai[x][0]);
+        dst[1] = make_double2(ar[x][1], ai[x][1]);
+      }
+    }
+  }
+}
+
+// global -> shared: rows [r0, r0+rows) of blocks A and B into tile[row][32]
+__device__ __forceinline__ void load_tile(cplx* tile, const cplx* gA, const cplx* gB,
+                                          int rows) {
+  const int total = rows * PB;
+  for (int e = threadIdx.x; e < total; e += JT) {
+    const int r = e >> 5, c = e & 31;
+    const cplx* src = (c < BC) ? (gA + (size_t)r * BC + c) : (gB + (size_t)r * BC + (c - BC));
+    tile[e] = ldcg(src);
+  }
+}
 
 // ------------------------------------------------------------------ Jacobi kernel
-// Persistent cooperative kernel.  Stage-to-stage hand-over of panels is point to point:
-// ready[panel] counts the stages completed on that panel (release/acquire through L2),
-// so a CTA only waits for the two CTAs that produced its inputs, not for the grid.
-// One grid.sync per SWEEP carries the convergence vote.
+// Persistent cooperative kernel: load -> sweeps -> column norms -> rank rule.
 __global__ void __launch_bounds__(JT, 1)
-jacobi_kernel(cplx* __restrict__ xp, cplx* __restrict__ wp, int p, int q, int nb,
-              int stage_x, int stage_w, double tol, double neg_rel,
-              int* __restrict__ flags, int* __restrict__ ready,
-              double* __restrict__ pn, Header* __restrict__ hdr) {
+jacobi_kernel(const cplx* __restrict__ theta, long long rs, long long cs,
+              cplx* __restrict__ y, cplx* __restrict__ gpart, cplx* __restrict__ jbuf,
+              int* __restrict__ ctrl, double* __restrict__ sig2,
+              double* __restrict__ sval, int* __restrict__ perm,
+              Header* __restrict__ hdr, int32_t* __restrict__ info, int p, int q, int nb,
+              int R, int RS, int SE, int transposed, int minmn, double tol, double eps,
+              double neg_rel) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
-  __shared__ JacobiShared S;
-  cg::grid_group grid = cg::this_grid();
+  __shared__ InnerShared S;
+  __shared__ double s_red[JT / 32];
+  cplx* tile = reinterpret_cast<cplx*>(dyn_smem);          // [CHUNK][32]
+  cplx* sj = tile + (size_t)CHUNK_ROWS * PB;               // [32][32] rotation to apply
+  cplx* sg = sj + PB * PB;                                 // [32][32] scratch (Gram halves)
 
-  cplx* sXI = reinterpret_cast<cplx*>(dyn_smem);
-  cplx* sXJ = sXI + (stage_x ? (size_t)p * PC : 0);
-  cplx* sWI = sXJ + (stage_x ? (size_t)p * PC : 0);
-  cplx* sWJ = sWI + (stage_w ? (size_t)q * PC : 0);
-  const int npairs = nb / 2;
-  const size_t xpan = (size_t)p * PC, wpan = (size_t)q * PC;
+  const int T = p + q;
+  const int S_slots = nb / 2;
+  int* bar = ctrl;
+  int* flags = ctrl + 2;
+  int* ready = flags + NFLAGS;
+  int* cnt = ready + (size_t)nb * R;
+  int* flagj = cnt + 2 * S_slots;
+  int epoch = 0;
+  const int t = threadIdx.x;
+  const size_t blk_elems = (size_t)T * BC;
 
-  int sweeps_done = 0;
-  int total_rot = 0;
-  int status = 1;   // 1 = not converged
-  const double fro = sqrt(hdr->fro2);
   long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long tq = clock64();
 #define PHASE(k) { const long long tn_ = clock64(); pc[k] += tn_ - tq; tq = tn_; }
+
+  // ---- load: Y = [X ; I], ||X||_F^2
+  {
+    double local = 0.0;
+    const long long total = (long long)nb * T * BC;
+    for (long long e = blockIdx.x * (long long)JT + t; e < total;
+         e += (long long)gridDim.x * JT) {
+      const int c16 = (int)(e % BC);
+      const long long u = e / BC;
+      const int row = (int)(u % T);
+      const int blk = (int)(u / T);
+      const int col = blk * BC + c16;
+      cplx v = make_double2(0.0, 0.0);
+      if (row < p) {
+        if (col < q) {
+          if (!transposed) {
+            v = theta[row * rs + col * cs];
+          } else {           // X = theta^H : X[row][col] = conj(theta[col][row])
+            v = theta[col * rs + row * cs];
+            v.y = -v.y;
+          }
+        }
+        local = fma(v.x, v.x, local);
+        local = fma(v.y, v.y, local);
+      } else if (row - p == col) {
+        v.x = 1.0;
+      }
+      y[e] = v;
+    }
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((t & 31) == 0) s_red[t >> 5] = local;
+    __syncthreads();
+    if (t == 0) {
+      double tot = 0.0;
+      for (int w = 0; w < JT / 32; ++w) tot += s_red[w];
+      if (tot != 0.0) atomicAdd(&hdr->fro2, tot);
+    }
+    __threadfence();
+  }
+  grid_barrier(bar, epoch);
+  const double fro = sqrt(__ldcg(&hdr->fro2));
+  PHASE(1)
+
+  const int r_slice = blockIdx.x % R;
+  const int s_first = blockIdx.x / R;
+  const int row0 = r_slice * RS;
+  const int nrows = min(RS, T - row0);            // rows of this slice (> 0 by layout)
+  const int xrows = max(0, min(nrows, p - row0)); // of which X rows (the Gram part)
+  const bool single_chunk = nrows <= CHUNK_ROWS;
+  const bool leader = (r_slice == 0);
+
+  int sweeps_done = 0, total_rot = 0, status = 1;
+  const double tol2 = tol * tol;
+  const double neg2 = (neg_rel * fro) * (neg_rel * fro);
   for (int sweep = 0; sweep < MAX_SWEEPS; ++sweep) {
     int my_rot = 0;
-    // absolute floor: 8 eps ||X||_F, doubled every sweep after FLOOR_GROW_AFTER so that the
-    // iteration always terminates
+    // absolute floor: 8 eps ||X||_F, doubled every sweep after FLOOR_GROW_AFTER so that
+    // the iteration always terminates
     double kappa = 8.0;
     for (int k = FLOOR_GROW_AFTER; k < sweep; ++k) kappa *= 2.0;
     const double floor_ = kappa * 2.220446049250313e-16 * fro;
-    const double floor2 = floor_ * floor_, tol2 = tol * tol;
-    const double neg2 = (neg_rel * fro) * (neg_rel * fro);
+    const double floor2 = floor_ * floor_;
     for (int stage = 0; stage < nb - 1; ++stage) {
-      const int gstage = sweep * (nb - 1) + stage;
-      for (int idx = blockIdx.x; idx < npairs; idx += gridDim.x) {
-        const int ka = idx, kb = nb - 1 - idx;
-        int pa = (ka == 0) ? 0 : 1 + ((ka - 1 + stage) % (nb - 1));
-        int pb = 1 + ((kb - 1 + stage) % (nb - 1));
-        if (pa > pb) { const int t = pa; pa = pb; pb = t; }
-        cplx* gXI = xp + pa * xpan;
-        cplx* gXJ = xp + pb * xpan;
-        cplx* gWI = wp + pa * wpan;
-        cplx* gWJ = wp + pb * wpan;
-        // wait until both input panels have finished the previous stage
-        if (threadIdx.x == 0) {
-          while (ld_acquire(ready + pa) < gstage) {}
-          while (ld_acquire(ready + pb) < gstage) {}
-          // both panels already below the negligible level: skip the stage for them
-          S.skip = 0;   // (panel-level skipping disabled: see pair_converged)
+      const int g = sweep * (nb - 1) + stage;
+      const int par = g & 1;
+      for (int s = s_first; s < S_slots; s += SE) {
+        int pa, pb;
+        outer_pair(s, stage, nb, pa, pb);
+        cplx* gA = y + pa * blk_elems + (size_t)row0 * BC;
+        cplx* gB = y + pb * blk_elems + (size_t)row0 * BC;
+        // 1. wait until both input blocks (this slice) have finished the previous stage
+        if (t == 0) {
+          while (ld_acquire(ready + pa * R + r_slice) < g) {}
+          while (ld_acquire(ready + pb * R + r_slice) < g) {}
         }
         __syncthreads();
         PHASE(0)
-        if (S.skip) {
+        // 2./3. stage the slice, partial Gram of the X rows
+        double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int c0 = 0; c0 < nrows; c0 += CHUNK_ROWS) {
+          const int crow = min(CHUNK_ROWS, nrows - c0);
+          if (c0 > 0) __syncthreads();
+          load_tile(tile, gA + (size_t)c0 * BC, gB + (size_t)c0 * BC, crow);
           __syncthreads();
-          if (threadIdx.x == 0) {
-            st_release(ready + pa, gstage + 1);
-            st_release(ready + pb, gstage + 1);
+          const int xr = max(0, min(crow, xrows - c0));
+          if (xr > 0) gram_accumulate(tile, xr, acc);
+        }
+        PHASE(1)
+        cplx* my_part = gpart + ((size_t)(par * S_slots + s) * R + r_slice) * (PB * PB);
+        if (xrows > 0) {
+          const int kh = t >> 8, oi = (t >> 4) & 15, oj = t & 15;
+          if (kh == 1) {
+            cplx* d = sg + (2 * oi) * PB + 2 * oj;
+            d[0] = make_double2(acc[0], acc[1]); d[1] = make_double2(acc[2], acc[3]);
+            d[PB] = make_double2(acc[4], acc[5]); d[PB + 1] = make_double2(acc[6], acc[7]);
           }
-          ++pc[7];
-          continue;
-        }
-        if (stage_x) {
-          load_panel(sXI, gXI, p, 0, JT);
-          load_panel(sXJ, gXJ, p, 0, JT);
           __syncthreads();
-          PHASE(1)
-          gram8<false>(sXI, sXJ, p, S);
-        } else {
-          gram8<true>(gXI, gXJ, p, S);
+          if (kh == 0) {
+            const cplx* d = sg + (2 * oi) * PB + 2 * oj;
+            cplx* o = my_part + (2 * oi) * PB + 2 * oj;
+            o[0] = make_double2(acc[0] + d[0].x, acc[1] + d[0].y);
+            o[1] = make_double2(acc[2] + d[1].x, acc[3] + d[1].y);
+            o[PB] = make_double2(acc[4] + d[PB].x, acc[5] + d[PB].y);
+            o[PB + 1] = make_double2(acc[6] + d[PB + 1].x, acc[7] + d[PB + 1].y);
+          }
+          __threadfence();
         }
+        __syncthreads();
+        if (t == 0) red_release_add(cnt + par * S_slots + s, 1);
         PHASE(2)
-        if (threadIdx.x < 32) {
-          eig8_warp0(S, tol2, floor2, neg2);
-        } else if (stage_w) {      // overlap: the other warps fetch the W panels
-          load_panel(sWI, gWI, q, 32, JT - 32);
-          load_panel(sWJ, gWJ, q, 32, JT - 32);
-        }
-        __syncthreads();
-        PHASE(3)
-        if (S.need) {
-          ++my_rot;
-          if (stage_x) apply8<false>(sXI, sXJ, p, S); else apply8<true>(gXI, gXJ, p, S);
-          if (stage_w) apply8<false>(sWI, sWJ, q, S); else apply8<true>(gWI, gWJ, q, S);
+        // 4. leader: reduce, decide, solve, publish J
+        int need;
+        cplx* my_j = jbuf + (size_t)(par * S_slots + s) * (PB * PB);
+        if (leader) {
+          if (t == 0) {
+            const int want = (g / 2 + 1) * R;     // cnt is cumulative per parity
+            while (ld_acquire(cnt + par * S_slots + s) < want) {}
+          }
           __syncthreads();
-          PHASE(4)
-          if (stage_x) { store_panel(gXI, sXI, p); store_panel(gXJ, sXJ, p); }
-          if (stage_w) { store_panel(gWI, sWI, q); store_panel(gWJ, sWJ, q); }
+          const int rx = (p + RS - 1) / RS;       // slices that hold X rows
+          const cplx* base = gpart + (size_t)(par * S_slots + s) * R * (PB * PB);
+          for (int e = t; e < PB * PB; e += JT) {
+            double sr_ = 0.0, si_ = 0.0;
+            for (int rr = 0; rr < rx; ++rr) {
+              const cplx v = ldcg(base + (size_t)rr * (PB * PB) + e);
+              sr_ += v.x; si_ += v.y;
+            }
+            const int i = e >> 5, j = e & 31;
+            S.gr[i][j] = sr_; S.gi[i][j] = si_;
+            S.jr[i][j] = (i == j) ? 1.0 : 0.0; S.ji[i][j] = 0.0;
+          }
+          __syncthreads();
+          // exact Hermitian symmetry (upper triangle wins), convergence test
+          int viol = 0;
+          for (int e = t; e < PB * PB; e += JT) {
+            const int i = e >> 5, j = e & 31;
+            if (i < j) {
+              const double a = S.gr[i][i], b = S.gr[j][j];
+              const double xr = S.gr[i][j], xi = S.gi[i][j];
+              if (!pair_converged(a, b, xr * xr + xi * xi, tol2, floor2, neg2)) viol = 1;
+            }
+          }
+          need = __syncthreads_or(viol);
+          if (need) {
+            for (int e = t; e < PB * PB; e += JT) {
+              const int i = e >> 5, j = e & 31;
+              if (i > j) { S.gr[i][j] = S.gr[j][i]; S.gi[i][j] = -S.gi[j][i]; }
+              if (i == j) S.gi[i][j] = 0.0;
+            }
+            __syncthreads();
+            inner_sweep(S, floor2, neg2);
+            // sort columns by descending norm^2 (the diagonal of the rotated Gram matrix)
+            if (t < PB) {
+              const double lam = S.gr[t][t];
+              int rank = 0;
+#pragma unroll 8
+              for (int o = 0; o < PB; ++o) {
+                const double lo = S.gr[o][o];
+                if (lo > lam || (lo == lam && o < t)) ++rank;
+              }
+              S.order[rank] = t;
+            }
+            __syncthreads();
+            for (int e = t; e < PB * PB; e += JT) {
+              const int i = e >> 5, j = e & 31;
+              const int src = S.order[j];
+              const cplx v = make_double2(S.jr[i][src], S.ji[i][src]);
+              sj[e] = v;
+              my_j[e] = v;
+            }
+            __threadfence();
+            ++my_rot;
+          }
+          __syncthreads();
+          if (t == 0) st_release(flagj + s, 2 * (g + 1) + (need ? 1 : 0));
+        } else {
+          if (t == 0) {
+            int f;
+            while ((f = ld_acquire(flagj + s)) < 2 * (g + 1)) {}
+            S.flag = f;
+          }
+          __syncthreads();
+          need = S.flag & 1;
+          if (need) {
+            for (int e = t; e < PB * PB; e += JT) sj[e] = ldcg(my_j + e);
+            __syncthreads();
+          }
+        }
+        PHASE(3)
+        // 5. apply J to this slice of [X ; W]
+        if (need) {
+          for (int c0 = 0; c0 < nrows; c0 += CHUNK_ROWS) {
+            const int crow = min(CHUNK_ROWS, nrows - c0);
+            if (!single_chunk) {
+              __syncthreads();
+              load_tile(tile, gA + (size_t)c0 * BC, gB + (size_t)c0 * BC, crow);
+              __syncthreads();
+            }
+            cplx* oA = gA + (size_t)c0 * BC;
+            cplx* oB = gB + (size_t)c0 * BC;
+            if (crow <= 32) apply_tile<1>(tile, crow, sj, oA, oB);
+            else if (crow <= 64) apply_tile<2>(tile, crow, sj, oA, oB);
+            else apply_tile<4>(tile, crow, sj, oA, oB);
+          }
+          __threadfence();
         }
         __syncthreads();
-        if (threadIdx.x == 0) {   // release is cumulative over the CTA barrier above
-          pn[pa] = S.pmax[0];
-          pn[pb] = S.pmax[1];
-          st_release(ready + pa, gstage + 1);
-          st_release(ready + pb, gstage + 1);
+        if (t == 0) {   // release is cumulative over the CTA barrier above
+          st_release(ready + pa * R + r_slice, g + 1);
+          st_release(ready + pb * R + r_slice, g + 1);
         }
-        PHASE(5)
+        PHASE(4)
         ++pc[7];
       }
     }
-    // convergence vote: flags[sweep] counts pairs rotated in this sweep
-    if (threadIdx.x == 0 && my_rot) atomicAdd(&flags[sweep], my_rot);
-    grid.sync();
-    const int rot = *((volatile int*)&flags[sweep]);
-    PHASE(6)
+    // convergence vote: flags[sweep] counts the stages rotated in this sweep
+    if (t == 0 && my_rot) atomicAdd(&flags[sweep], my_rot);
+    grid_barrier(bar, epoch);
+    const int rot = __ldcg(&flags[sweep]);
+    PHASE(5)
     total_rot += rot;
     sweeps_done = sweep + 1;
     if (rot == 0) { status = 0; break; }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    hdr->sweeps = sweeps_done;
-    hdr->status = status;
-    hdr->rotations = total_rot;
-    for (int k = 0; k < 8; ++k) hdr->phase_cycles[k] = pc[k];
+
+  // ---- sigma_j^2 = ||X[:, j]||^2 : one warp per column block, all CTAs
+  {
+    const int lane = t & 31, warp = t >> 5;
+    for (int blk = blockIdx.x * (JT / 32) + warp; blk < nb; blk += gridDim.x * (JT / 32)) {
+      const cplx* X = y + blk * blk_elems;
+      const int c = lane & 15, half = lane >> 4;
+      double acc = 0.0;
+      for (int row = half; row < p; row += 2) {
+        const cplx v = ldcg(X + (size_t)row * BC + c);
+        acc = fma(v.x, v.x, acc);
+        acc = fma(v.y, v.y, acc);
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+      if (lane < 16) sig2[blk * BC + c] = acc;
+    }
+    __threadfence();
+  }
+  grid_barrier(bar, epoch);
+  if (blockIdx.x != 0) return;
+
+  // ---- CTA 0: sort (descending), tail-norm rule, publish keep
+  {
+    const int ncols = nb * BC;
+    int npow = 1;
+    while (npow < ncols) npow <<= 1;
+    double* key = reinterpret_cast<double*>(dyn_smem);
+    int* idx = reinterpret_cast<int*>(key + npow);
+    for (int e = t; e < npow; e += JT) {
+      key[e] = (e < ncols) ? __ldcg(sig2 + e) : -1.0;   // padding sorts last
+      idx[e] = e;
+    }
+    __syncthreads();
+    for (int k = 2; k <= npow; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int e = t; e < npow; e += JT) {
+          const int o = e ^ j;
+          if (o > e) {
+            const bool desc = ((e & k) == 0);
+            const double a = key[e], b = key[o];
+            const int ia = idx[e], ib = idx[o];
+            const bool a_first = (a > b) || (a == b && ia < ib);
+            if (desc ? !a_first : a_first) {
+              key[e] = b; key[o] = a;
+              idx[e] = ib; idx[o] = ia;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    for (int e = t; e < q; e += JT) {
+      sval[e] = sqrt(fmax(key[e], 0.0));
+      perm[e] = idx[e];
+    }
+    __syncthreads();
+    if (t == 0) {
+      // keep = #{ j : sqrt(sum_{i>=j} s_i^2) > eps*s_0 }, accumulated from the
+      // smallest value upwards exactly like numpy.cumsum(s[::-1]**2).
+      const int r = minmn;            // number of genuine singular values
+      int keep = r;
+      const double s0 = (r > 0) ? sqrt(fmax(key[0], 0.0)) : 0.0;
+      if (eps >= 0.0) {
+        const double thr = eps * s0;
+        double tail = 0.0;
+        keep = 0;
+        for (int j = r - 1; j >= 0; --j) {
+          const double s = sqrt(fmax(key[j], 0.0));
+          tail += s * s;
+          if (sqrt(tail) > thr) ++keep;
+        }
+      }
+      PHASE(6)
+      hdr->keep = keep;
+      hdr->s0 = s0;
+      hdr->sweeps = sweeps_done;
+      hdr->status = status;
+      hdr->rotations = total_rot;
+      for (int k = 0; k < 8; ++k) hdr->phase_cycles[k] = pc[k];
+      info[0] = keep;
+      info[1] = sweeps_done;
+      info[2] = status;
+      info[3] = total_rot;
+    }
   }
 #undef PHASE
 }
 
-// ------------------------------------------------------------------ finalize
-// sigma_j^2 = ||X[:, j]||^2 ; one warp per panel.
-__global__ void colnorm_kernel(const cplx* __restrict__ xp, int p, int nb,
-                               double* __restrict__ sig2) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= nb) return;
-  const cplx* X = xp + (size_t)warp * p * PC;
-  double acc[PC] = {0.0, 0.0, 0.0, 0.0};
-  for (int row = lane; row < p; row += 32) {
-#pragma unroll
-    for (int c = 0; c < PC; ++c) {
-      const cplx v = X[(size_t)row * PC + c];
-      acc[c] = fma(v.x, v.x, acc[c]);
-      acc[c] = fma(v.y, v.y, acc[c]);
-    }
-  }
-#pragma unroll
-  for (int c = 0; c < PC; ++c) {
-    double v = acc[c];
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) sig2[warp * PC + c] = v;
-  }
-}
-
-// Sort (descending), apply the tail-norm rule, publish keep.  One CTA.
-__global__ void __launch_bounds__(1024)
-rank_kernel(const double* __restrict__ sig2, int ncols, int q, int minmn,
-            double eps, double* __restrict__ sval, int* __restrict__ perm,
-            Header* __restrict__ hdr, int32_t* __restrict__ info) {
-  extern __shared__ __align__(16) unsigned char dyn_smem[];
-  int npow = 1;
-  while (npow < ncols) npow <<= 1;
-  double* key = reinterpret_cast<double*>(dyn_smem);
-  int* idx = reinterpret_cast<int*>(key + npow);
-  for (int e = threadIdx.x; e < npow; e += blockDim.x) {
-    // padded / dummy columns sort to the end
-    key[e] = (e < ncols) ? sig2[e] : -1.0;   // zero padding columns sort last
-    idx[e] = e;
-  }
-  __syncthreads();
-  // bitonic sort, descending
-  for (int k = 2; k <= npow; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int e = threadIdx.x; e < npow; e += blockDim.x) {
-        const int o = e ^ j;
-        if (o > e) {
-          const bool desc = ((e & k) == 0);
-          const double a = key[e], b = key[o];
-          const int ia = idx[e], ib = idx[o];
-          const bool a_first = (a > b) || (a == b && ia < ib);
-          if (desc ? !a_first : a_first) {
-            key[e] = b; key[o] = a;
-            idx[e] = ib; idx[o] = ia;
-          }
-        }
-      }
-      __syncthreads();
-    }
-  }
-  for (int e = threadIdx.x; e < q; e += blockDim.x) {
-    sval[e] = sqrt(fmax(key[e], 0.0));
-    perm[e] = idx[e];
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    // keep = #{ j : sqrt(sum_{i>=j} s_i^2) > eps*s_0 }, accumulated from the
-    // smallest value upwards exactly like numpy.cumsum(s[::-1]**2).
-    const int r = minmn;            // number of genuine singular values
-    int keep = r;
-    const double s0 = (r > 0) ? sqrt(fmax(key[0], 0.0)) : 0.0;
-    if (eps >= 0.0) {
-      const double thr = eps * s0;
-      double tail = 0.0;
-      keep = 0;
-      for (int j = r - 1; j >= 0; --j) {
-        const double s = sqrt(fmax(key[j], 0.0));
-        tail += s * s;
-        if (sqrt(tail) > thr) ++keep;
-      }
-    }
-    hdr->keep = keep;
-    hdr->s0 = s0;
-    info[0] = keep;
-    info[1] = hdr->sweeps;
-    info[2] = hdr->status;
-    info[3] = hdr->rotations;
-  }
-}
-
 // ------------------------------------------------------------------ emit
-__global__ void emit_kernel(const cplx* __restrict__ xp, const cplx* __restrict__ wp,
-                            const double* __restrict__ sval,
+__global__ void emit_kernel(const cplx* __restrict__ y, const double* __restrict__ sval,
                             const int* __restrict__ perm, int m, int n, int p, int q,
                             int transposed, int keep, cplx* __restrict__ u, int u_na,
                             long long u_so, long long u_sa, long long u_sj,
-                            cplx* __restrict__ svh, cplx* __restrict__ ucont) {
+                            cplx* __restrict__ svh) {
   // element space: [0, m*keep) -> U ; [m*keep, (m+n)*keep) -> SVh
   const long long nu = (long long)m * keep, nv = (long long)n * keep;
+  const size_t T = (size_t)p + q;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < nu + nv;
        e += (long long)gridDim.x * blockDim.x) {
     if (e < nu) {
-      if (!u && !ucont) continue;
+      if (!u) continue;
       const int j = (int)(e % keep);
       const int i = (int)(e / keep);
       const int c = perm[j];
-      const size_t pan = c / PC, c4 = c % PC;
+      const size_t blk = c / BC, c16 = c % BC;
       cplx v;
       if (!transposed) {         // U = Y / sigma
-        v = xp[(pan * p + i) * PC + c4];
+        v = y[(blk * T + i) * BC + c16];
         const double s = sval[j];
         const double inv = (s > 0.0) ? 1.0 / s : 0.0;
         v.x *= inv; v.y *= inv;
       } else {                   // U = W
-        v = wp[(pan * q + i) * PC + c4];
+        v = y[(blk * T + p + i) * BC + c16];
       }
-      if (u) u[(long long)(i / u_na) * u_so + (long long)(i % u_na) * u_sa + j * u_sj] = v;
-      if (ucont) ucont[(long long)i * keep + j] = v;
+      u[(long long)(i / u_na) * u_so + (long long)(i % u_na) * u_sa + j * u_sj] = v;
     } else {
       if (!svh) continue;
       const long long f = e - nu;
       const int col = (int)(f % n);
       const int j = (int)(f / n);
       const int c = perm[j];
-      const size_t pan = c / PC, c4 = c % PC;
+      const size_t blk = c / BC, c16 = c % BC;
       cplx v;
       if (!transposed) {         // S Vh[j, col] = sigma_j * conj(W[col, c])
-        v = wp[(pan * q + col) * PC + c4];
+        v = y[(blk * T + p + col) * BC + c16];
         const double s = sval[j];
         v = make_double2(v.x * s, -v.y * s);
       } else {                   // S Vh[j, col] = conj(Y[col, c])
-        v = xp[(pan * p + col) * PC + c4];
+        v = y[(blk * T + col) * BC + c16];
         v.y = -v.y;
       }
       svh[(long long)j * n + col] = v;
     }
   }
 }
+
+constexpr size_t kDynSmem = (size_t)CHUNK_ROWS * PB * sizeof(cplx) + 2 * PB * PB * sizeof(cplx);
 
 }  // namespace
 
@@ -675,105 +776,57 @@ extern "C" int b200_svd_factor(void* stream_, const void* theta, int m, int n,
     return B200_EINVAL;
   }
   const Layout L = make_layout(m, n);
-  if (L.nb * PC > 16384) {
+  if (L.nb * BC > 16384) {
     b200::set_error("b200_svd_factor: min(m,n)=%d exceeds 16384", L.q);
     return B200_ESIZE;
   }
   unsigned char* base = (unsigned char*)work;
   Header* hdr = (Header*)(base + L.header);
-  cplx* xp = (cplx*)(base + L.xp);
-  cplx* wp = (cplx*)(base + L.wp);
+  int* ctrl = (int*)(base + L.ctrl);
   double* sig2 = (double*)(base + L.sig2);
   double* sval = (double*)(base + L.sval);
   int* perm = (int*)(base + L.perm);
-  int* flags = (int*)(base + L.flags);
-  int* ready = (int*)(base + L.ready);
-  double* pn = (double*)(base + L.pn);
+  cplx* gpart = (cplx*)(base + L.gpart);
+  cplx* jbuf = (cplx*)(base + L.jbuf);
+  cplx* y = (cplx*)(base + L.y);
 
-  Header h;
-  h.m = m; h.n = n; h.p = L.p; h.q = L.q; h.npan = L.npan; h.nb = L.nb;
-  h.transposed = L.transposed; h.keep = 0; h.sweeps = 0; h.status = 1;
-  h.rotations = 0; h.pad = 0; h.eps = eps; h.s0 = 0.0; h.fro2 = 0.0; h.pad2 = 0.0;
-  h.theta = theta; h.rs = rs; h.cs = cs;
-  B200_CUDA_CHECK(cudaMemcpyAsync(hdr, &h, sizeof(h), cudaMemcpyHostToDevice, stream));
-  B200_CUDA_CHECK(cudaMemsetAsync(flags, 0, NFLAGS * sizeof(int), stream));
-  B200_CUDA_CHECK(cudaMemsetAsync(ready, 0, (size_t)L.nb * sizeof(int), stream));
+  // header + control words are contiguous: one memset clears both (fro2 = 0, counters = 0)
+  B200_CUDA_CHECK(cudaMemsetAsync(base, 0, L.ctrl + L.ctrl_bytes, stream));
 
-  {
-    const long long total = (long long)L.nb * (L.p + (wp ? L.q : 0)) * PC;
-    int blocks = (int)((total + 255) / 256);
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    svd_load_kernel<<<blocks, 256, 0, stream>>>((const cplx*)theta, rs, cs, m, n,
-                                                L.p, L.q, L.nb, L.transposed, xp, wp,
-                                                &hdr->fro2, pn);
-    B200_LAUNCH_CHECK();
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA_CHECK(cudaFuncSetAttribute(
+        jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmem));
+    attr_set = true;
   }
-  {
-    static int dev_sms = 0;
-    if (!dev_sms) {
-      int dev = 0;
-      B200_CUDA_CHECK(cudaGetDevice(&dev));
-      B200_CUDA_CHECK(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, dev));
-      B200_CUDA_CHECK(cudaFuncSetAttribute(
-          jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-          SMEM_STAGE_LIMIT));
-    }
-    const size_t x_bytes = (size_t)2 * L.p * PC * sizeof(cplx);
-    const size_t w_bytes = (size_t)2 * L.q * PC * sizeof(cplx);
-    int stage_x = x_bytes <= (size_t)SMEM_STAGE_LIMIT ? 1 : 0;
-    int stage_w = (stage_x && x_bytes + w_bytes <= (size_t)SMEM_STAGE_LIMIT) ? 1 : 0;
-    size_t dyn = (stage_x ? x_bytes : 0) + (stage_w ? w_bytes : 0);
-    int per_sm = 0;
-    B200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        &per_sm, jacobi_kernel, JT, dyn));
-    if (per_sm < 1) {
-      b200::set_error("b200_svd_factor: Jacobi kernel cannot be resident (dyn smem %zu)", dyn);
-      return B200_ECUDA;
-    }
-    int grid = L.nb / 2;
-    const int cap = per_sm * dev_sms;
-    if (grid > cap) grid = cap;
-    int p = L.p, q = L.q, nb = L.nb;
-    // relative orthogonality target |cos| <= 1e-11 (singular values are second order in
-    // it); never tighter than the rounding level of a length-p dot product
-    double tol = 2.0 * sqrt((double)L.p) * 2.220446049250313e-16;
-    if (tol < 1e-11) tol = 1e-11;
-    // columns below 1e-2*eps*||X||_F can never be kept nor change the rank decision
-    double neg_rel = (eps > 0.0) ? 1e-2 * eps : 0.0;
-    void* args[] = {&xp, &wp, &p, &q, &nb, &stage_x, &stage_w, &tol, &neg_rel,
-                    &flags, &ready, &pn, &hdr};
-    b200::profile_begin(stream);
-    B200_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)jacobi_kernel, dim3(grid),
-                                                dim3(JT), args, dyn, stream));
-    b200::count_launch();
-    {   // SURVEY 8d convention: 4*(14 m n^2 + 8 n^3) with m >= n
-      const double mm = (double)L.p, nn = (double)L.q;
-      b200::profile_end(stream, 4.0 * (14.0 * mm * nn * nn + 8.0 * nn * nn * nn),
-                        &hdr->sweeps);
-    }
+  const int ncols = L.nb * BC;
+  int npow = 1;
+  while (npow < ncols) npow <<= 1;
+  if ((size_t)npow * (sizeof(double) + sizeof(int)) > kDynSmem) {
+    b200::set_error("b200_svd_factor: sort buffer exceeds shared memory");
+    return B200_ESIZE;
   }
-  {
-    const int warps = L.nb;
-    const int blocks = (warps * 32 + 255) / 256;
-    colnorm_kernel<<<blocks, 256, 0, stream>>>(xp, L.p, L.nb, sig2);
-    B200_LAUNCH_CHECK();
-  }
-  {
-    static bool attr_set = false;
-    if (!attr_set) {
-      B200_CUDA_CHECK(cudaFuncSetAttribute(
-          rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 12));
-      attr_set = true;
-    }
-    const int ncols = L.nb * PC;
-    int npow = 1;
-    while (npow < ncols) npow <<= 1;
-    const size_t dyn = (size_t)npow * (sizeof(double) + sizeof(int));
-    const int minmn = (m < n) ? m : n;
-    // info is written to device-visible pinned host memory directly
-    rank_kernel<<<1, 1024, dyn, stream>>>(sig2, ncols, L.q, minmn, eps, sval, perm,
-                                          hdr, info_host);
-    B200_LAUNCH_CHECK();
+  const cplx* th = (const cplx*)theta;
+  long long rs_ = rs, cs_ = cs;
+  int p = L.p, q = L.q, nb = L.nb, R = L.R, RS = L.RS, SE = L.SE, tr = L.transposed;
+  int minmn = (m < n) ? m : n;
+  // relative orthogonality target |cos| <= 1e-11 (singular values are second order in
+  // it); never tighter than the rounding level of a length-p dot product
+  double tol = 2.0 * sqrt((double)L.p) * 2.220446049250313e-16;
+  if (tol < 1e-11) tol = 1e-11;
+  // columns below 1e-2*eps*||X||_F can never be kept nor change the rank decision
+  double neg_rel = (eps > 0.0) ? 1e-2 * eps : 0.0;
+  void* args[] = {&th, &rs_, &cs_, &y, &gpart, &jbuf, &ctrl, &sig2, &sval, &perm, &hdr,
+                  &info_host, &p, &q, &nb, &R, &RS, &SE, &tr, &minmn, &tol, &eps, &neg_rel};
+  const int grid = L.SE * L.R;
+  b200::profile_begin(stream);
+  B200_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)jacobi_kernel, dim3(grid), dim3(JT),
+                                              args, kDynSmem, stream));
+  b200::count_launch();
+  {   // SURVEY 8d convention: 4*(14 m n^2 + 8 n^3) with m >= n
+    const double mm = (double)L.p, nn = (double)L.q;
+    b200::profile_end(stream, 4.0 * (14.0 * mm * nn * nn + 8.0 * nn * nn * nn),
+                      &hdr->sweeps);
   }
   return B200_OK;
 }
@@ -792,12 +845,11 @@ extern "C" int b200_svd_emit(void* stream_, const void* work, const void* theta,
   const long long total = (long long)(m + n) * keep;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  cplx* ucont = nullptr;
   (void)theta; (void)rs; (void)cs;
   emit_kernel<<<blocks, 256, 0, stream>>>(
-      (const cplx*)(base + L.xp), (const cplx*)(base + L.wp),
-      (const double*)(base + L.sval), (const int*)(base + L.perm), m, n, L.p, L.q,
-      L.transposed, keep, (cplx*)u, u_na, u_so, u_sa, u_sj, (cplx*)svh, ucont);
+      (const cplx*)(base + L.y), (const double*)(base + L.sval),
+      (const int*)(base + L.perm), m, n, L.p, L.q, L.transposed, keep, (cplx*)u, u_na,
+      u_so, u_sa, u_sj, (cplx*)svh);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }
