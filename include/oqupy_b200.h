@@ -97,9 +97,11 @@ int b200_svd_emit(void* stream, const void* work, const void* theta, int m, int 
                   int64_t rs, int64_t cs, int keep, void* u, int u_na, int64_t u_so,
                   int64_t u_sa, int64_t u_sj, void* svh);
 int b200_svd_values(void* stream, const void* work, int m, int n, double* s_out);
-/* diagnostics: SM-clock cycles CTA 0 spent per phase of the sweep kernel
- * {wait, load X, gram, eig (+load W), apply, store, sweep vote, #stages} */
-int b200_svd_phase_cycles(void* stream, const void* work, long long* out8);
+/* diagnostics: SM-clock cycles CTA 0 (leader of pair slot 0) spent per phase of the
+ * Jacobi kernel: {0 wait for input blocks, 1 load + partial Gram, 2 publish, 3 wait
+ * for all partials, 4 reduce + convergence test, 5 inner 32x32 sweep, 6 sort + publish
+ * J, 7 apply + hand-over, 8 sweep vote, 9 norms/rank, 10..14 spare, 15 #stages} */
+int b200_svd_phase_cycles(void* stream, const void* work, long long* out16);
 
 /* ---------------------------------------------------------------------------
  * compute_dynamics step for ONE environment and `nvec` ensemble members that

@@ -187,7 +187,7 @@ class CudaOps:
         self._check(code, "b200_svd_emit")
 
     def svd_phase_cycles(self, h):
-        out = (ctypes.c_longlong * 8)()
+        out = (ctypes.c_longlong * 16)()
         self._check(self.lib.b200_svd_phase_cycles(self._stream(), h.work.data_ptr(),
                                                    out), "b200_svd_phase_cycles")
         return list(out)

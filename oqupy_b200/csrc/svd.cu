@@ -14,11 +14,13 @@
 //     the stacked matrix.  Per stage it
 //       1. stages its slice of the two blocks in shared memory,
 //       2. forms the partial 32x32 Gram matrix of its X rows and publishes it,
-//       3. (slice 0 = leader) sums the partials in a fixed order (deterministic),
-//          runs ONE cyclic sweep of a two-sided Jacobi eigensolver on the 32x32
-//          Hermitian Gram matrix (cross-block pairs first, 2x2-block ownership: no
-//          buffer hazards), sorts the columns by descending norm and publishes the
-//          32x32 rotation J,
+//       3. sums the partials of all slices in a fixed order (deterministic) and runs
+//          ONE cyclic sweep of a two-sided Jacobi eigensolver on the 32x32 Hermitian
+//          Gram matrix (cross-block pairs first, 2x2-block ownership: no buffer
+//          hazards; only the rounds that hold a violating pair), sorted by descending
+//          norm.  EVERY slice solves the same 32x32 problem redundantly: bit-identical
+//          results, and no L2 round trip to hand the rotation J from a leader to the
+//          other slices (latency, not work, is what a sequential chain pays for),
 //       4. applies J to its slice of [X ; W] and writes it back.
 //     Hand-over between stages is point to point through L2 (st.release / ld.acquire
 //     per (block, slice)); only the end of a sweep is a grid-wide barrier (the
@@ -44,19 +46,21 @@ constexpr int MAX_SWEEPS = 120;   // <= NFLAGS
 constexpr int NFLAGS = 128;
 constexpr int FLOOR_GROW_AFTER = 90;
 constexpr int CHUNK_ROWS = 256;   // rows of a slice staged in shared memory at a time
-constexpr int MIN_SLICE_ROWS = 32;
+constexpr int X_SLICE_ROWS = 24;  // target rows of an X slice / a W slice
+constexpr int W_SLICE_ROWS = 40;
 constexpr int GP = PB + 1;        // padded leading dimension of the 32x32 work matrices
 
 struct Header {        // lives at the start of the workspace (device)
   int m, n, p, q, nb, transposed, keep, sweeps;
-  int status, rotations, R, RS;
+  int status, rotations, R, RSx;
   double eps, s0, fro2, pad2;
-  long long phase_cycles[8];  // CTA 0: wait, load, gram, solve/J-wait, apply+store, vote, -, stages
+  long long phase_cycles[16]; // CTA 0: 0 wait-ready, 1 load+gram, 2 publish, 3 cnt-wait, 4 sum+test,
+                              // 5 inner sweep, 6 sort, 7 apply+release, 8 vote, 9 final, 15 stages
 };
 
 struct Layout {
-  size_t header, ctrl, ctrl_bytes, sig2, sval, perm, gpart, jbuf, y, total;
-  int p, q, T, nb, S, R, RS, SE, transposed;
+  size_t header, ctrl, ctrl_bytes, sig2, sval, perm, gpart, y, total;
+  int p, q, T, nb, S, R, Rx, Rw, RSx, RSw, SE, transposed;
 };
 
 __host__ __device__ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -81,7 +85,6 @@ int device_sms() {
 //   [2 .. 2+NFLAGS)           rotated-stage count per sweep
 //   ready[nb*R]               stages completed per (block, slice)
 //   cnt[2*S]                  slices that published their partial Gram (double-buffered)
-//   flagj[S]                  2*(stage+1) + need, per slot
 __host__ Layout make_layout(int m, int n) {
   Layout L;
   L.transposed = (m < n) ? 1 : 0;
@@ -95,25 +98,41 @@ __host__ Layout make_layout(int m, int n) {
   const int sms = device_sms();
   int max_r = sms / L.S;
   if (max_r < 1) max_r = 1;
-  int r = (L.T + MIN_SLICE_ROWS - 1) / MIN_SLICE_ROWS;
-  if (r > max_r) r = max_r;
-  int rs = (L.T + r - 1) / r;
-  rs = (rs + 3) & ~3;
-  L.RS = rs;
-  L.R = (L.T + rs - 1) / rs;
+  // Row slices: X rows cost a Gram pass AND an apply pass, W rows only an apply pass,
+  // so X slices are made smaller.  Slices never mix X and W rows (except R == 1).
+  const int want_x = (L.p + X_SLICE_ROWS - 1) / X_SLICE_ROWS;
+  const int want_w = (L.q + W_SLICE_ROWS - 1) / W_SLICE_ROWS;
+  if (max_r == 1) {
+    L.Rx = 1; L.Rw = 0;
+  } else if (want_x + want_w <= max_r) {
+    L.Rx = want_x; L.Rw = want_w;
+  } else {
+    int rx = (int)(max_r * (2.0 * L.p) / (2.0 * L.p + L.q) + 0.5);
+    if (rx < 1) rx = 1;
+    if (rx > max_r - 1) rx = max_r - 1;
+    L.Rx = rx; L.Rw = max_r - rx;
+  }
+  if (L.Rw == 0) {
+    L.RSx = L.T; L.RSw = 0;
+  } else {
+    L.RSx = (((L.p + L.Rx - 1) / L.Rx) + 3) & ~3;
+    L.Rx = (L.p + L.RSx - 1) / L.RSx;
+    L.RSw = (((L.q + L.Rw - 1) / L.Rw) + 3) & ~3;
+    L.Rw = (L.q + L.RSw - 1) / L.RSw;
+  }
+  L.R = L.Rx + L.Rw;
   L.SE = L.S;                       // slots resident at once
   if (L.SE * L.R > sms) L.SE = sms / L.R;
   if (L.SE < 1) L.SE = 1;
   size_t off = 0;
   L.header = off; off = align256(off + sizeof(Header));
   L.ctrl = off;
-  L.ctrl_bytes = sizeof(int) * (size_t)(2 + NFLAGS + (size_t)L.nb * L.R + 3 * (size_t)L.S);
+  L.ctrl_bytes = sizeof(int) * (size_t)(2 + NFLAGS + (size_t)L.nb * L.R + 2 * (size_t)L.S);
   off = align256(off + L.ctrl_bytes);
   L.sig2 = off; off = align256(off + (size_t)L.nb * BC * sizeof(double));
   L.sval = off; off = align256(off + (size_t)L.nb * BC * sizeof(double));
   L.perm = off; off = align256(off + (size_t)L.nb * BC * sizeof(int));
   L.gpart = off; off = align256(off + (size_t)2 * L.S * L.R * PB * PB * sizeof(cplx));
-  L.jbuf = off; off = align256(off + (size_t)2 * L.S * PB * PB * sizeof(cplx));
   // W accumulates the right rotations.  (Forming S*Vh as U^H*theta instead is NOT an
   // option: columns of U are orthogonal only down to the absolute rounding floor, and
   // the projection would amplify that by sigma_0/sigma_j.)
@@ -199,63 +218,81 @@ struct InnerShared {
   double gr[PB][GP], gi[PB][GP];   // Hermitian working matrix
   double jr[PB][GP], ji[PB][GP];   // accumulated rotations
   double rc[BC], rsr[BC], rsi[BC]; // per pair of the round: c, s e^{i phi}
-  int rp[BC], rq[BC], ract[BC];
+  int ract[BC];
+  unsigned short sched[PB - 1][BC]; // inner ordering: p | q << 8
+  unsigned char round_of[PB][PB];   // round in which the pair (i, j) meets
   int order[PB];
-  int need, flag;
+  unsigned mask;                    // rounds that hold a violating pair
+  int viol;
 };
 
+// threshold of the inner rotations: a pair is rotated when |g|^2 exceeds it
+__device__ __forceinline__ double inner_threshold(double a, double b, double floor2,
+                                                  double neg2) {
+  const double big = fmax(a, b), small = fmax(fmin(a, b), 0.0);
+  const double fl = 0.0625 * floor2;
+  const double loose = fma(1e-4 * big, small, big * fl);
+  const double strict = big * fma(1e-28, small, fl);
+  return (big < neg2) ? loose : strict;
+}
+
 // One cyclic sweep of two-sided Jacobi on the 32x32 Hermitian matrix S.gr + i S.gi,
-// accumulating J.  All JT threads participate.  Thread (a, b), a, b in [0,16), owns the
-// 2x2 block (rows of pair a) x (columns of pair b): G' = R_a^H G R_b touches only its
-// own four entries, so the update is in place.  Threads 256.. own two rows of J each.
+// accumulating J; only the rounds in `mask` are visited.  Threads 0..255 own the 2x2
+// blocks of G: thread (a, b), a, b in [0,16), owns (rows of pair a) x (columns of pair
+// b); G' = R_a^H G R_b touches only its own four entries, so the update is in place, and
+// the diagonal-block thread (a, a) holds exactly the three numbers the rotation of pair
+// a is made from.  Threads 256..511 own two rows x one column pair of J each.
 // R = [[c, se], [-conj(se), c]] acting on columns (p, q).
-__device__ void inner_sweep(InnerShared& S, double floor2, double neg2) {
+__device__ void inner_sweep(InnerShared& S, unsigned mask, double floor2, double neg2) {
   const int t = threadIdx.x;
-  for (int round = 0; round < PB - 1; ++round) {
-    int act = 0;
-    if (t < BC) {
-      int i, j;
-      inner_pair(round, t, i, j);
-      const double a = S.gr[i][i], b = S.gr[j][j];
-      const double xr = S.gr[i][j], xi = S.gi[i][j];
-      const double mag2 = xr * xr + xi * xi;
-      double c = 1.0, sr_ = 0.0, si_ = 0.0;
-      if (mag2 > 0.0 && !pair_converged(a, b, mag2, 1e-28, 0.0625 * floor2, neg2)) {
-        // cos(2t) = |h|/r, c = sqrt((1+cos 2t)/2), s e^{i phi} = sign(h) g/(2 r c)
-        const double h = 0.5 * (b - a);
-        const double inv_r = rsqrt(h * h + mag2);
-        const double w = 0.5 + 0.5 * fabs(h) * inv_r;
-        const double ic = rsqrt(w);            // two rsqrt: no sqrt, no division
-        c = w * ic;
-        const double k = ((h >= 0.0) ? 0.5 : -0.5) * inv_r * ic;
-        sr_ = xr * k;
-        si_ = xi * k;
-        act = 1;
-      }
-      S.rp[t] = i; S.rq[t] = j; S.ract[t] = act;
-      S.rc[t] = c; S.rsr[t] = sr_; S.rsi[t] = si_;
+  const bool gthread = t < 256;
+  const int u = t & 255;
+  const int a = u >> 4, b = u & 15;
+  while (mask) {
+    const int round = __ffs(mask) - 1;
+    mask &= mask - 1;
+    const int sa = S.sched[round][a], sb = S.sched[round][b];
+    const int pa = sa & 0xff, qa = sa >> 8, pb = sb & 0xff, qb = sb >> 8;
+    double g00r, g00i, g01r, g01i, g10r, g10i, g11r, g11i;
+    const int r0 = gthread ? pa : 2 * a, r1 = gthread ? qa : 2 * a + 1;
+    if (gthread) {
+      g00r = S.gr[r0][pb]; g00i = S.gi[r0][pb]; g01r = S.gr[r0][qb]; g01i = S.gi[r0][qb];
+      g10r = S.gr[r1][pb]; g10i = S.gi[r1][pb]; g11r = S.gr[r1][qb]; g11i = S.gi[r1][qb];
+    } else {
+      g00r = S.jr[r0][pb]; g00i = S.ji[r0][pb]; g01r = S.jr[r0][qb]; g01i = S.ji[r0][qb];
+      g10r = S.jr[r1][pb]; g10i = S.ji[r1][pb]; g11r = S.jr[r1][qb]; g11i = S.ji[r1][qb];
     }
-    if (!__syncthreads_or(act)) continue;
-    if (t < 256) {
-      const int a = t >> 4, b = t & 15;
-      const int aa = S.ract[a], ab = S.ract[b];
-      if (aa | ab) {
-        const int pa = S.rp[a], qa = S.rq[a], pb = S.rp[b], qb = S.rq[b];
+    if (gthread && a == b) {
+      // straight-line: the rotation and the test are independent dependency chains
+      const double mag2 = fma(g01r, g01r, g01i * g01i);
+      const double thr = inner_threshold(g00r, g11r, floor2, neg2);
+      // cos(2t) = |h|/r, c = sqrt((1+cos 2t)/2), s e^{i phi} = sign(h) g/(2 r c)
+      const double h = 0.5 * (g11r - g00r);
+      const double inv_r = rsqrt(fma(h, h, mag2) + 1e-300);
+      const double w = fma(0.5 * fabs(h), inv_r, 0.5);
+      const double ic = rsqrt(w);            // two rsqrt: no sqrt, no division
+      const double k = ((h >= 0.0) ? 0.5 : -0.5) * inv_r * ic;
+      const bool act = (mag2 > thr) && (fmax(g00r, g11r) > 0.0);
+      S.ract[a] = act ? 1 : 0;
+      S.rc[a] = act ? w * ic : 1.0;
+      S.rsr[a] = act ? g01r * k : 0.0;
+      S.rsi[a] = act ? g01i * k : 0.0;
+    }
+    __syncthreads();
+    const int aa = gthread ? S.ract[a] : 0, ab = S.ract[b];
+    if (aa | ab) {
+      const double cb = S.rc[b], sbr = S.rsr[b], sbi = S.rsi[b];
+      // column op: T[:,0] = cb g[:,0] - conj(seb) g[:,1] ; T[:,1] = seb g[:,0] + cb g[:,1]
+      const double t00r = cb * g00r - (sbr * g01r + sbi * g01i);
+      const double t00i = cb * g00i - (sbr * g01i - sbi * g01r);
+      const double t01r = cb * g01r + (sbr * g00r - sbi * g00i);
+      const double t01i = cb * g01i + (sbr * g00i + sbi * g00r);
+      const double t10r = cb * g10r - (sbr * g11r + sbi * g11i);
+      const double t10i = cb * g10i - (sbr * g11i - sbi * g11r);
+      const double t11r = cb * g11r + (sbr * g10r - sbi * g10i);
+      const double t11i = cb * g11i + (sbr * g10i + sbi * g10r);
+      if (gthread) {
         const double ca = S.rc[a], sar = S.rsr[a], sai = S.rsi[a];
-        const double cb = S.rc[b], sbr = S.rsr[b], sbi = S.rsi[b];
-        const double g00r = S.gr[pa][pb], g00i = S.gi[pa][pb];
-        const double g01r = S.gr[pa][qb], g01i = S.gi[pa][qb];
-        const double g10r = S.gr[qa][pb], g10i = S.gi[qa][pb];
-        const double g11r = S.gr[qa][qb], g11i = S.gi[qa][qb];
-        // column op: T[:,0] = cb g[:,0] - conj(seb) g[:,1] ; T[:,1] = seb g[:,0] + cb g[:,1]
-        const double t00r = cb * g00r - (sbr * g01r + sbi * g01i);
-        const double t00i = cb * g00i - (sbr * g01i - sbi * g01r);
-        const double t01r = cb * g01r + (sbr * g00r - sbi * g00i);
-        const double t01i = cb * g01i + (sbr * g00i + sbi * g00r);
-        const double t10r = cb * g10r - (sbr * g11r + sbi * g11i);
-        const double t10i = cb * g10i - (sbr * g11i - sbi * g11r);
-        const double t11r = cb * g11r + (sbr * g10r - sbi * g10i);
-        const double t11i = cb * g11i + (sbr * g10i + sbi * g10r);
         // row op: G'[0,:] = ca T[0,:] - sea T[1,:] ; G'[1,:] = conj(sea) T[0,:] + ca T[1,:]
         double n00r = ca * t00r - (sar * t10r - sai * t10i);
         double n00i = ca * t00i - (sar * t10i + sai * t10r);
@@ -269,27 +306,11 @@ __device__ void inner_sweep(InnerShared& S, double floor2, double neg2) {
           n00i = 0.0; n11i = 0.0;
           n01r = 0.0; n01i = 0.0; n10r = 0.0; n10i = 0.0;
         }
-        S.gr[pa][pb] = n00r; S.gi[pa][pb] = n00i;
-        S.gr[pa][qb] = n01r; S.gi[pa][qb] = n01i;
-        S.gr[qa][pb] = n10r; S.gi[qa][pb] = n10i;
-        S.gr[qa][qb] = n11r; S.gi[qa][qb] = n11i;
-      }
-    } else {
-      const int u = t - 256;
-      const int b = u & 15, r0 = (u >> 4) * 2;
-      if (S.ract[b]) {
-        const int pb = S.rp[b], qb = S.rq[b];
-        const double cb = S.rc[b], sbr = S.rsr[b], sbi = S.rsi[b];
-#pragma unroll
-        for (int rr = 0; rr < 2; ++rr) {
-          const int r = r0 + rr;
-          const double v0r = S.jr[r][pb], v0i = S.ji[r][pb];
-          const double v1r = S.jr[r][qb], v1i = S.ji[r][qb];
-          S.jr[r][pb] = cb * v0r - (sbr * v1r + sbi * v1i);
-          S.ji[r][pb] = cb * v0i - (sbr * v1i - sbi * v1r);
-          S.jr[r][qb] = cb * v1r + (sbr * v0r - sbi * v0i);
-          S.ji[r][qb] = cb * v1i + (sbr * v0i + sbi * v0r);
-        }
+        S.gr[r0][pb] = n00r; S.gi[r0][pb] = n00i; S.gr[r0][qb] = n01r; S.gi[r0][qb] = n01i;
+        S.gr[r1][pb] = n10r; S.gi[r1][pb] = n10i; S.gr[r1][qb] = n11r; S.gi[r1][qb] = n11i;
+      } else {
+        S.jr[r0][pb] = t00r; S.ji[r0][pb] = t00i; S.jr[r0][qb] = t01r; S.ji[r0][qb] = t01i;
+        S.jr[r1][pb] = t10r; S.ji[r1][pb] = t10i; S.jr[r1][qb] = t11r; S.ji[r1][qb] = t11i;
       }
     }
     __syncthreads();
@@ -297,15 +318,16 @@ __device__ void inner_sweep(InnerShared& S, double floor2, double neg2) {
 }
 
 // Partial Gram matrix of `rows` rows of the staged tile ([row][32] complex) into
-// registers: thread (kh, oi, oj) accumulates the 2x2 block rows (2oi, 2oi+1), columns
-// (2oj, 2oj+1) of T^H T over the rows r = kh (mod 2).
+// registers: thread (kh, oi, oj) accumulates the entries rows {oi, oi+16} x columns
+// {oj, oj+16} of T^H T over the rows r = kh (mod 2)  (bank-conflict free).
 __device__ __forceinline__ void gram_accumulate(const cplx* tile, int rows, double acc[8]) {
   const int t = threadIdx.x;
   const int kh = t >> 8, oi = (t >> 4) & 15, oj = t & 15;
+#pragma unroll 2
   for (int r = kh; r < rows; r += 2) {
     const cplx* row = tile + (size_t)r * PB;
-    const cplx a0 = row[2 * oi], a1 = row[2 * oi + 1];
-    const cplx b0 = row[2 * oj], b1 = row[2 * oj + 1];
+    const cplx a0 = row[oi], a1 = row[oi + BC];
+    const cplx b0 = row[oj], b1 = row[oj + BC];
     // conj(a) * b
     acc[0] = fma(a0.x, b0.x, acc[0]); acc[0] = fma(a0.y, b0.y, acc[0]);
     acc[1] = fma(a0.x, b0.y, acc[1]); acc[1] = fma(-a0.y, b0.x, acc[1]);
@@ -318,8 +340,9 @@ __device__ __forceinline__ void gram_accumulate(const cplx* tile, int rows, doub
   }
 }
 
-// out[row][:] = tile[row][:] * J  for `rows` rows; NR rows per thread.  Output columns
-// 0..15 go to block A, 16..31 to block B (both [row][16] in global memory).
+// out[row][:] = tile[row][:] * J  for `rows` rows; NR rows per thread.  Thread column
+// tx owns output columns tx (-> block A) and tx+16 (-> block B), both [row][16] in
+// global memory.
 template <int NR>
 __device__ __forceinline__ void apply_tile(const cplx* tile, int rows, const cplx* sj,
                                            cplx* outA, cplx* outB) {
@@ -327,15 +350,18 @@ __device__ __forceinline__ void apply_tile(const cplx* tile, int rows, const cpl
   const int tx = t & 15, ty = t >> 4;     // 16 column pairs x 32 row groups
   for (int rbase = ty * NR; rbase < rows; rbase += 32 * NR) {
     double ar[NR][2], ai[NR][2];
+    int rr[NR];
 #pragma unroll
-    for (int x = 0; x < NR; ++x) { ar[x][0] = ar[x][1] = ai[x][0] = ai[x][1] = 0.0; }
-#pragma unroll 4
+    for (int x = 0; x < NR; ++x) {
+      ar[x][0] = ar[x][1] = ai[x][0] = ai[x][1] = 0.0;
+      rr[x] = (rbase + x < rows) ? rbase + x : rows - 1;
+    }
+#pragma unroll 8
     for (int k = 0; k < PB; ++k) {
-      const cplx j0 = sj[k * PB + 2 * tx], j1 = sj[k * PB + 2 * tx + 1];
+      const cplx j0 = sj[k * PB + tx], j1 = sj[k * PB + tx + BC];
 #pragma unroll
       for (int x = 0; x < NR; ++x) {
-        const int r = (rbase + x < rows) ? rbase + x : rows - 1;
-        const cplx v = tile[(size_t)r * PB + k];
+        const cplx v = tile[(size_t)rr[x] * PB + k];
         ar[x][0] = fma(v.x, j0.x, ar[x][0]); ar[x][0] = fma(-v.y, j0.y, ar[x][0]);
         ai[x][0] = fma(v.x, j0.y, ai[x][0]); ai[x][0] = fma(v.y, j0.x, ai[x][0]);
         ar[x][1] = fma(v.x, j1.x, ar[x][1]); ar[x][1] = fma(-v.y, j1.y, ar[x][1]);
@@ -346,23 +372,33 @@ __device__ __forceinline__ void apply_tile(const cplx* tile, int rows, const cpl
     for (int x = 0; x < NR; ++x) {
       const int r = rbase + x;
       if (r < rows) {
-        cplx* dst = (tx < 8) ? (outA + (size_t)r * BC + 2 * tx)
-                             : (outB + (size_t)r * BC + 2 * (tx - 8));
-        dst[0] = make_double2(ar[x][0], ai[x][0]);
-        dst[1] = make_double2(ar[x][1], ai[x][1]);
+        outA[(size_t)r * BC + tx] = make_double2(ar[x][0], ai[x][0]);
+        outB[(size_t)r * BC + tx] = make_double2(ar[x][1], ai[x][1]);
       }
     }
   }
 }
 
-// global -> shared: rows [r0, r0+rows) of blocks A and B into tile[row][32]
+// global -> shared: `rows` rows of blocks A and B into tile[row][32]; four independent
+// L2 loads in flight per thread
 __device__ __forceinline__ void load_tile(cplx* tile, const cplx* gA, const cplx* gB,
                                           int rows) {
   const int total = rows * PB;
-  for (int e = threadIdx.x; e < total; e += JT) {
-    const int r = e >> 5, c = e & 31;
-    const cplx* src = (c < BC) ? (gA + (size_t)r * BC + c) : (gB + (size_t)r * BC + (c - BC));
-    tile[e] = ldcg(src);
+  for (int e0 = threadIdx.x; e0 < total; e0 += 4 * JT) {
+    cplx v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * JT;
+      if (e < total) {
+        const int r = e >> 5, c = e & 31;
+        v[u] = ldcg((c < BC) ? (gA + (size_t)r * BC + c) : (gB + (size_t)r * BC + (c - BC)));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * JT;
+      if (e < total) tile[e] = v[u];
+    }
   }
 }
 
@@ -370,12 +406,12 @@ __device__ __forceinline__ void load_tile(cplx* tile, const cplx* gA, const cplx
 // Persistent cooperative kernel: load -> sweeps -> column norms -> rank rule.
 __global__ void __launch_bounds__(JT, 1)
 jacobi_kernel(const cplx* __restrict__ theta, long long rs, long long cs,
-              cplx* __restrict__ y, cplx* __restrict__ gpart, cplx* __restrict__ jbuf,
+              cplx* __restrict__ y, cplx* __restrict__ gpart,
               int* __restrict__ ctrl, double* __restrict__ sig2,
               double* __restrict__ sval, int* __restrict__ perm,
               Header* __restrict__ hdr, int32_t* __restrict__ info, int p, int q, int nb,
-              int R, int RS, int SE, int transposed, int minmn, double tol, double eps,
-              double neg_rel) {
+              int Rx, int Rw, int RSx, int RSw, int SE, int transposed, int minmn,
+              double tol, double eps, double neg_rel) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ InnerShared S;
   __shared__ double s_red[JT / 32];
@@ -384,20 +420,28 @@ jacobi_kernel(const cplx* __restrict__ theta, long long rs, long long cs,
   cplx* sg = sj + PB * PB;                                 // [32][32] scratch (Gram halves)
 
   const int T = p + q;
+  const int R = Rx + Rw;
   const int S_slots = nb / 2;
   int* bar = ctrl;
   int* flags = ctrl + 2;
   int* ready = flags + NFLAGS;
   int* cnt = ready + (size_t)nb * R;
-  int* flagj = cnt + 2 * S_slots;
   int epoch = 0;
   const int t = threadIdx.x;
   const size_t blk_elems = (size_t)T * BC;
 
-  long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long pc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   long long tq = clock64();
 #define PHASE(k) { const long long tn_ = clock64(); pc[k] += tn_ - tq; tq = tn_; }
 
+  // inner ordering table
+  for (int e = t; e < (PB - 1) * BC; e += JT) {
+    int i, j;
+    inner_pair(e / BC, e % BC, i, j);
+    S.sched[e / BC][e % BC] = (unsigned short)(i | (j << 8));
+    S.round_of[i][j] = (unsigned char)(e / BC);
+    S.round_of[j][i] = (unsigned char)(e / BC);
+  }
   // ---- load: Y = [X ; I], ||X||_F^2
   {
     double local = 0.0;
@@ -434,7 +478,6 @@ jacobi_kernel(const cplx* __restrict__ theta, long long rs, long long cs,
       for (int w = 0; w < JT / 32; ++w) tot += s_red[w];
       if (tot != 0.0) atomicAdd(&hdr->fro2, tot);
     }
-    __threadfence();
   }
   grid_barrier(bar, epoch);
   const double fro = sqrt(__ldcg(&hdr->fro2));
@@ -442,15 +485,17 @@ jacobi_kernel(const cplx* __restrict__ theta, long long rs, long long cs,
 
   const int r_slice = blockIdx.x % R;
   const int s_first = blockIdx.x / R;
-  const int row0 = r_slice * RS;
-  const int nrows = min(RS, T - row0);            // rows of this slice (> 0 by layout)
-  const int xrows = max(0, min(nrows, p - row0)); // of which X rows (the Gram part)
+  int row0, nrows, xrows;
+  if (Rw == 0) { row0 = 0; nrows = T; xrows = p; }
+  else if (r_slice < Rx) { row0 = r_slice * RSx; nrows = min(RSx, p - row0); xrows = nrows; }
+  else { row0 = p + (r_slice - Rx) * RSw; nrows = min(RSw, T - row0); xrows = 0; }
   const bool single_chunk = nrows <= CHUNK_ROWS;
   const bool leader = (r_slice == 0);
 
   int sweeps_done = 0, total_rot = 0, status = 1;
   const double tol2 = tol * tol;
   const double neg2 = (neg_rel * fro) * (neg_rel * fro);
+  int pa = 0, pb = 0;
   for (int sweep = 0; sweep < MAX_SWEEPS; ++sweep) {
     int my_rot = 0;
     // absolute floor: 8 eps ||X||_F, doubled every sweep after FLOOR_GROW_AFTER so that
@@ -463,14 +508,17 @@ jacobi_kernel(const cplx* __restrict__ theta, long long rs, long long cs,
       const int g = sweep * (nb - 1) + stage;
       const int par = g & 1;
       for (int s = s_first; s < S_slots; s += SE) {
-        int pa, pb;
         outer_pair(s, stage, nb, pa, pb);
         cplx* gA = y + pa * blk_elems + (size_t)row0 * BC;
         cplx* gB = y + pb * blk_elems + (size_t)row0 * BC;
+        // W-only slices have no partial Gram: announce that right away
+        if (xrows == 0 && t == 0) red_release_add(cnt + par * S_slots + s, 1);
         // 1. wait until both input blocks (this slice) have finished the previous stage
         if (t == 0) {
           while (ld_acquire(ready + pa * R + r_slice) < g) {}
           while (ld_acquire(ready + pb * R + r_slice) < g) {}
+          S.mask = 0u;
+          S.viol = 0;
         }
         __syncthreads();
         PHASE(0)
@@ -485,107 +533,125 @@ jacobi_kernel(const cplx* __restrict__ theta, long long rs, long long cs,
           if (xr > 0) gram_accumulate(tile, xr, acc);
         }
         PHASE(1)
-        cplx* my_part = gpart + ((size_t)(par * S_slots + s) * R + r_slice) * (PB * PB);
         if (xrows > 0) {
+          cplx* my_part = gpart + ((size_t)(par * S_slots + s) * R + r_slice) * (PB * PB);
           const int kh = t >> 8, oi = (t >> 4) & 15, oj = t & 15;
+          cplx* d = sg + oi * PB + oj;
           if (kh == 1) {
-            cplx* d = sg + (2 * oi) * PB + 2 * oj;
-            d[0] = make_double2(acc[0], acc[1]); d[1] = make_double2(acc[2], acc[3]);
-            d[PB] = make_double2(acc[4], acc[5]); d[PB + 1] = make_double2(acc[6], acc[7]);
+            d[0] = make_double2(acc[0], acc[1]);
+            d[BC] = make_double2(acc[2], acc[3]);
+            d[BC * PB] = make_double2(acc[4], acc[5]);
+            d[BC * PB + BC] = make_double2(acc[6], acc[7]);
           }
           __syncthreads();
           if (kh == 0) {
-            const cplx* d = sg + (2 * oi) * PB + 2 * oj;
-            cplx* o = my_part + (2 * oi) * PB + 2 * oj;
+            cplx* o = my_part + oi * PB + oj;
             o[0] = make_double2(acc[0] + d[0].x, acc[1] + d[0].y);
-            o[1] = make_double2(acc[2] + d[1].x, acc[3] + d[1].y);
-            o[PB] = make_double2(acc[4] + d[PB].x, acc[5] + d[PB].y);
-            o[PB + 1] = make_double2(acc[6] + d[PB + 1].x, acc[7] + d[PB + 1].y);
+            o[BC] = make_double2(acc[2] + d[BC].x, acc[3] + d[BC].y);
+            o[BC * PB + BC] = make_double2(acc[6] + d[BC * PB + BC].x,
+                                           acc[7] + d[BC * PB + BC].y);
+            // (the lower-left quadrant is the conjugate transpose of the upper right)
           }
-          __threadfence();
+          __syncthreads();
+          // release is cumulative over the CTA barrier above
+          if (t == 0) red_release_add(cnt + par * S_slots + s, 1);
+        }
+        PHASE(2)
+        // 4. every slice: wait for all partials, reduce (fixed order), test, solve
+        if (t == 0) {
+          const int want = (g / 2 + 1) * R;     // cnt is cumulative per parity
+          while (ld_acquire(cnt + par * S_slots + s) < want) {}
         }
         __syncthreads();
-        if (t == 0) red_release_add(cnt + par * S_slots + s, 1);
-        PHASE(2)
-        // 4. leader: reduce, decide, solve, publish J
-        int need;
-        cplx* my_j = jbuf + (size_t)(par * S_slots + s) * (PB * PB);
-        if (leader) {
-          if (t == 0) {
-            const int want = (g / 2 + 1) * R;     // cnt is cumulative per parity
-            while (ld_acquire(cnt + par * S_slots + s) < want) {}
-          }
-          __syncthreads();
-          const int rx = (p + RS - 1) / RS;       // slices that hold X rows
+        PHASE(3)
+        {
           const cplx* base = gpart + (size_t)(par * S_slots + s) * R * (PB * PB);
-          for (int e = t; e < PB * PB; e += JT) {
-            double sr_ = 0.0, si_ = 0.0;
-            for (int rr = 0; rr < rx; ++rr) {
-              const cplx v = ldcg(base + (size_t)rr * (PB * PB) + e);
-              sr_ += v.x; si_ += v.y;
+          // thread t sums the entries (i0, j0) of the upper half and (i0+16, j0) of the
+          // lower half; only the upper triangle is needed
+          const int i0 = t >> 5, j0 = t & 31, i1 = i0 + BC;
+          const bool up1 = (j0 >= i1);
+          double s0r = 0.0, s0i = 0.0, s1r = 0.0, s1i = 0.0;
+          if (j0 >= i0) {
+#pragma unroll 4
+            for (int rr = 0; rr < Rx; ++rr) {      // fixed order: deterministic
+              const cplx v0 = ldcg(base + (size_t)rr * (PB * PB) + t);
+              s0r += v0.x; s0i += v0.y;
             }
-            const int i = e >> 5, j = e & 31;
-            S.gr[i][j] = sr_; S.gi[i][j] = si_;
-            S.jr[i][j] = (i == j) ? 1.0 : 0.0; S.ji[i][j] = 0.0;
           }
-          __syncthreads();
-          // exact Hermitian symmetry (upper triangle wins), convergence test
+          if (up1) {
+#pragma unroll 4
+            for (int rr = 0; rr < Rx; ++rr) {
+              const cplx v1 = ldcg(base + (size_t)rr * (PB * PB) + t + JT);
+              s1r += v1.x; s1i += v1.y;
+            }
+          }
+          if (i0 == j0) s0i = 0.0;
+          if (i1 == j0) s1i = 0.0;
+          if (j0 >= i0) {
+            S.gr[i0][j0] = s0r; S.gi[i0][j0] = s0i;
+            S.gr[j0][i0] = s0r; S.gi[j0][i0] = -s0i;
+          }
+          if (up1) {
+            S.gr[i1][j0] = s1r; S.gi[i1][j0] = s1i;
+            S.gr[j0][i1] = s1r; S.gi[j0][i1] = -s1i;
+          }
+          S.jr[i0][j0] = (i0 == j0) ? 1.0 : 0.0; S.ji[i0][j0] = 0.0;
+          S.jr[i1][j0] = (i1 == j0) ? 1.0 : 0.0; S.ji[i1][j0] = 0.0;
+        }
+        __syncthreads();
+        // convergence test on the raw Gram matrix (upper triangle): `viol` decides
+        // whether the stage rotates at all, `mask` which inner rounds are visited
+        {
+          unsigned my_mask = 0u;
           int viol = 0;
+#pragma unroll
           for (int e = t; e < PB * PB; e += JT) {
             const int i = e >> 5, j = e & 31;
             if (i < j) {
               const double a = S.gr[i][i], b = S.gr[j][j];
               const double xr = S.gr[i][j], xi = S.gi[i][j];
-              if (!pair_converged(a, b, xr * xr + xi * xi, tol2, floor2, neg2)) viol = 1;
+              const double g2 = xr * xr + xi * xi;
+              if (!pair_converged(a, b, g2, tol2, floor2, neg2)) viol = 1;
+              if (g2 > inner_threshold(a, b, floor2, neg2) && fmax(a, b) > 0.0)
+                my_mask |= 1u << S.round_of[i][j];
             }
           }
-          need = __syncthreads_or(viol);
-          if (need) {
-            for (int e = t; e < PB * PB; e += JT) {
-              const int i = e >> 5, j = e & 31;
-              if (i > j) { S.gr[i][j] = S.gr[j][i]; S.gi[i][j] = -S.gi[j][i]; }
-              if (i == j) S.gi[i][j] = 0.0;
-            }
-            __syncthreads();
-            inner_sweep(S, floor2, neg2);
-            // sort columns by descending norm^2 (the diagonal of the rotated Gram matrix)
-            if (t < PB) {
-              const double lam = S.gr[t][t];
-              int rank = 0;
-#pragma unroll 8
-              for (int o = 0; o < PB; ++o) {
-                const double lo = S.gr[o][o];
-                if (lo > lam || (lo == lam && o < t)) ++rank;
-              }
-              S.order[rank] = t;
-            }
-            __syncthreads();
-            for (int e = t; e < PB * PB; e += JT) {
-              const int i = e >> 5, j = e & 31;
-              const int src = S.order[j];
-              const cplx v = make_double2(S.jr[i][src], S.ji[i][src]);
-              sj[e] = v;
-              my_j[e] = v;
-            }
-            __threadfence();
-            ++my_rot;
-          }
-          __syncthreads();
-          if (t == 0) st_release(flagj + s, 2 * (g + 1) + (need ? 1 : 0));
-        } else {
-          if (t == 0) {
-            int f;
-            while ((f = ld_acquire(flagj + s)) < 2 * (g + 1)) {}
-            S.flag = f;
-          }
-          __syncthreads();
-          need = S.flag & 1;
-          if (need) {
-            for (int e = t; e < PB * PB; e += JT) sj[e] = ldcg(my_j + e);
-            __syncthreads();
+          my_mask = __reduce_or_sync(0xffffffffu, my_mask);
+          viol = __any_sync(0xffffffffu, viol);
+          if ((t & 31) == 0) {
+            if (my_mask) atomicOr(&S.mask, my_mask);
+            if (viol) S.viol = 1;
           }
         }
-        PHASE(3)
+        __syncthreads();
+        const int need = S.viol;
+        PHASE(4)
+        if (need) {
+          inner_sweep(S, S.mask, floor2, neg2);
+          PHASE(5)
+          // sort columns by descending norm^2 (the diagonal of the rotated Gram matrix)
+          {
+            const int lane = t & 31, w = t >> 5;
+            const double lo = S.gr[lane][lane];
+#pragma unroll
+            for (int c = w; c < PB; c += JT / 32) {
+              const double lam = S.gr[c][c];
+              const unsigned before = __ballot_sync(0xffffffffu,
+                                                    lo > lam || (lo == lam && lane < c));
+              if (lane == 0) S.order[__popc(before)] = c;
+            }
+          }
+          __syncthreads();
+#pragma unroll
+          for (int e = t; e < PB * PB; e += JT) {
+            const int i = e >> 5, j = e & 31;
+            const int src = S.order[j];
+            sj[e] = make_double2(S.jr[i][src], S.ji[i][src]);
+          }
+          if (leader) ++my_rot;
+          __syncthreads();
+        }
+        PHASE(6)
         // 5. apply J to this slice of [X ; W]
         if (need) {
           for (int c0 = 0; c0 < nrows; c0 += CHUNK_ROWS) {
@@ -601,22 +667,21 @@ jacobi_kernel(const cplx* __restrict__ theta, long long rs, long long cs,
             else if (crow <= 64) apply_tile<2>(tile, crow, sj, oA, oB);
             else apply_tile<4>(tile, crow, sj, oA, oB);
           }
-          __threadfence();
         }
         __syncthreads();
         if (t == 0) {   // release is cumulative over the CTA barrier above
           st_release(ready + pa * R + r_slice, g + 1);
           st_release(ready + pb * R + r_slice, g + 1);
         }
-        PHASE(4)
-        ++pc[7];
+        PHASE(7)
+        ++pc[15];
       }
     }
     // convergence vote: flags[sweep] counts the stages rotated in this sweep
     if (t == 0 && my_rot) atomicAdd(&flags[sweep], my_rot);
     grid_barrier(bar, epoch);
     const int rot = __ldcg(&flags[sweep]);
-    PHASE(5)
+    PHASE(8)
     total_rot += rot;
     sweeps_done = sweep + 1;
     if (rot == 0) { status = 0; break; }
@@ -693,13 +758,13 @@ jacobi_kernel(const cplx* __restrict__ theta, long long rs, long long cs,
           if (sqrt(tail) > thr) ++keep;
         }
       }
-      PHASE(6)
+      PHASE(9)
       hdr->keep = keep;
       hdr->s0 = s0;
       hdr->sweeps = sweeps_done;
       hdr->status = status;
       hdr->rotations = total_rot;
-      for (int k = 0; k < 8; ++k) hdr->phase_cycles[k] = pc[k];
+      for (int k = 0; k < 16; ++k) hdr->phase_cycles[k] = pc[k];
       info[0] = keep;
       info[1] = sweeps_done;
       info[2] = status;
@@ -787,7 +852,6 @@ extern "C" int b200_svd_factor(void* stream_, const void* theta, int m, int n,
   double* sval = (double*)(base + L.sval);
   int* perm = (int*)(base + L.perm);
   cplx* gpart = (cplx*)(base + L.gpart);
-  cplx* jbuf = (cplx*)(base + L.jbuf);
   cplx* y = (cplx*)(base + L.y);
 
   // header + control words are contiguous: one memset clears both (fro2 = 0, counters = 0)
@@ -808,7 +872,8 @@ extern "C" int b200_svd_factor(void* stream_, const void* theta, int m, int n,
   }
   const cplx* th = (const cplx*)theta;
   long long rs_ = rs, cs_ = cs;
-  int p = L.p, q = L.q, nb = L.nb, R = L.R, RS = L.RS, SE = L.SE, tr = L.transposed;
+  int p = L.p, q = L.q, nb = L.nb, Rx = L.Rx, Rw = L.Rw, RSx = L.RSx, RSw = L.RSw, SE = L.SE,
+      tr = L.transposed;
   int minmn = (m < n) ? m : n;
   // relative orthogonality target |cos| <= 1e-11 (singular values are second order in
   // it); never tighter than the rounding level of a length-p dot product
@@ -816,8 +881,9 @@ extern "C" int b200_svd_factor(void* stream_, const void* theta, int m, int n,
   if (tol < 1e-11) tol = 1e-11;
   // columns below 1e-2*eps*||X||_F can never be kept nor change the rank decision
   double neg_rel = (eps > 0.0) ? 1e-2 * eps : 0.0;
-  void* args[] = {&th, &rs_, &cs_, &y, &gpart, &jbuf, &ctrl, &sig2, &sval, &perm, &hdr,
-                  &info_host, &p, &q, &nb, &R, &RS, &SE, &tr, &minmn, &tol, &eps, &neg_rel};
+  void* args[] = {&th, &rs_, &cs_, &y, &gpart, &ctrl, &sig2, &sval, &perm, &hdr,
+                  &info_host, &p, &q, &nb, &Rx, &Rw, &RSx, &RSw, &SE, &tr, &minmn, &tol, &eps,
+                  &neg_rel};
   const int grid = L.SE * L.R;
   b200::profile_begin(stream);
   B200_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)jacobi_kernel, dim3(grid), dim3(JT),
@@ -854,12 +920,12 @@ extern "C" int b200_svd_emit(void* stream_, const void* work, const void* theta,
   return B200_OK;
 }
 
-extern "C" int b200_svd_phase_cycles(void* stream_, const void* work, long long* out8) {
-  if (!work || !out8) { b200::set_error("b200_svd_phase_cycles: invalid argument"); return B200_EINVAL; }
+extern "C" int b200_svd_phase_cycles(void* stream_, const void* work, long long* out16) {
+  if (!work || !out16) { b200::set_error("b200_svd_phase_cycles: invalid argument"); return B200_EINVAL; }
   Header h;
   B200_CUDA_CHECK(cudaMemcpyAsync(&h, work, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream_));
   B200_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream_));
-  for (int k = 0; k < 8; ++k) out8[k] = h.phase_cycles[k];
+  for (int k = 0; k < 16; ++k) out16[k] = h.phase_cycles[k];
   return B200_OK;
 }
 

@@ -27,7 +27,9 @@ def main():
         t0 = time.perf_counter()
         h = orig(theta, m, n, rs, cs, eps, off)
         torch.cuda.synchronize()
-        rec.append((m, n, h.keep, h.sweeps, (time.perf_counter() - t0) * 1e3))
+        ms = (time.perf_counter() - t0) * 1e3
+        pc = ops.svd_phase_cycles(h)
+        rec.append((m, n, h.keep, h.sweeps, ms, pc))
         return h
 
     ops.svd_factor = timed
@@ -40,7 +42,10 @@ def main():
     rec_sorted = sorted(rec, key=lambda r: -r[4])
     print("top 15 (m, n, keep, sweeps, ms):")
     for r in rec_sorted[:15]:
-        print("  ", r[0], r[1], r[2], r[3], round(r[4], 2))
+        print("  ", r[0], r[1], r[2], r[3], round(r[4], 2), "phase kcyc", [round(c / 1e3) for c in r[5][:10]], "stages", r[5][15])
+    print("typical mid-size (every 25th call):")
+    for r in rec[5::25]:
+        print("  ", r[0], r[1], r[2], r[3], round(r[4], 3), "phase kcyc", [round(c / 1e3) for c in r[5][:10]], "stages", r[5][15])
     # histogram by min dimension
     bins = [0, 32, 64, 128, 256, 512, 1024, 4096]
     for lo, hi in zip(bins[:-1], bins[1:]):
