@@ -285,7 +285,7 @@ def gpu_arm(args):
         "gpu_launches": int(cnt[0]),
         "clocks": clocks,
         "roofline": {
-            "kernel": "jacobi_kernel (block-Jacobi truncated SVD, fp64 DMMA)",
+            "kernel": "jacobi_kernel (row-sliced block-Jacobi truncated SVD, fp64)",
             "bound": "tensor", "achieved": achieved, "peak": peak,
             "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
             "traffic": traffic,
