@@ -81,9 +81,8 @@ int device_sms() {
 
 // ctrl region (ints, zeroed by one memset per factorisation):
 //   [0]            grid barrier counter
-//   [1]            done: a sweep finished without any rotation (set once)
+//   [1]            spare
 //   [2 .. 2+NFLAGS)           rotated-stage count per sweep
-//   reports[NFLAGS]           slots that finished the sweep
 //   ready[nb*R]               stages completed per (block, slice)
 //   cnt[2*S]                  slices that published their partial Gram (double-buffered)
 __host__ Layout make_layout(int m, int n) {
@@ -128,7 +127,7 @@ __host__ Layout make_layout(int m, int n) {
   size_t off = 0;
   L.header = off; off = align256(off + sizeof(Header));
   L.ctrl = off;
-  L.ctrl_bytes = sizeof(int) * (size_t)(2 + 2 * NFLAGS + (size_t)L.nb * L.R + 2 * (size_t)L.S);
+  L.ctrl_bytes = sizeof(int) * (size_t)(2 + NFLAGS + (size_t)L.nb * L.R + 2 * (size_t)L.S);
   off = align256(off + L.ctrl_bytes);
   L.sig2 = off; off = align256(off + (size_t)L.nb * BC * sizeof(double));
   L.sval = off; off = align256(off + (size_t)L.nb * BC * sizeof(double));
@@ -225,7 +224,6 @@ struct InnerShared {
   int order[PB];
   unsigned mask;                    // rounds that hold a violating pair
   int viol;
-  int stop;                         // convergence observed: leave the sweep loops
 };
 
 // threshold of the inner rotations: a pair is rotated when |g|^2 exceeds it
@@ -415,20 +413,18 @@ jacobi_kernel(const cplx* __restrict__ theta, long long rs, long long cs,
               int Rx, int Rw, int RSx, int RSw, int SE, int transposed, int minmn,
               double tol, double eps, double neg_rel) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
+  __shared__ InnerShared S;
   __shared__ double s_red[JT / 32];
   cplx* tile = reinterpret_cast<cplx*>(dyn_smem);          // [CHUNK][32]
   cplx* sj = tile + (size_t)CHUNK_ROWS * PB;               // [32][32] rotation to apply
   cplx* sg = sj + PB * PB;                                 // [32][32] scratch (Gram halves)
-  InnerShared& S = *reinterpret_cast<InnerShared*>(sg + PB * PB);
 
   const int T = p + q;
   const int R = Rx + Rw;
   const int S_slots = nb / 2;
   int* bar = ctrl;
-  int* done = ctrl + 1;
   int* flags = ctrl + 2;
-  int* reports = flags + NFLAGS;
-  int* ready = reports + NFLAGS;
+  int* ready = flags + NFLAGS;
   int* cnt = ready + (size_t)nb * R;
   int epoch = 0;
   const int t = threadIdx.x;
@@ -496,20 +492,11 @@ jacobi_kernel(const cplx* __restrict__ theta, long long rs, long long cs,
   const bool single_chunk = nrows <= CHUNK_ROWS;
   const bool leader = (r_slice == 0);
 
-  // Convergence is detected WITHOUT a grid barrier per sweep: every slot leader adds its
-  // rotated stages to flags[sweep] and then reports; a CTA that sees a fully reported
-  // sweep with zero rotations raises `done` and leaves, and everybody polling a flag
-  // also polls `done`.  (After a rotation-free sweep the data is final and every later
-  // stage is a no-op, so it does not matter at which stage a CTA leaves.)
-  int sweeps_done = MAX_SWEEPS, total_rot = 0, status = 1;
-  int chk = 0;                       // thread 0: first sweep not yet known to be complete
-  bool stop = false;
-  int nled = 0;                      // slots this CTA leads
-  if (leader) for (int s = s_first; s < S_slots; s += SE) ++nled;
+  int sweeps_done = 0, total_rot = 0, status = 1;
   const double tol2 = tol * tol;
   const double neg2 = (neg_rel * fro) * (neg_rel * fro);
   int pa = 0, pb = 0;
-  for (int sweep = 0; sweep < MAX_SWEEPS && !stop; ++sweep) {
+  for (int sweep = 0; sweep < MAX_SWEEPS; ++sweep) {
     int my_rot = 0;
     // absolute floor: 8 eps ||X||_F, doubled every sweep after FLOOR_GROW_AFTER so that
     // the iteration always terminates
@@ -517,10 +504,10 @@ jacobi_kernel(const cplx* __restrict__ theta, long long rs, long long cs,
     for (int k = FLOOR_GROW_AFTER; k < sweep; ++k) kappa *= 2.0;
     const double floor_ = kappa * 2.220446049250313e-16 * fro;
     const double floor2 = floor_ * floor_;
-    for (int stage = 0; stage < nb - 1 && !stop; ++stage) {
+    for (int stage = 0; stage < nb - 1; ++stage) {
       const int g = sweep * (nb - 1) + stage;
       const int par = g & 1;
-      for (int s = s_first; s < S_slots && !stop; s += SE) {
+      for (int s = s_first; s < S_slots; s += SE) {
         outer_pair(s, stage, nb, pa, pb);
         cplx* gA = y + pa * blk_elems + (size_t)row0 * BC;
         cplx* gB = y + pb * blk_elems + (size_t)row0 * BC;
@@ -528,22 +515,13 @@ jacobi_kernel(const cplx* __restrict__ theta, long long rs, long long cs,
         if (xrows == 0 && t == 0) red_release_add(cnt + par * S_slots + s, 1);
         // 1. wait until both input blocks (this slice) have finished the previous stage
         if (t == 0) {
-          int st = 0;
-          while (chk < sweep) {       // has an earlier sweep completed without rotations?
-            if (ld_acquire(reports + chk) < S_slots) break;
-            total_rot += __ldcg(flags + chk);
-            if (__ldcg(flags + chk) == 0) { st = 1; st_release(done, 1); break; }
-            ++chk;
-          }
-          while (!st && ld_acquire(ready + pa * R + r_slice) < g) st = ld_acquire(done);
-          while (!st && ld_acquire(ready + pb * R + r_slice) < g) st = ld_acquire(done);
+          while (ld_acquire(ready + pa * R + r_slice) < g) {}
+          while (ld_acquire(ready + pb * R + r_slice) < g) {}
           S.mask = 0u;
           S.viol = 0;
-          S.stop = st;
         }
         __syncthreads();
         PHASE(0)
-        if (S.stop) { stop = true; break; }
         // 2./3. stage the slice, partial Gram of the X rows
         double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (int c0 = 0; c0 < nrows; c0 += CHUNK_ROWS) {
@@ -582,13 +560,10 @@ jacobi_kernel(const cplx* __restrict__ theta, long long rs, long long cs,
         // 4. every slice: wait for all partials, reduce (fixed order), test, solve
         if (t == 0) {
           const int want = (g / 2 + 1) * R;     // cnt is cumulative per parity
-          int st = 0;
-          while (!st && ld_acquire(cnt + par * S_slots + s) < want) st = ld_acquire(done);
-          S.stop = st;
+          while (ld_acquire(cnt + par * S_slots + s) < want) {}
         }
         __syncthreads();
         PHASE(3)
-        if (S.stop) { stop = true; break; }
         {
           const cplx* base = gpart + (size_t)(par * S_slots + s) * R * (PB * PB);
           // thread t sums the entries (i0, j0) of the upper half and (i0+16, j0) of the
@@ -652,9 +627,7 @@ jacobi_kernel(const cplx* __restrict__ theta, long long rs, long long cs,
         const int need = S.viol;
         PHASE(4)
         if (need) {
-          // late sweeps (few violating rounds) visit only those; earlier every round,
-          // because rotations fill other pairs in to first order
-          inner_sweep(S, (__popc(S.mask) >= 6) ? 0x7fffffffu : S.mask, floor2, neg2);
+          inner_sweep(S, S.mask, floor2, neg2);
           PHASE(5)
           // sort columns by descending norm^2 (the diagonal of the rotated Gram matrix)
           {
@@ -705,24 +678,13 @@ jacobi_kernel(const cplx* __restrict__ theta, long long rs, long long cs,
       }
     }
     // convergence vote: flags[sweep] counts the stages rotated in this sweep
-    if (!stop && leader && t == 0) {
-      if (my_rot) atomicAdd(&flags[sweep], my_rot);
-      __threadfence();
-      red_release_add(reports + sweep, nled);
-    }
+    if (t == 0 && my_rot) atomicAdd(&flags[sweep], my_rot);
+    grid_barrier(bar, epoch);
+    const int rot = __ldcg(&flags[sweep]);
     PHASE(8)
-  }
-  // everybody agrees on the sweep that converged: the first fully reported one without
-  // rotations (all reports of a sweep precede `done`)
-  grid_barrier(bar, epoch);
-  if (__ldcg(done)) {
-    status = 0;
-    total_rot = 0;
-    for (int k = 0; k < MAX_SWEEPS; ++k) {
-      const int f = __ldcg(flags + k);
-      if (__ldcg(reports + k) >= S_slots && f == 0) { sweeps_done = k + 1; break; }
-      total_rot += f;
-    }
+    total_rot += rot;
+    sweeps_done = sweep + 1;
+    if (rot == 0) { status = 0; break; }
   }
 
   // ---- sigma_j^2 = ||X[:, j]||^2 : one warp per column block, all CTAs
@@ -860,8 +822,7 @@ __global__ void emit_kernel(const cplx* __restrict__ y, const double* __restrict
   }
 }
 
-constexpr size_t kDynSmem = (size_t)CHUNK_ROWS * PB * sizeof(cplx) + 2 * PB * PB * sizeof(cplx) +
-                            sizeof(InnerShared);
+constexpr size_t kDynSmem = (size_t)CHUNK_ROWS * PB * sizeof(cplx) + 2 * PB * PB * sizeof(cplx);
 
 }  // namespace
 
