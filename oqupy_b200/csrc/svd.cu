@@ -195,34 +195,29 @@ __device__ __forceinline__ void outer_pair(int idx, int stage, int nb, int& pa, 
   pb = 1 + ((kb - 1 + stage) % (nb - 1));
   if (pa > pb) { const int t = pa; pa = pb; pb = t; }
 }
-// inner ordering over 32 columns, 31 rounds of 16 disjoint pairs: rounds 0..15 pair
-// every column of the first block with every column of the second (the pairs that have
-// never met), rounds 16..30 are two simultaneous 16-player tournaments inside the blocks.
-__device__ __forceinline__ void inner_pair(int round, int k, int& i, int& j) {
-  if (round < BC) {
-    i = k;
-    j = BC + ((k + round) & (BC - 1));
-  } else {
-    const int st = round - BC;          // 0..14
-    const int half = k >> 3, kk = k & 7;
-    const int ka = kk, kb = BC - 1 - kk;
-    int a = (ka == 0) ? 0 : 1 + ((ka - 1 + st) % (BC - 1));
-    int b = 1 + ((kb - 1 + st) % (BC - 1));
-    if (a > b) { const int t = a; a = b; b = t; }
-    i = half * BC + a;
-    j = half * BC + b;
-  }
+// Inner ordering over 32 columns: round r pairs column i with i XOR k(r), k = 16..31
+// (every column of the first block with every column of the second: the pairs that
+// have never met) and then k = 1..15 (inside the blocks).  Every pair meets exactly once
+// and a partner is one butterfly shuffle away.
+__device__ __forceinline__ int round_xor(int round) { return (round < BC) ? BC + round : round - (BC - 1); }
+__device__ __forceinline__ int round_of_pair(int i, int j) {
+  const int k = i ^ j;
+  return (k & BC) ? (k - BC) : (k + BC - 1);
+}
+// pair index a in [0,16) -> smaller column of the pair (the bit hb = msb(k) is cleared)
+__device__ __forceinline__ int pair_first(int a, int hb) {
+  return ((a >> hb) << (hb + 1)) | (a & ((1 << hb) - 1));
+}
+__device__ __forceinline__ int pair_index(int col, int hb) {
+  return ((col >> (hb + 1)) << hb) | (col & ((1 << hb) - 1));
 }
 
 struct InnerShared {
   double gr[PB][GP], gi[PB][GP];   // Hermitian working matrix
-  double jr[PB][GP], ji[PB][GP];   // accumulated rotations
   double rc[BC], rsr[BC], rsi[BC]; // per pair of the round: c, s e^{i phi}
   int ract[BC];
-  unsigned short sched[PB - 1][BC]; // inner ordering: p | q << 8
-  unsigned char round_of[PB][PB];   // round in which the pair (i, j) meets
-  int order[PB];
-  unsigned mask;                    // rounds that hold a violating pair
+  int rank[PB];                    // position of column c after sorting by norm
+  unsigned mask;                   // rounds that hold a violating pair
   int viol;
 };
 
@@ -236,63 +231,69 @@ __device__ __forceinline__ double inner_threshold(double a, double b, double flo
   return (big < neg2) ? loose : strict;
 }
 
-// One cyclic sweep of two-sided Jacobi on the 32x32 Hermitian matrix S.gr + i S.gi,
-// accumulating J; only the rounds in `mask` are visited.  Threads 0..255 own the 2x2
-// blocks of G: thread (a, b), a, b in [0,16), owns (rows of pair a) x (columns of pair
-// b); G' = R_a^H G R_b touches only its own four entries, so the update is in place, and
-// the diagonal-block thread (a, a) holds exactly the three numbers the rotation of pair
-// a is made from.  Threads 256..511 own two rows x one column pair of J each.
-// R = [[c, se], [-conj(se), c]] acting on columns (p, q).
-__device__ void inner_sweep(InnerShared& S, unsigned mask, double floor2, double neg2) {
+// One cyclic sweep of two-sided Jacobi on the 32x32 Hermitian matrix S.gr + i S.gi; only
+// the rounds in `mask` are visited.  The accumulated rotation J (columns sorted by
+// descending norm) is left in sj[32][32].
+//   * threads 0..255 own the 2x2 blocks of G in shared memory: thread (a, b) owns (rows
+//     of pair a) x (columns of pair b); G' = R_a^H G R_b touches only its own four
+//     entries, so the update is in place, and the diagonal-block thread (a, a) holds
+//     exactly the three numbers the rotation of pair a is made from;
+//   * J never touches shared memory during the sweep: warps 8..11 keep it in REGISTERS,
+//     lane = column, 8 rows per warp; J' = J R mixes column j with column j XOR k, one
+//     __shfl_xor away.  (The sweep is bound by shared-memory traffic; this halves it.)
+// R = [[c, se], [-conj(se), c]] acting on columns (p, q = p XOR k).
+__device__ void inner_sweep(InnerShared& S, unsigned mask, double floor2, double neg2,
+                            cplx* __restrict__ sj) {
   const int t = threadIdx.x;
   const bool gthread = t < 256;
-  const int u = t & 255;
-  const int a = u >> 4, b = u & 15;
+  const bool jthread = (t >= 256) && (t < 384);
+  const int a = (t >> 4) & 15, b = t & 15;
+  const int lane = t & 31, jrow0 = ((t - 256) >> 5) * 8;
+  cplx jv[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) jv[r] = make_double2((jthread && jrow0 + r == lane) ? 1.0 : 0.0, 0.0);
   while (mask) {
     const int round = __ffs(mask) - 1;
     mask &= mask - 1;
-    const int sa = S.sched[round][a], sb = S.sched[round][b];
-    const int pa = sa & 0xff, qa = sa >> 8, pb = sb & 0xff, qb = sb >> 8;
-    double g00r, g00i, g01r, g01i, g10r, g10i, g11r, g11i;
-    const int r0 = gthread ? pa : 2 * a, r1 = gthread ? qa : 2 * a + 1;
+    const int k = round_xor(round);
+    const int hb = 31 - __clz(k);
+    const int pa = pair_first(a, hb), qa = pa ^ k, pb = pair_first(b, hb), qb = pb ^ k;
+    double g00r = 0, g00i = 0, g01r = 0, g01i = 0, g10r = 0, g10i = 0, g11r = 0, g11i = 0;
     if (gthread) {
-      g00r = S.gr[r0][pb]; g00i = S.gi[r0][pb]; g01r = S.gr[r0][qb]; g01i = S.gi[r0][qb];
-      g10r = S.gr[r1][pb]; g10i = S.gi[r1][pb]; g11r = S.gr[r1][qb]; g11i = S.gi[r1][qb];
-    } else {
-      g00r = S.jr[r0][pb]; g00i = S.ji[r0][pb]; g01r = S.jr[r0][qb]; g01i = S.ji[r0][qb];
-      g10r = S.jr[r1][pb]; g10i = S.ji[r1][pb]; g11r = S.jr[r1][qb]; g11i = S.ji[r1][qb];
-    }
-    if (gthread && a == b) {
-      // straight-line: the rotation and the test are independent dependency chains
-      const double mag2 = fma(g01r, g01r, g01i * g01i);
-      const double thr = inner_threshold(g00r, g11r, floor2, neg2);
-      // cos(2t) = |h|/r, c = sqrt((1+cos 2t)/2), s e^{i phi} = sign(h) g/(2 r c)
-      const double h = 0.5 * (g11r - g00r);
-      const double inv_r = rsqrt(fma(h, h, mag2) + 1e-300);
-      const double w = fma(0.5 * fabs(h), inv_r, 0.5);
-      const double ic = rsqrt(w);            // two rsqrt: no sqrt, no division
-      const double k = ((h >= 0.0) ? 0.5 : -0.5) * inv_r * ic;
-      const bool act = (mag2 > thr) && (fmax(g00r, g11r) > 0.0);
-      S.ract[a] = act ? 1 : 0;
-      S.rc[a] = act ? w * ic : 1.0;
-      S.rsr[a] = act ? g01r * k : 0.0;
-      S.rsi[a] = act ? g01i * k : 0.0;
+      g00r = S.gr[pa][pb]; g00i = S.gi[pa][pb]; g01r = S.gr[pa][qb]; g01i = S.gi[pa][qb];
+      g10r = S.gr[qa][pb]; g10i = S.gi[qa][pb]; g11r = S.gr[qa][qb]; g11i = S.gi[qa][qb];
+      if (a == b) {
+        // straight-line: the rotation and the test are independent dependency chains
+        const double mag2 = fma(g01r, g01r, g01i * g01i);
+        const double thr = inner_threshold(g00r, g11r, floor2, neg2);
+        // cos(2t) = |h|/r, c = sqrt((1+cos 2t)/2), s e^{i phi} = sign(h) g/(2 r c)
+        const double h = 0.5 * (g11r - g00r);
+        const double inv_r = rsqrt(fma(h, h, mag2) + 1e-300);
+        const double w = fma(0.5 * fabs(h), inv_r, 0.5);
+        const double ic = rsqrt(w);            // two rsqrt: no sqrt, no division
+        const double kk = ((h >= 0.0) ? 0.5 : -0.5) * inv_r * ic;
+        const bool act = (mag2 > thr) && (fmax(g00r, g11r) > 0.0);
+        S.ract[a] = act ? 1 : 0;
+        S.rc[a] = act ? w * ic : 1.0;
+        S.rsr[a] = act ? g01r * kk : 0.0;
+        S.rsi[a] = act ? g01i * kk : 0.0;
+      }
     }
     __syncthreads();
-    const int aa = gthread ? S.ract[a] : 0, ab = S.ract[b];
-    if (aa | ab) {
-      const double cb = S.rc[b], sbr = S.rsr[b], sbi = S.rsi[b];
-      // column op: T[:,0] = cb g[:,0] - conj(seb) g[:,1] ; T[:,1] = seb g[:,0] + cb g[:,1]
-      const double t00r = cb * g00r - (sbr * g01r + sbi * g01i);
-      const double t00i = cb * g00i - (sbr * g01i - sbi * g01r);
-      const double t01r = cb * g01r + (sbr * g00r - sbi * g00i);
-      const double t01i = cb * g01i + (sbr * g00i + sbi * g00r);
-      const double t10r = cb * g10r - (sbr * g11r + sbi * g11i);
-      const double t10i = cb * g10i - (sbr * g11i - sbi * g11r);
-      const double t11r = cb * g11r + (sbr * g10r - sbi * g10i);
-      const double t11i = cb * g11i + (sbr * g10i + sbi * g10r);
-      if (gthread) {
+    if (gthread) {
+      const int aa = S.ract[a], ab = S.ract[b];
+      if (aa | ab) {
+        const double cb = S.rc[b], sbr = S.rsr[b], sbi = S.rsi[b];
         const double ca = S.rc[a], sar = S.rsr[a], sai = S.rsi[a];
+        // column op: T[:,0] = cb g[:,0] - conj(seb) g[:,1] ; T[:,1] = seb g[:,0] + cb g[:,1]
+        const double t00r = cb * g00r - (sbr * g01r + sbi * g01i);
+        const double t00i = cb * g00i - (sbr * g01i - sbi * g01r);
+        const double t01r = cb * g01r + (sbr * g00r - sbi * g00i);
+        const double t01i = cb * g01i + (sbr * g00i + sbi * g00r);
+        const double t10r = cb * g10r - (sbr * g11r + sbi * g11i);
+        const double t10i = cb * g10i - (sbr * g11i - sbi * g11r);
+        const double t11r = cb * g11r + (sbr * g10r - sbi * g10i);
+        const double t11i = cb * g11i + (sbr * g10i + sbi * g10r);
         // row op: G'[0,:] = ca T[0,:] - sea T[1,:] ; G'[1,:] = conj(sea) T[0,:] + ca T[1,:]
         double n00r = ca * t00r - (sar * t10r - sai * t10i);
         double n00i = ca * t00i - (sar * t10i + sai * t10r);
@@ -306,15 +307,48 @@ __device__ void inner_sweep(InnerShared& S, unsigned mask, double floor2, double
           n00i = 0.0; n11i = 0.0;
           n01r = 0.0; n01i = 0.0; n10r = 0.0; n10i = 0.0;
         }
-        S.gr[r0][pb] = n00r; S.gi[r0][pb] = n00i; S.gr[r0][qb] = n01r; S.gi[r0][qb] = n01i;
-        S.gr[r1][pb] = n10r; S.gi[r1][pb] = n10i; S.gr[r1][qb] = n11r; S.gi[r1][qb] = n11i;
-      } else {
-        S.jr[r0][pb] = t00r; S.ji[r0][pb] = t00i; S.jr[r0][qb] = t01r; S.ji[r0][qb] = t01i;
-        S.jr[r1][pb] = t10r; S.ji[r1][pb] = t10i; S.jr[r1][qb] = t11r; S.ji[r1][qb] = t11i;
+        S.gr[pa][pb] = n00r; S.gi[pa][pb] = n00i; S.gr[pa][qb] = n01r; S.gi[pa][qb] = n01i;
+        S.gr[qa][pb] = n10r; S.gi[qa][pb] = n10i; S.gr[qa][qb] = n11r; S.gi[qa][qb] = n11i;
+      }
+    } else if (jthread) {
+      // column `lane` of J: new = c * own + be * partner, be = se (second of the pair)
+      // or -conj(se) (first)
+      const bool second = (lane >> hb) & 1;
+      const int pi = pair_index(second ? (lane ^ k) : lane, hb);
+      const int act = S.ract[pi];
+      const double c = S.rc[pi];
+      const double ber = second ? S.rsr[pi] : -S.rsr[pi], bei = S.rsi[pi];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const double pr = __shfl_xor_sync(0xffffffffu, jv[r].x, k);
+        const double pim = __shfl_xor_sync(0xffffffffu, jv[r].y, k);
+        if (act) {
+          const double nr = c * jv[r].x + (ber * pr - bei * pim);
+          const double ni = c * jv[r].y + (ber * pim + bei * pr);
+          jv[r] = make_double2(nr, ni);
+        }
       }
     }
     __syncthreads();
   }
+  // sort columns by descending norm^2 (the diagonal of the rotated Gram matrix)
+  {
+    const int w = t >> 5;
+    const double lo = S.gr[lane][lane];
+#pragma unroll
+    for (int c = w; c < PB; c += JT / 32) {
+      const double lam = S.gr[c][c];
+      const unsigned before = __ballot_sync(0xffffffffu, lo > lam || (lo == lam && lane < c));
+      if (lane == 0) S.rank[c] = __popc(before);
+    }
+  }
+  __syncthreads();
+  if (jthread) {
+    const int dst = S.rank[lane];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) sj[(jrow0 + r) * PB + dst] = jv[r];
+  }
+  __syncthreads();
 }
 
 // Partial Gram matrix of `rows` rows of the staged tile ([row][32] complex) into
@@ -434,14 +468,6 @@ jacobi_kernel(const cplx* __restrict__ theta, long long rs, long long cs,
   long long tq = clock64();
 #define PHASE(k) { const long long tn_ = clock64(); pc[k] += tn_ - tq; tq = tn_; }
 
-  // inner ordering table
-  for (int e = t; e < (PB - 1) * BC; e += JT) {
-    int i, j;
-    inner_pair(e / BC, e % BC, i, j);
-    S.sched[e / BC][e % BC] = (unsigned short)(i | (j << 8));
-    S.round_of[i][j] = (unsigned char)(e / BC);
-    S.round_of[j][i] = (unsigned char)(e / BC);
-  }
   // ---- load: Y = [X ; I], ||X||_F^2
   {
     double local = 0.0;
@@ -595,8 +621,6 @@ jacobi_kernel(const cplx* __restrict__ theta, long long rs, long long cs,
             S.gr[i1][j0] = s1r; S.gi[i1][j0] = s1i;
             S.gr[j0][i1] = s1r; S.gi[j0][i1] = -s1i;
           }
-          S.jr[i0][j0] = (i0 == j0) ? 1.0 : 0.0; S.ji[i0][j0] = 0.0;
-          S.jr[i1][j0] = (i1 == j0) ? 1.0 : 0.0; S.ji[i1][j0] = 0.0;
         }
         __syncthreads();
         // convergence test on the raw Gram matrix (upper triangle): `viol` decides
@@ -613,7 +637,7 @@ jacobi_kernel(const cplx* __restrict__ theta, long long rs, long long cs,
               const double g2 = xr * xr + xi * xi;
               if (!pair_converged(a, b, g2, tol2, floor2, neg2)) viol = 1;
               if (g2 > inner_threshold(a, b, floor2, neg2) && fmax(a, b) > 0.0)
-                my_mask |= 1u << S.round_of[i][j];
+                my_mask |= 1u << round_of_pair(i, j);
             }
           }
           my_mask = __reduce_or_sync(0xffffffffu, my_mask);
@@ -627,27 +651,8 @@ jacobi_kernel(const cplx* __restrict__ theta, long long rs, long long cs,
         const int need = S.viol;
         PHASE(4)
         if (need) {
-          inner_sweep(S, S.mask, floor2, neg2);
+          inner_sweep(S, S.mask, floor2, neg2, sj);
           PHASE(5)
-          // sort columns by descending norm^2 (the diagonal of the rotated Gram matrix)
-          {
-            const int lane = t & 31, w = t >> 5;
-            const double lo = S.gr[lane][lane];
-#pragma unroll
-            for (int c = w; c < PB; c += JT / 32) {
-              const double lam = S.gr[c][c];
-              const unsigned before = __ballot_sync(0xffffffffu,
-                                                    lo > lam || (lo == lam && lane < c));
-              if (lane == 0) S.order[__popc(before)] = c;
-            }
-          }
-          __syncthreads();
-#pragma unroll
-          for (int e = t; e < PB * PB; e += JT) {
-            const int i = e >> 5, j = e & 31;
-            const int src = S.order[j];
-            sj[e] = make_double2(S.jr[i][src], S.ji[i][src]);
-          }
           if (leader) ++my_rot;
           __syncthreads();
         }
