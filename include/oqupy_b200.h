@@ -31,7 +31,7 @@ int b200_abi_version(void);
 uint64_t b200_launch_count(void);
 
 /* Live per-kernel timing for the roofline report (bench.py): when enabled, every
- * launch of the dominant kernel (the block-Jacobi SVD sweep kernel) is bracketed by
+ * launch of the dominant kernel (jacobi_kernel, the truncated SVD) is bracketed by
  * CUDA events on its own stream.  b200_profile_read synchronises the device, adds
  * up the finished launches and returns: total kernel milliseconds, total
  * ALGORITHMIC flops (4*(14 m n^2 + 8 n^3), m >= n, per truncated SVD),
@@ -66,7 +66,7 @@ int b200_zgemm_strided(void* stream, int m, int n, int k, int nb1, int nb2,
                        int64_t s_b2, int accumulate);
 
 /* ---------------------------------------------------------------------------
- * eps-truncated SVD  (one-sided block-Jacobi, fp64 DMMA Gram/apply panels).
+ * eps-truncated SVD  (one-sided block Jacobi, row-sliced 2-D grid, one cooperative launch).
  *
  * b200_svd_factor: theta is an m x n matrix addressed theta[i*rs + j*cs].
  *   Computes all singular triplets on the device, sorts them, applies the
