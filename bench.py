@@ -107,6 +107,11 @@ def run_cpu(steps, warmup, budget_s, infl):
     """The oracle port (numpy/LAPACK restatement of the reference path) on the host
     cores: same step window; stops early when the time budget is exhausted."""
     from oracle import tempo_np as onp
+    try:    # torchrun exports OMP_NUM_THREADS=1: give LAPACK/BLAS all host cores back
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:  # pylint: disable=broad-except
+        pass
     pt = onp.PtTempoOracle(2, influence_fn(infl), 1000, 200, 1e-9)
     pt.initialize()
     for _ in range(warmup):
@@ -257,8 +262,10 @@ def gpu_arm(args):
     big = max(svd_log, key=lambda x: x[0] * x[1]) if svd_log else None
 
     # bounded CPU baseline on this box's host cores (oracle port), same step window
+    # (rank 0, N=1 only: with N > 1 the other ranks' host threads share the cores)
     cdone, cdt, _ = run_cpu(args.steps, args.warmup, args.cpu_budget,
-                            load_operands(0)[1]) if not args.no_cpu else (0, 1.0, None)
+                            load_operands(0)[1]) \
+        if not (args.no_cpu or world > 1) else (0, 1.0, None)
     cpu_val = cdone / cdt if cdone else None
 
     line = {
