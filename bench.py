@@ -210,6 +210,8 @@ def gpu_arm(args):
     ops.profile_enable(True)
     ops.profile_read()
     ops.svd_log = []
+    be.pop_svd_log()                 # native chain: switch the per-SVD log on
+    be.chain_stats(reset=True)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -230,8 +232,9 @@ def gpu_arm(args):
     h2d, d2h = ops.h2d_bytes - h0, ops.d2h_bytes - d0
     k_ms, k_flops, k_launches, k_sweeps = ops.profile_read()
     ops.profile_enable(False)
-    svd_log = ops.svd_log
+    svd_log = ops.svd_log + be.pop_svd_log()
     ops.svd_log = None
+    d2h += be.chain_stats()[2]       # the 16-byte keep read-backs of the native chain
 
     t = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device=dev)
     cnt = torch.tensor([launches], dtype=torch.float64, device=dev)

@@ -104,6 +104,52 @@ int b200_svd_values(void* stream, const void* work, int m, int n, double* s_out)
 int b200_svd_phase_cycles(void* stream, const void* work, long long* out16);
 
 /* ---------------------------------------------------------------------------
+ * Native matrix-product chain: the device-resident counterpart of NodeArray for the
+ * PT-TEMPO path (oqupy/backends/node_array.py).  A chain owns its sites
+ * (chi_l, a, chi_r) in device memory and runs a whole zip-up / svd-sweep in ONE call
+ * (contraction GEMM -> truncated SVD -> exact-size outputs, site after site; the only
+ * host round trip per site is the 16-byte `keep` read-back).
+ *
+ * b200_chain_pt_zip_up_left replaces mps.zip_up(mpo, axes=[(0,0)], right_index=-1,
+ *   direction="left", max_truncation_err=eps, relative=True)
+ *   (oqupy/backends/pt_tempo_backend.py:267-274 -> node_array.py:482-552) for the
+ *   implicit (delta-structured) PT-TEMPO influence MPO (pt_tempo_backend.py:142-152):
+ *     kind FIRST  B[x,y,r]   = d_xy d_xr vec[x]          mat = vec (rows entries)
+ *     kind MID    B[l,x,y,r] = d_lr d_xy mat[l,x]         mat (rows x cols)
+ *     kind LAST   B[l,0,y,0] = mat[l,y]                   newest site
+ *     kind CLOSED B[l,x,y,0] = d_xy mat[l,x]              end phase (mat times closing vector)
+ * b200_chain_svd_sweep replaces mps.svd_sweep(from_index, to_index, eps, relative=True)
+ *   (pt_tempo_backend.py:171-181, 276-280 -> node_array.py:226-299); negative indices
+ *   count from the end.
+ */
+#define B200_PT_FIRST 0
+#define B200_PT_MID 1
+#define B200_PT_LAST 2
+#define B200_PT_CLOSED 3
+typedef struct {
+  int kind;
+  int rows, cols;
+  const void* mat; /* device, complex128, row-major */
+} b200_pt_site;
+
+void* b200_chain_create(void* stream);
+int b200_chain_destroy(void* chain);
+int b200_chain_len(void* chain);
+/* append a site (copied device-to-device) */
+int b200_chain_push(void* chain, const void* dev_src, int chi_l, int a, int chi_r);
+int b200_chain_shape(void* chain, int i, int32_t* out3);
+/* copy site i (contiguous) into caller-owned device memory */
+int b200_chain_read(void* chain, int i, void* dev_dst);
+int b200_chain_svd_sweep(void* chain, int from_index, int to_index, double eps);
+int b200_chain_pt_zip_up_left(void* chain, const b200_pt_site* mpo, int n_mpo, double eps);
+/* counters since the last reset: truncated SVDs, Jacobi sweeps, D2H bytes (keep read-backs) */
+int b200_chain_stats(void* chain, uint64_t* nsvd, uint64_t* sweeps, uint64_t* d2h_bytes,
+                     int reset);
+/* per-SVD log (m, n, keep, sweeps as 4 x int32): returns the entries copied to `out`
+ * (and clears them); `enable` switches logging on/off */
+int b200_chain_log(void* chain, int enable, int32_t* out, int cap_entries);
+
+/* ---------------------------------------------------------------------------
  * compute_dynamics step for ONE environment and `nvec` ensemble members that
  * share the process tensor (oqupy/system_dynamics.py:631-700):
  *   v'[e, r, j] = sum_x P2[e][j,x] * sum_l T[l, r, x] * (sum_i P1[e][x,i] v[e, l, i])

@@ -20,6 +20,9 @@ EXPORTS = [
     "b200_zgemm_strided", "b200_svd_workspace_bytes", "b200_svd_factor",
     "b200_svd_emit", "b200_svd_values", "b200_svd_phase_cycles", "b200_dyn_workspace_bytes",
     "b200_dyn_step", "b200_caps_step",
+    "b200_chain_create", "b200_chain_destroy", "b200_chain_len", "b200_chain_push",
+    "b200_chain_shape", "b200_chain_read", "b200_chain_svd_sweep",
+    "b200_chain_pt_zip_up_left", "b200_chain_stats", "b200_chain_log",
 ]
 
 
@@ -31,6 +34,12 @@ class _Operand(Structure):
     _fields_ = [("ptr", c_void_p), ("row", c_int64), ("col", c_int64),
                 ("b1", c_int64), ("b2", c_int64), ("conj", c_int)]
 
+
+class _PtSite(Structure):
+    _fields_ = [("kind", c_int), ("rows", c_int), ("cols", c_int), ("mat", c_void_p)]
+
+
+PT_KINDS = {"first": 0, "mid": 1, "last": 2, "closed": 3}
 
 _lib = None
 
@@ -79,6 +88,27 @@ def load_library():
     lib.b200_caps_step.restype = c_int
     lib.b200_caps_step.argtypes = [c_void_p, c_int, c_int, c_int] + \
         [c_void_p] * 4
+    lib.b200_chain_create.restype = c_void_p
+    lib.b200_chain_create.argtypes = [c_void_p]
+    lib.b200_chain_destroy.restype = c_int
+    lib.b200_chain_destroy.argtypes = [c_void_p]
+    lib.b200_chain_len.restype = c_int
+    lib.b200_chain_len.argtypes = [c_void_p]
+    lib.b200_chain_push.restype = c_int
+    lib.b200_chain_push.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int]
+    lib.b200_chain_shape.restype = c_int
+    lib.b200_chain_shape.argtypes = [c_void_p, c_int, POINTER(c_int32)]
+    lib.b200_chain_read.restype = c_int
+    lib.b200_chain_read.argtypes = [c_void_p, c_int, c_void_p]
+    lib.b200_chain_svd_sweep.restype = c_int
+    lib.b200_chain_svd_sweep.argtypes = [c_void_p, c_int, c_int, c_double]
+    lib.b200_chain_pt_zip_up_left.restype = c_int
+    lib.b200_chain_pt_zip_up_left.argtypes = [c_void_p, POINTER(_PtSite), c_int, c_double]
+    lib.b200_chain_stats.restype = c_int
+    lib.b200_chain_stats.argtypes = [c_void_p, POINTER(c_uint64), POINTER(c_uint64),
+                                     POINTER(c_uint64), c_int]
+    lib.b200_chain_log.restype = c_int
+    lib.b200_chain_log.argtypes = [c_void_p, c_int, POINTER(c_int32), c_int]
     _lib = lib
     return lib
 
@@ -237,6 +267,83 @@ class CudaOps:
 
     def synchronize(self):
         torch.cuda.synchronize(self.device)
+
+
+class NativeChain:
+    """Device-resident matrix-product chain owned by the C++ engine (csrc/chain.cu):
+    the counterpart of NodeArray for the PT-TEMPO path.  A whole zip-up / svd-sweep is
+    ONE C-ABI call."""
+
+    def __init__(self, ops):
+        self.ops = ops
+        self.lib = ops.lib
+        self.h = self.lib.b200_chain_create(ops._stream())
+        if not self.h:
+            raise B200Error("b200_chain_create failed: "
+                            f"{self.lib.b200_last_error().decode()}")
+        self._shape = (c_int32 * 3)()
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.b200_chain_destroy(c_void_p(self.h))
+                self.h = None
+        except Exception:  # pylint: disable=broad-except
+            pass
+
+    def __len__(self):
+        return int(self.lib.b200_chain_len(c_void_p(self.h)))
+
+    def push(self, tensor):
+        """Append a (chi_l, a, chi_r) complex128 device tensor (copied)."""
+        t = tensor.contiguous()
+        dl, da, dr = (int(x) for x in t.shape)
+        self.ops._check(self.lib.b200_chain_push(c_void_p(self.h), t.data_ptr(), dl, da, dr),
+                        "b200_chain_push")
+
+    def shape(self, i):
+        self.ops._check(self.lib.b200_chain_shape(c_void_p(self.h), i, self._shape),
+                        "b200_chain_shape")
+        return tuple(int(x) for x in self._shape)
+
+    def site(self, i):
+        """Copy of site i as a torch tensor (chi_l, a, chi_r)."""
+        out = self.ops.empty(*self.shape(i))
+        self.ops._check(self.lib.b200_chain_read(c_void_p(self.h), i, out.data_ptr()),
+                        "b200_chain_read")
+        return out
+
+    def svd_sweep(self, from_index, to_index, eps):
+        self.ops._check(self.lib.b200_chain_svd_sweep(c_void_p(self.h), from_index, to_index,
+                                                      float(eps)), "b200_chain_svd_sweep")
+
+    def pt_zip_up_left(self, mpo, eps):
+        """mpo: list of chain.PtSite (kind, device matrix)."""
+        arr = (_PtSite * len(mpo))()
+        for k, site in enumerate(mpo):
+            arr[k].kind = PT_KINDS[site.kind]
+            m = site.mat
+            if m.dim() == 1:
+                arr[k].rows, arr[k].cols = int(m.shape[0]), 1
+            else:
+                arr[k].rows, arr[k].cols = int(m.shape[0]), int(m.shape[1])
+            arr[k].mat = m.data_ptr()
+        self.ops._check(self.lib.b200_chain_pt_zip_up_left(c_void_p(self.h), arr, len(mpo),
+                                                           float(eps)),
+                        "b200_chain_pt_zip_up_left")
+
+    def stats(self, reset=False):
+        """(truncated SVDs, Jacobi sweeps, D2H bytes) since the last reset."""
+        a, b, c = c_uint64(0), c_uint64(0), c_uint64(0)
+        self.lib.b200_chain_stats(c_void_p(self.h), ctypes.byref(a), ctypes.byref(b),
+                                  ctypes.byref(c), 1 if reset else 0)
+        return a.value, b.value, c.value
+
+    def log(self, enable=True, cap=1 << 16):
+        """Pop the per-SVD log [(m, n, keep, sweeps)] and switch logging on/off."""
+        buf = (c_int32 * (4 * cap))()
+        n = self.lib.b200_chain_log(c_void_p(self.h), 1 if enable else 0, buf, cap)
+        return [tuple(buf[4 * i: 4 * i + 4]) for i in range(n)]
 
 
 _default_ops = None

@@ -14,8 +14,10 @@ from copy import copy
 
 import numpy as np
 
+import os
+
 from . import chain
-from ._lib import View, default_ops
+from ._lib import NativeChain, View, default_ops
 from .chain import PtSite, TempoSite
 
 CDTYPE = np.complex128
@@ -51,6 +53,13 @@ class PtTempoBackend:
         self._mps = None
         self._mpo = None
         self._closing = None
+        # On the device the chain lives in the native C++ engine (csrc/chain.cu: one
+        # C-ABI call per zip-up / sweep).  The Python chain (chain.py, same kernels) is
+        # the readable specification; it serves the TEMPO path, the per-SVD profiling
+        # tools (OQUPY_B200_PYCHAIN=1) and the CPU-only host-logic tests.
+        self._native = (getattr(self._ops, "name", "") == "cuda"
+                        and os.environ.get("OQUPY_B200_PYCHAIN", "0") != "1")
+        self._chain = None
 
     @property
     def step(self):
@@ -86,8 +95,16 @@ class PtTempoBackend:
             mps.append(ops.from_host(a))
         self._mpo, self._mps = mpo, mps
         n = len(mps)
-        chain.svd_sweep_left(ops, mps, n - 1, 0, self._epsrel)      # :171-175
-        chain.svd_sweep_right(ops, mps, 0, n - 1, self._epsrel)     # :177-181
+        if self._native:
+            self._chain = NativeChain(ops)
+            for t in mps:
+                self._chain.push(t)
+            self._mps = None
+            self._chain.svd_sweep(n - 1, 0, self._epsrel)           # :171-175
+            self._chain.svd_sweep(0, n - 1, self._epsrel)           # :177-181
+        else:
+            chain.svd_sweep_left(ops, mps, n - 1, 0, self._epsrel)      # :171-175
+            chain.svd_sweep_right(ops, mps, 0, n - 1, self._epsrel)     # :177-181
         self._step = 1
 
     def compute_step(self):
@@ -109,22 +126,47 @@ class PtTempoBackend:
             if infl is not None:
                 self._mpo[-1] = PtSite("last", ops.from_host(
                     np.asarray(infl, dtype=CDTYPE)))
-            self._mps.append(ops.from_host(np.ones((1, 1, 1))))     # :259-263
-        chain.pt_zip_up_left(ops, self._mps, self._mpo, self._epsrel)   # :267-274
-        chain.svd_sweep_right(ops, self._mps, self._step - 2,
-                              len(self._mps) - 1, self._epsrel)     # :276-280
+            new_site = ops.from_host(np.ones((1, 1, 1)))            # :259-263
+            if self._native:
+                self._chain.push(new_site)
+            else:
+                self._mps.append(new_site)
+        if self._native:
+            self._chain.pt_zip_up_left(self._mpo, self._epsrel)     # :267-274
+            self._chain.svd_sweep(self._step - 2, len(self._chain) - 1,
+                                  self._epsrel)                     # :276-280
+        else:
+            chain.pt_zip_up_left(ops, self._mps, self._mpo, self._epsrel)   # :267-274
+            chain.svd_sweep_right(ops, self._mps, self._step - 2,
+                                  len(self._mps) - 1, self._epsrel)     # :276-280
         return self._step < self._num_steps
+
+    def _site(self, k):
+        return self._chain.site(k) if self._native else self._mps[k]
+
+    def _num_sites(self):
+        return len(self._chain) if self._native else len(self._mps)
+
+    def pop_svd_log(self):
+        """[(m, n, keep, sweeps)] of the truncated SVDs since the last call (native chain)."""
+        return self._chain.log(True) if self._native and self._chain else []
+
+    def chain_stats(self, reset=False):
+        """(truncated SVDs, Jacobi sweeps, D2H bytes) of the native chain."""
+        return self._chain.stats(reset) if self._native and self._chain else (0, 0, 0)
 
     # -- results ----------------------------------------------------------------
     def get_mpo_tensor_device(self, step):
         """(past bond, future bond, array leg) * d on the device (:284-307)."""
-        assert len(self._mps) == self._num_steps
-        return (self._mps[step].permute(0, 2, 1) * self._dimension).contiguous()
+        assert self._num_sites() == self._num_steps
+        return (self._site(step).permute(0, 2, 1) * self._dimension).contiguous()
 
     def get_mpo_tensor(self, step):
         return self._ops.to_host(self.get_mpo_tensor_device(step))
 
     def get_bond_dimensions(self):
+        if self._native:
+            return [1] + [self._chain.shape(k)[2] for k in range(len(self._chain))]
         return [1] + [int(t.shape[2]) for t in self._mps]
 
     def update_process_tensor(self):

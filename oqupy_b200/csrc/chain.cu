@@ -1,0 +1,348 @@
+// Native matrix-product chain engine (host C++): the device-resident counterpart of
+// NodeArray (oqupy/backends/node_array.py:226-299, 413-554) for the PT-TEMPO path.
+//
+// A chain owns its sites in device memory (stream-ordered pool: cudaMallocAsync) and runs
+// a whole zip-up or svd-sweep in ONE C call: per site it launches the contraction GEMM
+// (b200_zgemm_strided), the truncated SVD (b200_svd_factor), waits for `keep` (the one
+// host round trip a dependent chain of exact-size sites needs), allocates the exact-size
+// outputs and launches b200_svd_emit.  Doing the loop here instead of in Python removes
+// ~70 us of interpreter time per SVD from a ~400-SVD dependency chain.
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+struct Site {
+  cplx* p;
+  int dl, da, dr;       // (chi_l, array leg, chi_r), contiguous complex128
+};
+
+struct Chain {
+  cudaStream_t stream;
+  std::vector<Site> sites;
+  void* work;
+  size_t work_bytes;
+  int32_t* info;        // pinned: {keep, sweeps, status, rotations}
+  cplx* one;            // device scalar 1
+  // statistics since the last reset
+  uint64_t nsvd, sweeps, d2h_bytes;
+  std::vector<int32_t> log;   // (m, n, keep, sweeps) per SVD when enabled
+  bool log_on;
+};
+
+int dev_alloc(Chain* c, cplx** out, size_t n) {
+  if (n == 0) n = 1;
+  B200_CUDA_CHECK(cudaMallocAsync((void**)out, n * sizeof(cplx), c->stream));
+  return B200_OK;
+}
+int dev_free(Chain* c, cplx* p) {
+  if (p) B200_CUDA_CHECK(cudaFreeAsync(p, c->stream));
+  return B200_OK;
+}
+
+#define B200_TRY(expr)                \
+  do {                                \
+    const int _rc = (expr);           \
+    if (_rc != B200_OK) return _rc;   \
+  } while (0)
+
+b200_operand op(const cplx* p, int64_t row, int64_t col, int64_t b1 = 0, int64_t b2 = 0) {
+  b200_operand o;
+  o.ptr = p; o.row = row; o.col = col; o.b1 = b1; o.b2 = b2; o.conj = 0;
+  return o;
+}
+
+int gemm(Chain* c, int m, int n, int k, int nb1, int nb2, const b200_operand& a,
+         const b200_operand& b, cplx* out, int64_t c_row, int64_t c_col, int64_t c_b1,
+         int64_t c_b2, const cplx* scale = nullptr, int64_t s_b1 = 0, int64_t s_b2 = 0) {
+  return b200_zgemm_strided(c->stream, m, n, k, nb1, nb2, &a, &b, out, c_row, c_col, c_b1,
+                            c_b2, scale, s_b1, s_b2, 0);
+}
+
+// truncated SVD of theta (m x n, element strides rs, cs); returns keep
+int split(Chain* c, const cplx* theta, int m, int n, int64_t rs, int64_t cs, double eps,
+          int* keep) {
+  const size_t need = b200_svd_workspace_bytes(m, n);
+  if (need > c->work_bytes) {
+    B200_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (c->work) B200_CUDA_CHECK(cudaFree(c->work));
+    c->work = nullptr;
+    c->work_bytes = 0;
+    const size_t want = need + need / 4;
+    B200_CUDA_CHECK(cudaMalloc(&c->work, want));
+    c->work_bytes = want;
+  }
+  B200_TRY(b200_svd_factor(c->stream, theta, m, n, rs, cs, eps, c->work, c->info));
+  B200_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  c->d2h_bytes += 16;
+  ++c->nsvd;
+  c->sweeps += (uint64_t)c->info[1];
+  if (c->log_on) {
+    c->log.push_back(m); c->log.push_back(n);
+    c->log.push_back(c->info[0]); c->log.push_back(c->info[1]);
+  }
+  if (c->info[2] != 0) {
+    b200::set_error("Jacobi SVD did not converge (%dx%d, %d sweeps)", m, n, c->info[1]);
+    return B200_ENOCONV;
+  }
+  *keep = c->info[0];
+  return B200_OK;
+}
+
+int emit(Chain* c, int m, int n, int keep, cplx* u, int u_na, int64_t u_so, int64_t u_sa,
+         int64_t u_sj, cplx* svh) {
+  return b200_svd_emit(c->stream, c->work, nullptr, m, n, 0, 0, keep, u, u_na, u_so, u_sa,
+                       u_sj, svh);
+}
+
+}  // namespace
+
+extern "C" {
+
+void* b200_chain_create(void* stream) {
+  Chain* c = new Chain();
+  c->stream = (cudaStream_t)stream;
+  c->work = nullptr;
+  c->work_bytes = 0;
+  c->info = nullptr;
+  c->one = nullptr;
+  c->nsvd = c->sweeps = c->d2h_bytes = 0;
+  c->log_on = false;
+  if (cudaMallocHost((void**)&c->info, 4 * sizeof(int32_t)) != cudaSuccess ||
+      cudaMalloc((void**)&c->one, sizeof(cplx)) != cudaSuccess) {
+    b200::set_error("b200_chain_create: allocation failed");
+    delete c;
+    return nullptr;
+  }
+  {   // keep freed site memory cached in the stream-ordered pool across the per-SVD syncs
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t keep_all = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep_all);
+    }
+  }
+  const cplx h1 = make_double2(1.0, 0.0);
+  cudaMemcpyAsync(c->one, &h1, sizeof(cplx), cudaMemcpyHostToDevice, c->stream);
+  cudaStreamSynchronize(c->stream);
+  return c;
+}
+
+int b200_chain_destroy(void* h) {
+  Chain* c = (Chain*)h;
+  if (!c) return B200_OK;
+  cudaStreamSynchronize(c->stream);
+  for (auto& s : c->sites) if (s.p) cudaFreeAsync(s.p, c->stream);
+  cudaStreamSynchronize(c->stream);
+  if (c->work) cudaFree(c->work);
+  if (c->info) cudaFreeHost(c->info);
+  if (c->one) cudaFree(c->one);
+  delete c;
+  return B200_OK;
+}
+
+int b200_chain_len(void* h) { return h ? (int)((Chain*)h)->sites.size() : 0; }
+
+int b200_chain_push(void* h, const void* dev_src, int dl, int da, int dr) {
+  Chain* c = (Chain*)h;
+  if (!c || !dev_src || dl < 1 || da < 1 || dr < 1) {
+    b200::set_error("b200_chain_push: invalid argument");
+    return B200_EINVAL;
+  }
+  Site s;
+  s.dl = dl; s.da = da; s.dr = dr;
+  const size_t n = (size_t)dl * da * dr;
+  B200_TRY(dev_alloc(c, &s.p, n));
+  B200_CUDA_CHECK(cudaMemcpyAsync(s.p, dev_src, n * sizeof(cplx), cudaMemcpyDeviceToDevice,
+                                  c->stream));
+  c->sites.push_back(s);
+  return B200_OK;
+}
+
+int b200_chain_shape(void* h, int i, int32_t* out3) {
+  Chain* c = (Chain*)h;
+  if (!c || !out3 || i < 0 || i >= (int)c->sites.size()) {
+    b200::set_error("b200_chain_shape: invalid argument");
+    return B200_EINVAL;
+  }
+  out3[0] = c->sites[i].dl; out3[1] = c->sites[i].da; out3[2] = c->sites[i].dr;
+  return B200_OK;
+}
+
+int b200_chain_read(void* h, int i, void* dev_dst) {
+  Chain* c = (Chain*)h;
+  if (!c || !dev_dst || i < 0 || i >= (int)c->sites.size()) {
+    b200::set_error("b200_chain_read: invalid argument");
+    return B200_EINVAL;
+  }
+  const Site& s = c->sites[i];
+  B200_CUDA_CHECK(cudaMemcpyAsync(dev_dst, s.p, (size_t)s.dl * s.da * s.dr * sizeof(cplx),
+                                  cudaMemcpyDeviceToDevice, c->stream));
+  return B200_OK;
+}
+
+int b200_chain_stats(void* h, uint64_t* nsvd, uint64_t* sweeps, uint64_t* d2h_bytes,
+                     int reset) {
+  Chain* c = (Chain*)h;
+  if (!c) return B200_EINVAL;
+  if (nsvd) *nsvd = c->nsvd;
+  if (sweeps) *sweeps = c->sweeps;
+  if (d2h_bytes) *d2h_bytes = c->d2h_bytes;
+  if (reset) c->nsvd = c->sweeps = c->d2h_bytes = 0;
+  return B200_OK;
+}
+
+int b200_chain_log(void* h, int enable, int32_t* out, int cap_entries) {
+  Chain* c = (Chain*)h;
+  if (!c) return B200_EINVAL;
+  int n = (int)(c->log.size() / 4);
+  if (out) {
+    if (n > cap_entries) n = cap_entries;
+    for (int i = 0; i < 4 * n; ++i) out[i] = c->log[i];
+    c->log.clear();
+  }
+  c->log_on = (enable != 0);
+  return n;
+}
+
+// svd_sweep(from, to)  (oqupy/backends/node_array.py:226-299)
+int b200_chain_svd_sweep(void* h, int from, int to, double eps) {
+  Chain* c = (Chain*)h;
+  if (!c) return B200_EINVAL;
+  const int n = (int)c->sites.size();
+  if (from < 0) from += n;
+  if (to < 0) to += n;
+  if (from < 0 || from >= n || to < 0 || to >= n) {
+    b200::set_error("b200_chain_svd_sweep: index out of range");
+    return B200_EINVAL;
+  }
+  if (from < to) {          // left -> right: rows (l, a), cols r  (:252-273)
+    for (int i = from; i < to; ++i) {
+      Site a = c->sites[i];
+      const int m = a.dl * a.da, nr = a.dr;
+      int nj = 0;
+      B200_TRY(split(c, a.p, m, nr, nr, 1, eps, &nj));
+      cplx *u = nullptr, *svh = nullptr;
+      B200_TRY(dev_alloc(c, &u, (size_t)m * nj));
+      B200_TRY(dev_alloc(c, &svh, (size_t)nj * nr));
+      B200_TRY(emit(c, m, nr, nj, u, 1, nj, 0, 1, svh));
+      Site b = c->sites[i + 1];
+      const int bn = b.da * b.dr;
+      cplx* nb = nullptr;
+      B200_TRY(dev_alloc(c, &nb, (size_t)nj * bn));
+      B200_TRY(gemm(c, nj, bn, nr, 1, 1, op(svh, nr, 1), op(b.p, bn, 1), nb, bn, 1, 0, 0));
+      B200_TRY(dev_free(c, a.p));
+      B200_TRY(dev_free(c, b.p));
+      B200_TRY(dev_free(c, svh));
+      c->sites[i] = Site{u, a.dl, a.da, nj};
+      c->sites[i + 1] = Site{nb, nj, b.da, b.dr};
+    }
+  } else {                  // right -> left: rows (a, r), cols l  (:274-296)
+    for (int i = from; i > to; --i) {
+      Site a = c->sites[i];
+      const int m = a.da * a.dr, nl = a.dl;
+      int nj = 0;
+      B200_TRY(split(c, a.p, m, nl, 1, m, eps, &nj));
+      cplx *u = nullptr, *svh = nullptr;
+      B200_TRY(dev_alloc(c, &u, (size_t)m * nj));
+      B200_TRY(dev_alloc(c, &svh, (size_t)nj * nl));
+      B200_TRY(emit(c, m, nl, nj, u, 1, 1, 0, m, svh));
+      Site b = c->sites[i - 1];
+      const int bm = b.dl * b.da;
+      cplx* nb = nullptr;
+      B200_TRY(dev_alloc(c, &nb, (size_t)bm * nj));
+      B200_TRY(gemm(c, bm, nj, nl, 1, 1, op(b.p, nl, 1), op(svh, 1, nl), nb, nj, 1, 0, 0));
+      B200_TRY(dev_free(c, a.p));
+      B200_TRY(dev_free(c, b.p));
+      B200_TRY(dev_free(c, svh));
+      c->sites[i] = Site{u, nj, a.da, a.dr};
+      c->sites[i - 1] = Site{nb, b.dl, b.da, nj};
+    }
+  }
+  return B200_OK;
+}
+
+// mps.zip_up(mpo, right_index=-1, direction="left") with the implicit PT-TEMPO MPO
+// (oqupy/backends/node_array.py:482-552, pt_tempo_backend.py:142-152):
+//   Theta[(k,y),(l,e)] = M[e,y] sum_r carry[k,r,e] A[l,y,r];
+//   new site = U as (j, y, k), carry' = S Vh as (j, l, e).
+int b200_chain_pt_zip_up_left(void* h, const b200_pt_site* mpo, int nb, double eps) {
+  Chain* c = (Chain*)h;
+  if (!c || !mpo || nb < 1 || nb > (int)c->sites.size()) {
+    b200::set_error("b200_chain_pt_zip_up_left: invalid argument");
+    return B200_EINVAL;
+  }
+  const int left = (int)c->sites.size() - nb;
+  cplx* carry = nullptr;
+  int ck = 0, cr = 0, ce = 0;            // carry (k, r, e)
+  for (int ib = nb - 1; ib >= 0; --ib) {
+    const int ia = left + ib;
+    Site a = c->sites[ia];
+    const int nl = a.dl, nx = a.da, nr = a.dr;
+    const b200_pt_site& site = mpo[ib];
+    const cplx* mat = (const cplx*)site.mat;
+    if (site.kind == B200_PT_FIRST) {
+      const int ny = nx;
+      cplx* out = nullptr;
+      if (!carry) {       // closed single-site MPO: out[l,y,0] = vec[y] A[l,y,0]
+        if (nr != 1) { b200::set_error("pt_zip_up_left: bad first site"); return B200_EINVAL; }
+        B200_TRY(dev_alloc(c, &out, (size_t)nl * ny));
+        B200_TRY(gemm(c, nl, 1, 1, ny, 1, op(a.p, (int64_t)nx * nr, 0, nr), op(c->one, 0, 0),
+                      out, ny, 0, 1, 0, mat, 1, 0));
+        c->sites[ia] = Site{out, nl, ny, 1};
+      } else {            // out[l,y,k] = vec[y] sum_r A[l,y,r] C[k,r,y]
+        if (ce != ny || cr != nr) { b200::set_error("pt_zip_up_left: carry mismatch"); return B200_EINVAL; }
+        B200_TRY(dev_alloc(c, &out, (size_t)nl * ny * ck));
+        B200_TRY(gemm(c, nl, ck, nr, ny, 1, op(a.p, (int64_t)nx * nr, 1, nr),
+                      op(carry, ce, (int64_t)nr * ce, 1), out, (int64_t)ny * ck, 1, ck, 0,
+                      mat, 1, 0));
+        c->sites[ia] = Site{out, nl, ny, ck};
+      }
+      B200_TRY(dev_free(c, a.p));
+      if (ib != 0) { b200::set_error("pt_zip_up_left: 'first' site must be leftmost"); return B200_EINVAL; }
+      break;
+    }
+    const int ne = site.rows, ny = site.cols;
+    int nk = 0;
+    cplx* theta = nullptr;
+    if (!carry) {         // newest site: Theta[0,y,l,e] = M[e,y] A[l,x(y),0]
+      if (nr != 1 || (site.kind != B200_PT_LAST && site.kind != B200_PT_CLOSED)) {
+        b200::set_error("pt_zip_up_left: bad newest site");
+        return B200_EINVAL;
+      }
+      nk = 1;
+      B200_TRY(dev_alloc(c, &theta, (size_t)ny * nl * ne));
+      const int64_t xs = (site.kind == B200_PT_LAST) ? 0 : nr;
+      B200_TRY(gemm(c, 1, nl, 1, ny, ne, op(c->one, 0, 0), op(a.p, 0, (int64_t)nx * nr, xs),
+                    theta, 0, ne, (int64_t)nl * ne, 1, mat, 1, ny));
+    } else {
+      if (site.kind != B200_PT_MID || ny != nx || cr != nr || ce != ne) {
+        b200::set_error("pt_zip_up_left: bad middle site");
+        return B200_EINVAL;
+      }
+      nk = ck;
+      B200_TRY(dev_alloc(c, &theta, (size_t)nk * ny * nl * ne));
+      B200_TRY(gemm(c, nk, nl, nr, ny, ne, op(carry, (int64_t)nr * ne, ne, 0, 1),
+                    op(a.p, 1, (int64_t)nx * nr, nr), theta, (int64_t)ny * nl * ne, ne,
+                    (int64_t)nl * ne, 1, mat, 1, ny));
+    }
+    const int m = nk * ny, n = nl * ne;
+    int nj = 0;
+    B200_TRY(split(c, theta, m, n, n, 1, eps, &nj));
+    cplx *new_site = nullptr, *new_carry = nullptr;
+    B200_TRY(dev_alloc(c, &new_site, (size_t)nj * ny * nk));
+    B200_TRY(dev_alloc(c, &new_carry, (size_t)nj * nl * ne));
+    B200_TRY(emit(c, m, n, nj, new_site, ny, 1, nk, (int64_t)ny * nk, new_carry));
+    B200_TRY(dev_free(c, theta));
+    B200_TRY(dev_free(c, a.p));
+    if (carry) B200_TRY(dev_free(c, carry));
+    c->sites[ia] = Site{new_site, nj, ny, nk};
+    carry = new_carry; ck = nj; cr = nl; ce = ne;
+  }
+  if (carry) B200_TRY(dev_free(c, carry));
+  return B200_OK;
+}
+
+}  // extern "C"

@@ -36,6 +36,7 @@
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
+using b200::dmma884;
 
 namespace {
 
@@ -49,6 +50,9 @@ constexpr int CHUNK_ROWS = 256;   // rows of a slice staged in shared memory at 
 constexpr int X_SLICE_ROWS = 24;  // target rows of an X slice / a W slice
 constexpr int W_SLICE_ROWS = 40;
 constexpr int GP = PB + 1;        // padded leading dimension of the 32x32 work matrices
+constexpr int TS = PB + 4;        // row stride of the staged tile (complex): 576 B = 64 mod 128,
+                                  // so the 8x4 / 4x8 DMMA fragments load without bank conflicts
+constexpr int DMMA_MIN_ROWS = 48; // slices at least this tall use the fp64 tensor-core path
 
 struct Header {        // lives at the start of the workspace (device)
   int m, n, p, q, nb, transposed, keep, sweeps;
@@ -359,7 +363,7 @@ __device__ __forceinline__ void gram_accumulate(const cplx* tile, int rows, doub
   const int kh = t >> 8, oi = (t >> 4) & 15, oj = t & 15;
 #pragma unroll 2
   for (int r = kh; r < rows; r += 2) {
-    const cplx* row = tile + (size_t)r * PB;
+    const cplx* row = tile + (size_t)r * TS;
     const cplx a0 = row[oi], a1 = row[oi + BC];
     const cplx b0 = row[oj], b1 = row[oj + BC];
     // conj(a) * b
@@ -395,7 +399,7 @@ __device__ __forceinline__ void apply_tile(const cplx* tile, int rows, const cpl
       const cplx j0 = sj[k * PB + tx], j1 = sj[k * PB + tx + BC];
 #pragma unroll
       for (int x = 0; x < NR; ++x) {
-        const cplx v = tile[(size_t)rr[x] * PB + k];
+        const cplx v = tile[(size_t)rr[x] * TS + k];
         ar[x][0] = fma(v.x, j0.x, ar[x][0]); ar[x][0] = fma(-v.y, j0.y, ar[x][0]);
         ai[x][0] = fma(v.x, j0.y, ai[x][0]); ai[x][0] = fma(v.y, j0.x, ai[x][0]);
         ar[x][1] = fma(v.x, j1.x, ar[x][1]); ar[x][1] = fma(-v.y, j1.y, ar[x][1]);
@@ -413,25 +417,100 @@ __device__ __forceinline__ void apply_tile(const cplx* tile, int rows, const cpl
   }
 }
 
-// global -> shared: `rows` rows of blocks A and B into tile[row][32]; four independent
-// L2 loads in flight per thread
+// global -> shared: `rows` rows of blocks A and B into tile[row][TS]; four independent
+// L2 loads in flight per thread.  Rows up to the next multiple of 8 are zero-filled (the
+// DMMA paths work on whole 4- and 8-row fragments).
 __device__ __forceinline__ void load_tile(cplx* tile, const cplx* gA, const cplx* gB,
                                           int rows) {
-  const int total = rows * PB;
+  const int total = ((rows + 7) & ~7) * PB;
   for (int e0 = threadIdx.x; e0 < total; e0 += 4 * JT) {
     cplx v[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int e = e0 + u * JT;
+      v[u] = make_double2(0.0, 0.0);
       if (e < total) {
         const int r = e >> 5, c = e & 31;
-        v[u] = ldcg((c < BC) ? (gA + (size_t)r * BC + c) : (gB + (size_t)r * BC + (c - BC)));
+        if (r < rows)
+          v[u] = ldcg((c < BC) ? (gA + (size_t)r * BC + c) : (gB + (size_t)r * BC + (c - BC)));
       }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int e = e0 + u * JT;
-      if (e < total) tile[e] = v[u];
+      if (e < total) tile[(e >> 5) * TS + (e & 31)] = v[u];
+    }
+  }
+}
+
+// fp64 tensor-core (DMMA.8x8x4) partial Gram: warp w < 10 owns the 8x8 tile pair (I <= J)
+// of T^H T and runs over all rows: Gr = Tr^T Tr + Ti^T Ti, Gi = Tr^T Ti - Ti^T Tr.
+// Fragments: A[g][t] = T[k0+t][8I+g], B[t][g] = T[k0+t][8J+g], D[g][2t], D[g][2t+1].
+__device__ __forceinline__ void gram_dmma(const cplx* tile, int rows, double dacc[4]) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp >= 10) return;
+  int I = 0, rem = warp;
+  while (rem >= 4 - I) { rem -= 4 - I; ++I; }
+  const int J = I + rem;
+  const int g = lane >> 2, t = lane & 3;
+  const cplx* pI = tile + (size_t)t * TS + 8 * I + g;
+  const cplx* pJ = tile + (size_t)t * TS + 8 * J + g;
+  const int steps = (rows + 3) >> 2;
+#pragma unroll 2
+  for (int k = 0; k < steps; ++k) {
+    const cplx xi = pI[(size_t)k * 4 * TS], xj = pJ[(size_t)k * 4 * TS];
+    dmma884(dacc[0], dacc[1], xi.x, xj.x);
+    dmma884(dacc[0], dacc[1], xi.y, xj.y);
+    dmma884(dacc[2], dacc[3], xi.x, xj.y);
+    dmma884(dacc[2], dacc[3], -xi.y, xj.x);
+  }
+}
+__device__ __forceinline__ void gram_dmma_store(cplx* part, const double dacc[4]) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp >= 10) return;
+  int I = 0, rem = warp;
+  while (rem >= 4 - I) { rem -= 4 - I; ++I; }
+  const int J = I + rem;
+  const int g = lane >> 2, t = lane & 3;
+  cplx* o = part + (8 * I + g) * PB + 8 * J + 2 * t;
+  o[0] = make_double2(dacc[0], dacc[2]);
+  o[1] = make_double2(dacc[1], dacc[3]);
+}
+
+// fp64 tensor-core tile * J: a warp owns strips of 8 rows x all 32 columns;
+// Or = Tr Jr - Ti Ji, Oi = Tr Ji + Ti Jr.  A[g][t] = T[r0+g][k0+t], B[t][g] = J[k0+t][8c+g].
+__device__ __forceinline__ void apply_dmma(const cplx* tile, int rows, const cplx* sj,
+                                           cplx* outA, cplx* outB) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  for (int r0 = warp * 8; r0 < rows; r0 += (JT / 32) * 8) {
+    double orr[4][2], oi[4][2];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { orr[c][0] = orr[c][1] = oi[c][0] = oi[c][1] = 0.0; }
+    const cplx* pa = tile + (size_t)(r0 + g) * TS + t;
+    const cplx* pb = sj + t * PB + g;
+#pragma unroll 2
+    for (int k0 = 0; k0 < PB; k0 += 4) {
+      const cplx a = pa[k0];
+      const double nai = -a.y;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const cplx bj = pb[k0 * PB + 8 * c];
+        dmma884(orr[c][0], orr[c][1], a.x, bj.x);
+        dmma884(orr[c][0], orr[c][1], nai, bj.y);
+        dmma884(oi[c][0], oi[c][1], a.x, bj.y);
+        dmma884(oi[c][0], oi[c][1], a.y, bj.x);
+      }
+    }
+    const int r = r0 + g;
+    if (r < rows) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        cplx* dst = (c < 2) ? (outA + (size_t)r * BC + 8 * c + 2 * t)
+                            : (outB + (size_t)r * BC + 8 * (c - 2) + 2 * t);
+        dst[0] = make_double2(orr[c][0], oi[c][0]);
+        dst[1] = make_double2(orr[c][1], oi[c][1]);
+      }
     }
   }
 }
@@ -449,8 +528,8 @@ jacobi_kernel(const cplx* __restrict__ theta, long long rs, long long cs,
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ InnerShared S;
   __shared__ double s_red[JT / 32];
-  cplx* tile = reinterpret_cast<cplx*>(dyn_smem);          // [CHUNK][32]
-  cplx* sj = tile + (size_t)CHUNK_ROWS * PB;               // [32][32] rotation to apply
+  cplx* tile = reinterpret_cast<cplx*>(dyn_smem);          // [CHUNK][TS]
+  cplx* sj = tile + (size_t)CHUNK_ROWS * TS;               // [32][32] rotation to apply
   cplx* sg = sj + PB * PB;                                 // [32][32] scratch (Gram halves)
 
   const int T = p + q;
@@ -516,6 +595,9 @@ jacobi_kernel(const cplx* __restrict__ theta, long long rs, long long cs,
   else if (r_slice < Rx) { row0 = r_slice * RSx; nrows = min(RSx, p - row0); xrows = nrows; }
   else { row0 = p + (r_slice - Rx) * RSw; nrows = min(RSw, T - row0); xrows = 0; }
   const bool single_chunk = nrows <= CHUNK_ROWS;
+  // tall X slices form their partial Gram matrix on the fp64 tensor cores (slices that
+  // mix X and W rows -- only the single-slice layout -- keep the FMA path)
+  const bool gram_tc = (Rw > 0) && (xrows >= DMMA_MIN_ROWS);
   const bool leader = (r_slice == 0);
 
   int sweeps_done = 0, total_rot = 0, status = 1;
@@ -550,16 +632,25 @@ jacobi_kernel(const cplx* __restrict__ theta, long long rs, long long cs,
         PHASE(0)
         // 2./3. stage the slice, partial Gram of the X rows
         double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        double dacc[4] = {0, 0, 0, 0};
         for (int c0 = 0; c0 < nrows; c0 += CHUNK_ROWS) {
           const int crow = min(CHUNK_ROWS, nrows - c0);
           if (c0 > 0) __syncthreads();
           load_tile(tile, gA + (size_t)c0 * BC, gB + (size_t)c0 * BC, crow);
           __syncthreads();
           const int xr = max(0, min(crow, xrows - c0));
-          if (xr > 0) gram_accumulate(tile, xr, acc);
+          if (xr > 0) {
+            if (gram_tc) gram_dmma(tile, xr, dacc); else gram_accumulate(tile, xr, acc);
+          }
         }
         PHASE(1)
-        if (xrows > 0) {
+        if (xrows > 0 && gram_tc) {
+          cplx* my_part = gpart + ((size_t)(par * S_slots + s) * R + r_slice) * (PB * PB);
+          gram_dmma_store(my_part, dacc);
+          __syncthreads();
+          // release is cumulative over the CTA barrier above
+          if (t == 0) red_release_add(cnt + par * S_slots + s, 1);
+        } else if (xrows > 0) {
           cplx* my_part = gpart + ((size_t)(par * S_slots + s) * R + r_slice) * (PB * PB);
           const int kh = t >> 8, oi = (t >> 4) & 15, oj = t & 15;
           cplx* d = sg + oi * PB + oj;
@@ -669,8 +760,8 @@ jacobi_kernel(const cplx* __restrict__ theta, long long rs, long long cs,
             cplx* oA = gA + (size_t)c0 * BC;
             cplx* oB = gB + (size_t)c0 * BC;
             if (crow <= 32) apply_tile<1>(tile, crow, sj, oA, oB);
-            else if (crow <= 64) apply_tile<2>(tile, crow, sj, oA, oB);
-            else apply_tile<4>(tile, crow, sj, oA, oB);
+            else if (crow < DMMA_MIN_ROWS) apply_tile<2>(tile, crow, sj, oA, oB);
+            else apply_dmma(tile, crow, sj, oA, oB);
           }
         }
         __syncthreads();
@@ -827,7 +918,7 @@ __global__ void emit_kernel(const cplx* __restrict__ y, const double* __restrict
   }
 }
 
-constexpr size_t kDynSmem = (size_t)CHUNK_ROWS * PB * sizeof(cplx) + 2 * PB * PB * sizeof(cplx);
+constexpr size_t kDynSmem = (size_t)CHUNK_ROWS * TS * sizeof(cplx) + 2 * PB * PB * sizeof(cplx);
 
 }  // namespace
 

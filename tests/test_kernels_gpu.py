@@ -63,7 +63,7 @@ def ref_keep(s, eps):
 
 @pytest.mark.parametrize("m,n", [(4, 4), (4, 16), (16, 4), (3, 5), (9, 7), (33, 33),
                                  (64, 48), (48, 130), (200, 96), (96, 200),
-                                 (260, 260), (520, 130)])
+                                 (260, 260), (520, 130), (640, 600), (500, 900)])
 @pytest.mark.parametrize("eps", [1e-7, None])
 def test_trunc_svd(m, n, eps):
     ops = default_ops()

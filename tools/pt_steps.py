@@ -1,6 +1,9 @@
 """GPU: run the first steps of the config-2 PT-TEMPO build and print per-step timing."""
+import os
 import sys
 import time
+
+os.environ.setdefault("OQUPY_B200_PYCHAIN", "1")   # per-SVD instrumentation needs the Python chain
 
 import numpy as np
 import torch

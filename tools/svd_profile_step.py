@@ -1,6 +1,9 @@
 """GPU: time every SVD of one late PT-TEMPO step (config 2) and print the heavy hitters."""
+import os
 import sys
 import time
+
+os.environ.setdefault("OQUPY_B200_PYCHAIN", "1")   # per-SVD instrumentation needs the Python chain
 
 import numpy as np
 import torch
