@@ -5,11 +5,12 @@ influence-MPO x MPS zip-up, eps-truncated SVD sweeps, process-tensor export and
 the compute_dynamics loop.  Everything reaches the GPU through the C-ABI library
 ``liboqupy_b200.so`` (include/oqupy_b200.h); there is no CPU fallback.
 """
-from .backends import BaseTempoBackend, PtTempoBackend, TempoBackend
+from .backends import (BaseTempoBackend, MeanFieldTempoBackend, PtTempoBackend,
+                       TempoBackend)
 from .process_tensor import DeviceProcessTensor, dynamics_device
 from ._lib import B200Error, CudaOps, default_ops, load_library
 
-__all__ = ["BaseTempoBackend", "PtTempoBackend", "TempoBackend",
+__all__ = ["BaseTempoBackend", "MeanFieldTempoBackend", "PtTempoBackend", "TempoBackend",
            "DeviceProcessTensor", "dynamics_device", "B200Error", "CudaOps",
            "default_ops", "load_library"]
 __version__ = "0.1.0"

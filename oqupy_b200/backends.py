@@ -10,7 +10,7 @@ limited to what the reference also does on the host per step: calling the
 ``influence`` / ``propagators`` callbacks (d2 x d2 matrices) and O(d2^2) operand
 preparation.
 """
-from copy import copy
+from copy import copy, deepcopy
 
 import numpy as np
 
@@ -345,3 +345,72 @@ class TempoBackend(BaseTempoBackend):
         prop_1, prop_2 = self._propagators(self._step - 1)
         self._state = self.compute_system_step(self._step, prop_1, prop_2)
         return self._step, copy(self._state)
+
+
+class MeanFieldTempoBackend:
+    """One or more TEMPO networks with a coherent mean field
+    (tempo_backend.py:629-773): one device-resident :class:`BaseTempoBackend` per
+    system, propagated with the same (field-dependent) half-step propagators the
+    reference would use; the field equation of motion stays a host callback."""
+
+    def __init__(self, initial_state_list, initial_field, influence_list,
+                 unitary_transform_list, propagators_list, compute_field,
+                 compute_field_derivative, sum_north_list, sum_west_list, dkmax,
+                 epsrel, config=None, degeneracy_maps_list=None, dim_list=None,
+                 ops=None):
+        n = len(initial_state_list)
+        if degeneracy_maps_list is None:
+            degeneracy_maps_list = [None] * n
+        if dim_list is None:
+            dim_list = [None] * n
+        self._initial_state_list = initial_state_list
+        self._initial_field = initial_field
+        self._compute_field = compute_field
+        self._compute_field_derivative = compute_field_derivative
+        self._field = initial_field
+        self._state_list = initial_state_list
+        self._step = None
+        self._propagators_list = propagators_list
+        self._backend_list = [
+            BaseTempoBackend(state, influence, unitary, sum_north, sum_west, dkmax,
+                             epsrel, config, maps, dim, ops=ops)
+            for state, influence, unitary, sum_north, sum_west, maps, dim in zip(
+                initial_state_list, influence_list, unitary_transform_list,
+                sum_north_list, sum_west_list, degeneracy_maps_list, dim_list)]
+
+    @property
+    def step(self):
+        """The current step in the TEMPO computation."""
+        return self._step
+
+    def initialize(self):
+        """:740-745"""
+        self._step = 0
+        for backend in self._backend_list:
+            backend.initialize_mps_mpo()
+        return self._step, deepcopy(self._state_list), self._field
+
+    def compute_step(self):
+        """:747-773"""
+        current_step = self._step
+        next_step = current_step + 1
+        current_state_list = deepcopy(self._state_list)
+        current_field = self._field
+        current_field_derivative = self._compute_field_derivative(
+            current_step, current_state_list, current_field)
+        # the field enters each system's dynamics through its propagators
+        prop_tuple_list = [propagators(current_step, current_field,
+                                       current_field_derivative)
+                           for propagators in self._propagators_list]
+        next_state_list = [backend.compute_system_step(next_step, *prop_tuple)
+                           for backend, prop_tuple in zip(self._backend_list,
+                                                          prop_tuple_list)]
+        next_field = self._compute_field(current_step, current_state_list,
+                                         current_field, next_state_list)
+        self._state_list = next_state_list
+        self._field = next_field
+        self._step = next_step
+        return self._step, deepcopy(self._state_list), self._field
+
+    def get_bond_dimensions(self):
+        return [backend.get_bond_dimensions() for backend in self._backend_list]

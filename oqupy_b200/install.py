@@ -1,7 +1,7 @@
 """Drop-in hook for an existing OQuPy installation.
 
 OQuPy's front-ends resolve the backend classes by module-global name at call time
-(oqupy/tempo.py:424, oqupy/pt_tempo.py:218, oqupy/backends/tempo_backend.py:715), so
+(oqupy/tempo.py:424, 818, oqupy/pt_tempo.py:218, oqupy/backends/tempo_backend.py:715), so
 rebinding those names is a complete drop-in: ``oqupy.Tempo(...).compute()``,
 ``oqupy.PtTempo(...)`` / ``oqupy.pt_tempo_compute`` then run on the B200.  Selection
 follows the reference's config mechanism: the B200 classes are used when
@@ -40,10 +40,13 @@ def install(default=False):
     if not _ORIGINALS:
         _ORIGINALS.update(TempoBackend=tm.TempoBackend,
                           BaseTempoBackend=tb.BaseTempoBackend,
+                          MeanFieldTempoBackend=tm.MeanFieldTempoBackend,
                           PtTempoBackend=ptm.PtTempoBackend)
     tm.TempoBackend = _dispatch(_b200.TempoBackend, _ORIGINALS["TempoBackend"])
     tb.BaseTempoBackend = _dispatch(_b200.BaseTempoBackend,
                                     _ORIGINALS["BaseTempoBackend"])
+    tm.MeanFieldTempoBackend = _dispatch(_b200.MeanFieldTempoBackend,
+                                         _ORIGINALS["MeanFieldTempoBackend"])
     ptm.PtTempoBackend = _dispatch(_b200.PtTempoBackend,
                                    _ORIGINALS["PtTempoBackend"])
     if default:
@@ -61,6 +64,7 @@ def uninstall():
     import oqupy.tempo as tm  # pylint: disable=import-outside-toplevel
     tm.TempoBackend = _ORIGINALS["TempoBackend"]
     tb.BaseTempoBackend = _ORIGINALS["BaseTempoBackend"]
+    tm.MeanFieldTempoBackend = _ORIGINALS["MeanFieldTempoBackend"]
     ptm.PtTempoBackend = _ORIGINALS["PtTempoBackend"]
     oqupy.config.TEMPO_BACKEND_CONFIG.pop("backend", None)
     oqupy.config.PT_TEMPO_BACKEND_CONFIG.pop("backend", None)

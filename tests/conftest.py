@@ -36,3 +36,49 @@ def golden_callables(g):
         return p1, p2
 
     return influence, propagators
+
+
+def mean_field_callables(g):
+    """Replay of the host callbacks of the reference's mean-field run: the propagator
+    pair and the field it used at every step (tests/golden/make_golden_mean_field.py).
+    Returns (influence, propagators, compute_field, compute_field_derivative, seen)
+    where ``seen`` collects the (field, field derivative) values handed to propagators."""
+    infl = g["influences"]
+    seen = []
+
+    def influence(dk):
+        return None if dk < 0 else infl[dk]
+
+    def propagators(step, field, dfield):
+        seen.append((step, field, dfield))
+        return g["props_1"][step], g["props_2"][step]
+
+    def compute_field(step, states, field, next_states=None):
+        return complex(g["fields"][step + 1])
+
+    def compute_field_derivative(step, states, field):
+        return complex(g["dfields_in"][step])
+
+    return influence, propagators, compute_field, compute_field_derivative, seen
+
+
+def check_mean_field_run(backend, g, seen):
+    """Drive a MeanFieldTempoBackend-like object through the fixture and compare."""
+    d = int(g["dim"])
+    step, states, field = backend.initialize()
+    assert step == 0 and complex(field) == complex(g["initial_field"])
+    out = [np.asarray(states[0]).reshape(d, d)]
+    for k in range(int(g["num_steps"])):
+        step, states, field = backend.compute_step()
+        assert step == k + 1
+        assert complex(field) == complex(g["fields"][k + 1])
+        out.append(np.asarray(states[0]).reshape(d, d))
+    out = np.array(out)
+    np.testing.assert_allclose(out, g["states"], atol=50 * float(g["epsrel"]), rtol=0)
+    np.testing.assert_allclose(out[:5], g["states"][:5], atol=1e-9, rtol=0)
+    np.testing.assert_almost_equal(out[-1], g["rho_golden"], decimal=4)
+    # plumbing: every step's propagators saw the field of that step and its derivative
+    assert [s[0] for s in seen] == list(range(int(g["num_steps"])))
+    np.testing.assert_array_equal(np.array([s[1] for s in seen]), g["fields_in"])
+    np.testing.assert_array_equal(np.array([s[2] for s in seen]), g["dfields_in"])
+    return out

@@ -4,7 +4,8 @@ the test-only strided-view model of the C-ABI (tests/host_model_ops.py)."""
 import numpy as np
 import pytest
 
-from conftest import golden_callables, load_golden
+from conftest import (check_mean_field_run, golden_callables, load_golden,
+                      mean_field_callables)
 from host_model_ops import HostModelOps
 from oracle import tempo_np as onp
 import oqupy_b200 as ob
@@ -86,3 +87,15 @@ def test_unique_is_rejected_loudly():
         ob.PtTempoBackend(2, lambda k: None, None, np.ones(4), np.ones(4), 10, 5,
                           1e-6, degeneracy_maps=[np.arange(4), np.arange(4)],
                           ops=HostModelOps())
+
+
+def test_mean_field_backend_host_logic():
+    g = load_golden("mean_field_G")
+    influence, props, cfield, cdfield, seen = mean_field_callables(g)
+    d2 = int(g["dim"]) ** 2
+    be = ob.MeanFieldTempoBackend([g["initial_state"]], complex(g["initial_field"]),
+                                  [influence], [g["unitary"]], [props], cfield, cdfield,
+                                  [np.ones(d2)], [np.ones(d2)], None, float(g["epsrel"]),
+                                  ops=HostModelOps())
+    check_mean_field_run(be, g, seen)
+    assert be.get_bond_dimensions()[0] == list(g["bond_dims"])

@@ -51,3 +51,42 @@ def test_install_dispatch(monkeypatch):
     finally:
         install.uninstall()
     assert oqupy.tempo.TempoBackend is install._ORIGINALS["TempoBackend"]
+
+
+def test_install_dispatch_mean_field(monkeypatch):
+    """oqupy.MeanFieldTempo (reference front-end, test G of
+    tests/physics/mean_field_tempo_test.py) on the rebound MeanFieldTempoBackend."""
+    oqupy = load_reference()
+    from oqupy_b200 import backends, install
+    from host_model_ops import HostModelOps
+    ops = HostModelOps()
+    monkeypatch.setattr(backends, "default_ops", lambda: ops)
+    # numpy 2 rejects np.vectorize(h)(t) for array-valued h; the reference (numpy<2)
+    # only uses it as an input check
+    monkeypatch.setattr(np, "vectorize", lambda f, *a, **k: f)
+    sx, sz = oqupy.operators.sigma("x"), oqupy.operators.sigma("z")
+    system = oqupy.TimeDependentSystemWithField(
+        lambda t, field: 0.5 * sz + np.real(field) * sx)
+    mfs = oqupy.MeanFieldSystem(
+        [system], lambda t, states, field: -(1j + 1) * field
+        - 0.5j * np.matmul(sx, states[0]).trace().real)
+    corr = oqupy.PowerLawSD(alpha=0.1, zeta=1.0, cutoff=5.0, cutoff_type="gaussian",
+                            temperature=0.0)
+    bath = oqupy.Bath(0.5 * sz, corr)
+    params = oqupy.TempoParameters(dt=0.05, tcut=None, epsrel=1e-7)
+    rho0 = np.array([[0.5, 0.5], [0.5, 0.5]])
+    install.install()
+    try:
+        ref = oqupy.MeanFieldTempo(mfs, [bath], params, [rho0], 1.0, start_time=0.0)
+        new = oqupy.MeanFieldTempo(mfs, [bath], params, [rho0], 1.0, start_time=0.0,
+                                   backend_config={"backend": "b200"})
+        assert isinstance(new._backend_instance, backends.MeanFieldTempoBackend)
+        assert not isinstance(ref._backend_instance, backends.MeanFieldTempoBackend)
+        ref.compute(0.5, progress_type="silent")
+        new.compute(0.5, progress_type="silent")
+        dr, dn = ref.get_dynamics(), new.get_dynamics()
+        np.testing.assert_allclose(dn.fields, dr.fields, atol=1e-8)
+        np.testing.assert_allclose(dn.system_dynamics[0].states,
+                                   dr.system_dynamics[0].states, atol=1e-8)
+    finally:
+        install.uninstall()

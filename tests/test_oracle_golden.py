@@ -4,7 +4,8 @@ matrices quoted from the reference's own tests."""
 import numpy as np
 import pytest
 
-from conftest import golden_callables, load_golden
+from conftest import (check_mean_field_run, golden_callables, load_golden,
+                      mean_field_callables)
 from oracle import tempo_np as onp
 
 PT_CASES = ["pt_k12_eps7_n30", "pt_k8_eps9_n24", "pt_refA", "pt_refC"]
@@ -76,3 +77,18 @@ def test_truncation_rule_matches_in_repo_pin():
         chi = np.count_nonzero(np.cumsum(np.flip(s) ** 2) > (s[0] * eps) ** 2)
         u, sk, vh, rest = onp.truncated_svd(mat, eps)
         assert sk.size == chi and rest.size == 40 - chi
+
+
+def test_mean_field_oracle_matches_reference():
+    """MeanFieldTempoBackend (tempo_backend.py:629-773) replayed with the host callbacks
+    of the reference's own run of its test G (mean_field_tempo_test.py:21-69)."""
+    g = load_golden("mean_field_G")
+    influence, props, cfield, cdfield, seen = mean_field_callables(g)
+    d2 = int(g["dim"]) ** 2
+    mf = onp.MeanFieldTempoOracle([g["initial_state"]], complex(g["initial_field"]),
+                                  [influence], [g["unitary"]], [props], cfield, cdfield,
+                                  [np.ones(d2)], [np.ones(d2)], None, float(g["epsrel"]))
+    check_mean_field_run(mf, g, seen)
+    assert mf.networks[0].bond_dimensions() == list(g["bond_dims"])
+    np.testing.assert_almost_equal(complex(g["fields"][-1]), complex(g["field_golden"]),
+                                   decimal=4)
