@@ -152,3 +152,34 @@ def test_dyn_and_caps():
         np.testing.assert_allclose(ops.to_host(dcap),
                                    np.einsum("lrx,r,x->l", t, capn, tr2), atol=1e-10)
     assert ops.launch_count() > 0
+
+
+@pytest.mark.parametrize("m,n", [(1300, 1200), (2300, 2200)])
+def test_trunc_svd_large_multichunk(m, n):
+    """Slices taller than one shared-memory chunk (256 rows): 1300x1200 runs 2 X slices
+    (3 chunks each, DMMA Gram/apply) + 1 W slice; 2300x2200 has more pair slots than
+    SMs / 2, i.e. ONE slice that mixes X and W rows (FMA Gram, chunked)."""
+    ops = default_ops()
+    rng = np.random.default_rng(m + n)
+    k = min(m, n)
+    # graded spectrum without forming dense random orthogonal factors on the host
+    s = np.sort(10.0 ** rng.uniform(-12.0, 0.0, size=k))[::-1]
+    s[0] = 1.0
+    a = rnd(rng, m, 48) @ (rnd(rng, 48, n) * 1e-3)
+    q1, _ = np.linalg.qr(rnd(rng, m, 64))
+    q2, _ = np.linalg.qr(rnd(rng, n, 64))
+    mat = (q1 * s[:64]) @ q2.conj().T + 1e-7 * a
+    eps = 1e-6
+    h = ops.svd_factor(ops.from_host(mat), m, n, n, 1, eps)
+    s_ref = np.linalg.svd(mat, compute_uv=False)
+    assert h.keep == ref_keep(s_ref, eps)
+    sv = ops.svd_values(h)
+    kk = h.keep
+    np.testing.assert_allclose(sv[:kk], s_ref[:kk], atol=2e-13 * s_ref[0], rtol=1e-7)
+    np.testing.assert_allclose(np.linalg.norm(sv[kk:]), np.linalg.norm(s_ref[kk:]),
+                               rtol=1e-6, atol=1e-15 * s_ref[0])
+    u, svh = ops.empty(m, kk), ops.empty(kk, n)
+    ops.svd_emit(h, u=u, u_na=1, u_so=kk, u_sj=1, svh=svh)
+    u, svh = ops.to_host(u), ops.to_host(svh)
+    ur, sr, vhr = np.linalg.svd(mat, full_matrices=False)
+    np.testing.assert_allclose(u @ svh, (ur[:, :kk] * sr[:kk]) @ vhr[:kk], atol=1e-12)
