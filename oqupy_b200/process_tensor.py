@@ -141,3 +141,93 @@ def dynamics_device(pt, propagators, initial_states, num_steps=None, ops=None):
              View(rho[num_steps], col=1, b1=d2), nb1=nvec)
     out = ops.to_host(rho).transpose(1, 0, 2).reshape(nvec, num_steps + 1, d, d)
     return out[0] if single else out
+
+
+def gradient_device(pt, propagators, initial_state, target_derivative, num_steps=None,
+                    ops=None):
+    """compute_gradient_and_dynamics hot loops (oqupy/gradient.py:275-425): forward
+    propagation through the process tensor keeping every intermediate state on the
+    device, back-propagation of the target derivative through the bond-/leg-swapped
+    PT-MPO (system_dynamics.py:588-628), and per step the adjoint tensor
+    ``D[i, x, x', j] = sum_{l,r} F[l, i] T[l, r, x] d_xx' B[r, j]``
+    (system_dynamics.py:702-786; leg order of gradient.py:216-224).
+
+    One environment, no controls, rank-3 PT-MPO sites.  ``propagators(step)`` ->
+    (P1, P2) as (d2, d2) superoperators; ``target_derivative`` is a (d, d) array or a
+    callable of the final state.  Returns (propagator_derivatives, states): a list of
+    ``num_steps`` ndarrays (d2, d2, d2, d2) -- what ``oqupy.gradient._chain_rule`` takes
+    as ``adjoint_tensor`` -- and the (num_steps+1, d, d) dynamics.
+    """
+    from ._lib import View  # pylint: disable=import-outside-toplevel
+    ops = default_ops() if ops is None else ops
+    rho0 = np.asarray(initial_state, dtype=CDTYPE)
+    d = rho0.shape[0]
+    d2 = d * d
+    if num_steps is None:
+        num_steps = len(pt)
+    # ---- forward (gradient.py:275-316): the fused dynamics step, states kept
+    v = ops.from_host(rho0.reshape(1, 1, d2))
+    rho = ops.empty(num_steps + 1, 1, d2)
+    forward, props = [], []
+    for step in range(num_steps):
+        t = pt.get_mpo_tensor_device(step)
+        chi_l, chi_r, _ = t.shape
+        p1, p2 = (np.ascontiguousarray(np.asarray(p, dtype=CDTYPE))
+                  for p in propagators(step))
+        dp1, dp2 = ops.from_host(p1.reshape(1, d2, d2)), ops.from_host(p2.reshape(1, d2, d2))
+        props.append((dp1, dp2))
+        forward.append(v)
+        v_out = ops.empty(1, chi_r, d2)
+        ops.dyn_step(1, chi_l, chi_r, d2, t, dp1, dp2, v, v_out,
+                     cap=pt.get_cap_tensor_device(step), rho_out=rho[step])
+        v = v_out
+    cap = pt.get_cap_tensor_device(num_steps)
+    chi = v.shape[1]
+    ops.gemm(1, d2, chi, View(cap, col=1), View(v, row=d2, col=1),
+             View(rho[num_steps], col=1))
+    states = ops.to_host(rho).reshape(num_steps + 1, d, d)
+    # ---- backward (gradient.py:336-425)
+    target = target_derivative(states[-1]) if callable(target_derivative) \
+        else target_derivative
+    back = ops.from_host(np.asarray(target, dtype=CDTYPE).reshape(1, d2))   # (chi_N = 1, d2)
+    out = ops.empty(num_steps, d2, d2, d2)        # D3[step][x][i][j]
+
+    def adjoint(step, b):
+        """D3[x][i, j] = sum_{l,r} F[l, i] T[l, r, x] B[r, j] for the MPO of `step`."""
+        t = pt.get_mpo_tensor_device(step)
+        chi_l, chi_r, _ = t.shape
+        f = forward[step]                                     # (1, chi_l, d2)
+        tmp = ops.empty(d2, d2, chi_r)                        # [x][i][r]
+        ops.gemm(d2, chi_r, chi_l, View(f, row=1, col=d2),
+                 View(t, row=chi_r * d2, col=d2, b1=1),
+                 View(tmp, row=chi_r, col=1, b1=d2 * chi_r), nb1=d2)
+        ops.gemm(d2, d2, chi_r, View(tmp, row=chi_r, col=1, b1=d2 * chi_r),
+                 View(b, row=d2, col=1),
+                 View(out[step], row=d2, col=1, b1=d2 * d2), nb1=d2)
+
+    adjoint(num_steps - 1, back)
+    for step in range(num_steps - 1, 0, -1):
+        t = pt.get_mpo_tensor_device(step)
+        chi_l, chi_r, _ = t.shape
+        dp1, dp2 = props[step]
+        # B <- B P2   (_apply_system_superoperator with P2^T)
+        b1 = ops.empty(chi_r, d2)
+        ops.gemm(chi_r, d2, d2, View(back, row=d2, col=1), View(dp2, row=d2, col=1),
+                 View(b1, row=d2, col=1))
+        # B[l, x] <- sum_r T[l, r, x] B[r, x]   (MPO with bond and system legs swapped)
+        b2 = ops.empty(chi_l, d2)
+        ops.gemm(chi_l, 1, chi_r, View(t, row=chi_r * d2, col=d2, b1=1),
+                 View(b1, row=d2, col=0, b1=1), View(b2, row=d2, col=0, b1=1), nb1=d2)
+        # B <- B P1
+        back = ops.empty(chi_l, d2)
+        ops.gemm(chi_l, d2, d2, View(b2, row=d2, col=1), View(dp1, row=d2, col=1),
+                 View(back, row=d2, col=1))
+        adjoint(step - 1, back)
+    d3 = ops.to_host(out)                                     # (N, x, i, j)
+    derivs = []
+    for step in range(num_steps):
+        full = np.zeros((d2, d2, d2, d2), dtype=CDTYPE)
+        for x in range(d2):
+            full[:, x, x, :] = d3[step, x]
+        derivs.append(full)
+    return derivs, states

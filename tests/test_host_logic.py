@@ -99,3 +99,23 @@ def test_mean_field_backend_host_logic():
                                   ops=HostModelOps())
     check_mean_field_run(be, g, seen)
     assert be.get_bond_dimensions()[0] == list(g["bond_dims"])
+
+
+def test_gradient_host_logic():
+    """gradient_device (forward + back-propagation + adjoint tensors) against the
+    reference's own compute_gradient_and_dynamics on its test J."""
+    g = load_golden("gradient_J")
+    ops = HostModelOps()
+    _, pt, _ = build_pt(load_golden(str(g["pt_fixture"])), ops)
+
+    def props(k):
+        return g["props_1"][k], g["props_2"][k]
+    derivs, states = ob.gradient_device(pt, props, g["initial_state"],
+                                        g["target_derivative"], ops=ops)
+    np.testing.assert_allclose(states, g["states"], atol=1e-10, rtol=0)
+    np.testing.assert_allclose(np.array(derivs), g["propagator_derivatives"], atol=1e-10,
+                               rtol=0)
+    grad = onp.chain_rule(derivs, lambda k: (g["dprops_1"][k], g["dprops_2"][k]), props,
+                          int(g["num_steps"]), 1)
+    np.testing.assert_allclose(grad, g["grad_params"], atol=1e-10)
+    np.testing.assert_almost_equal(grad.real[:, 0], g["grad_params_golden"], decimal=4)

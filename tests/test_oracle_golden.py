@@ -92,3 +92,24 @@ def test_mean_field_oracle_matches_reference():
     assert mf.networks[0].bond_dimensions() == list(g["bond_dims"])
     np.testing.assert_almost_equal(complex(g["fields"][-1]), complex(g["field_golden"]),
                                    decimal=4)
+
+
+def test_gradient_oracle_matches_reference():
+    """compute_gradient_and_dynamics + _chain_rule (gradient.py:114-437) restated in the
+    oracle against the reference's own run of its test J (gradient_target_state_test.py)."""
+    g = load_golden("gradient_J")
+    ga = load_golden(str(g["pt_fixture"]))
+    pt, mpos, caps, _ = run_pt_oracle(ga)
+
+    def props(k):
+        return g["props_1"][k], g["props_2"][k]
+    derivs, states = onp.compute_gradient_and_dynamics(
+        mpos, caps, props, g["initial_state"], g["target_derivative"])
+    np.testing.assert_allclose(states, g["states"], atol=1e-10, rtol=0)
+    np.testing.assert_allclose(np.array(derivs), g["propagator_derivatives"], atol=1e-10,
+                               rtol=0)
+    grad = onp.chain_rule(derivs, lambda k: (g["dprops_1"][k], g["dprops_2"][k]), props,
+                          int(g["num_steps"]), 1)
+    np.testing.assert_allclose(grad, g["grad_params"], atol=1e-12)
+    # the reference test's own pin (grad_params_J, decimal=4)
+    np.testing.assert_almost_equal(grad.real[:, 0], g["grad_params_golden"], decimal=4)
