@@ -95,14 +95,22 @@ class DeviceProcessTensor:
 
 
 def dynamics_device(pt, propagators, initial_states, num_steps=None, ops=None):
-    """compute_dynamics hot loop (system_dynamics.py:131-170), one environment,
-    ``E`` ensemble members sharing the process tensor.
+    """compute_dynamics hot loop (system_dynamics.py:131-170).
 
-    propagators(step) -> (P1, P2), each (d2, d2) or (E, d2, d2).
-    initial_states: (d, d) or (E, d, d).  Returns ndarray (E, num_steps+1, d, d)
-    (E squeezed if the input was a single state).
+    ``pt``: one process tensor, or a list of them (one per environment,
+    system_dynamics.py:689-700: the state carries one bond leg per environment).
+    With ONE environment, ``E`` ensemble members may share the process tensor:
+    propagators(step) -> (P1, P2), each (d2, d2) or (E, d2, d2); initial_states (d, d) or
+    (E, d, d); returns ndarray (E, num_steps+1, d, d) (E squeezed for a single state).
+    With several environments: one state, (d2, d2) propagators, returns
+    (num_steps+1, d, d).
     """
     ops = default_ops() if ops is None else ops
+    if isinstance(pt, (list, tuple)):
+        if len(pt) > 1:
+            return _dynamics_multi_env(list(pt), propagators, initial_states, num_steps,
+                                       ops)
+        pt = pt[0]
     rho0 = np.asarray(initial_states, dtype=CDTYPE)
     single = rho0.ndim == 2
     if single:
@@ -141,6 +149,75 @@ def dynamics_device(pt, propagators, initial_states, num_steps=None, ops=None):
              View(rho[num_steps], col=1, b1=d2), nb1=nvec)
     out = ops.to_host(rho).transpose(1, 0, 2).reshape(nvec, num_steps + 1, d, d)
     return out[0] if single else out
+
+
+def _dynamics_multi_env(pts, propagators, initial_state, num_steps, ops):
+    """m >= 2 environments: the state is (chi_1, ..., chi_m, d2); each environment's
+    rank-3 PT-MPO site contracts its own bond leg, diagonal in the system leg x
+    (system_dynamics.py:689-700 with T4[l,r,x,x'] = T3[l,r,x] d_xx')."""
+    from ._lib import View  # pylint: disable=import-outside-toplevel
+    rho0 = np.asarray(initial_state, dtype=CDTYPE)
+    if rho0.ndim != 2:
+        raise NotImplementedError(
+            "oqupy_b200: ensembles over several environments are not supported yet")
+    m = len(pts)
+    d = rho0.shape[0]
+    d2 = d * d
+    if num_steps is None:
+        num_steps = min(len(p) for p in pts)
+    chis = [1] * m
+    v = ops.from_host(rho0.reshape(1, d2))
+    rho = ops.empty(num_steps + 1, d2)
+
+    def readout(state, dims, step, dst):
+        """rho = sum_{l_1..l_m} cap_1[l_1] .. cap_m[l_m] v[l_1..l_m, :]  (:643-651)"""
+        cur = state
+        rest = int(np.prod(dims)) * d2
+        for i in range(m):
+            rest //= dims[i]
+            cap = pts[i].get_cap_tensor_device(step)
+            out = dst if i == m - 1 else ops.empty(rest)
+            ops.gemm(1, rest, dims[i], View(cap, col=1), View(cur, row=rest, col=1),
+                     View(out, col=1))
+            cur = out
+
+    cache = {}
+    for step in range(num_steps):
+        readout(v, chis, step, rho[step])
+        p1, p2 = propagators(step)
+        key = (id(p1), id(p2))
+        if key not in cache:
+            cache.clear()
+            cache[key] = (ops.from_host(np.asarray(p1, dtype=CDTYPE)),
+                          ops.from_host(np.asarray(p2, dtype=CDTYPE)), p1, p2)
+        dp1, dp2 = cache[key][0], cache[key][1]
+        rows = int(np.prod(chis))
+        nxt = ops.empty(rows, d2)
+        ops.gemm(rows, d2, d2, View(v, row=d2, col=1), View(dp1, row=1, col=d2),
+                 View(nxt, row=d2, col=1))                          # v <- v P1^T
+        v = nxt
+        for i in range(m):
+            t = pts[i].get_mpo_tensor_device(step)
+            chi_l, chi_r, _ = t.shape
+            assert chi_l == chis[i]
+            na = int(np.prod(chis[:i]))                # legs before the contracted one
+            nb = int(np.prod(chis[i + 1:]))            # legs after it
+            nxt = ops.empty(na * chi_r * nb, d2)
+            # out[a, r, b, x] = sum_l T[l, r, x] v[a, l, b, x]; batches: x, a
+            ops.gemm(chi_r, nb, chi_l,
+                     View(t, row=d2, col=chi_r * d2, b1=1),
+                     View(v, row=nb * d2, col=d2, b1=1, b2=chi_l * nb * d2),
+                     View(nxt, row=nb * d2, col=d2, b1=1, b2=chi_r * nb * d2),
+                     nb1=d2, nb2=na)
+            v = nxt
+            chis[i] = chi_r
+        rows = int(np.prod(chis))
+        nxt = ops.empty(rows, d2)
+        ops.gemm(rows, d2, d2, View(v, row=d2, col=1), View(dp2, row=1, col=d2),
+                 View(nxt, row=d2, col=1))                          # v <- v P2^T
+        v = nxt
+    readout(v, chis, num_steps, rho[num_steps])
+    return ops.to_host(rho).reshape(num_steps + 1, d, d)
 
 
 def gradient_device(pt, propagators, initial_state, target_derivative, num_steps=None,

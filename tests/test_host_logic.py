@@ -119,3 +119,33 @@ def test_gradient_host_logic():
                           int(g["num_steps"]), 1)
     np.testing.assert_allclose(grad, g["grad_params"], atol=1e-10)
     np.testing.assert_almost_equal(grad.real[:, 0], g["grad_params_golden"], decimal=4)
+
+
+def _build_two_pts(g, ops):
+    pts = []
+    for key in ("influences_a", "influences_b"):
+        infl = g[key]
+        pt = ob.DeviceProcessTensor(2, dt=float(g["dt"]), ops=ops)
+        be = ob.PtTempoBackend(2, lambda dk, infl=infl: None if dk < 0 else infl[dk], pt,
+                               np.ones(4), np.ones(4), int(g["num_steps"]),
+                               int(g["dkmax"]), float(g["epsrel"]), ops=ops)
+        be.initialize()
+        while be.compute_step():
+            pass
+        be.update_process_tensor()
+        pts.append(pt)
+    return pts
+
+
+def test_multi_environment_dynamics_host_logic():
+    """compute_dynamics with two process tensors (system_dynamics.py:689-700)."""
+    g = load_golden("multi_env")
+    ops = HostModelOps()
+    pts = _build_two_pts(g, ops)
+    assert list(pts[0].get_bond_dimensions()) == list(g["bond_dims_a"])
+    assert list(pts[1].get_bond_dimensions()) == list(g["bond_dims_b"])
+    props = lambda step: (g["prop_1"], g["prop_2"])   # noqa: E731
+    states = ob.dynamics_device(pts, props, g["initial_state"], ops=ops)
+    np.testing.assert_allclose(states, g["states"], atol=1e-10, rtol=0)
+    swapped = ob.dynamics_device(pts[::-1], props, g["initial_state"], ops=ops)
+    np.testing.assert_allclose(swapped, g["states_swapped"], atol=1e-10, rtol=0)

@@ -113,3 +113,21 @@ def test_gradient_oracle_matches_reference():
     np.testing.assert_allclose(grad, g["grad_params"], atol=1e-12)
     # the reference test's own pin (grad_params_J, decimal=4)
     np.testing.assert_almost_equal(grad.real[:, 0], g["grad_params_golden"], decimal=4)
+
+
+def test_multi_environment_oracle_matches_reference():
+    """compute_dynamics with two process tensors (system_dynamics.py:689-700; the
+    setting of tests/physics/multi_environments_test.py with two different baths)."""
+    g = load_golden("multi_env")
+    mpos, caps = [], []
+    for key, bkey in (("influences_a", "bond_dims_a"), ("influences_b", "bond_dims_b")):
+        infl = g[key]
+        pt = onp.PtTempoOracle(2, lambda dk, infl=infl: None if dk < 0 else infl[dk],
+                               int(g["num_steps"]), int(g["dkmax"]), float(g["epsrel"]))
+        pt.compute()
+        assert [1] + pt.bond_dimensions() + [1] == list(g[bkey])
+        mpos.append(pt.mpo_tensors())
+        caps.append(onp.compute_caps(mpos[-1], 2))
+    props = lambda step: (g["prop_1"], g["prop_2"])   # noqa: E731
+    states = onp.compute_dynamics(mpos, caps, props, g["initial_state"])
+    np.testing.assert_allclose(states, g["states"], atol=1e-10, rtol=0)
