@@ -266,10 +266,22 @@ def gpu_arm(args):
 
     # bounded CPU baseline on this box's host cores (oracle port), same step window
     # (rank 0, N=1 only: with N > 1 the other ranks' host threads share the cores)
-    cdone, cdt, _ = run_cpu(args.steps, args.warmup, args.cpu_budget,
-                            load_operands(0)[1]) \
+    cdone, cdt, cbonds = run_cpu(args.steps, args.warmup, args.cpu_budget,
+                                 load_operands(0)[1]) \
         if not (args.no_cpu or world > 1) else (0, 1.0, None)
     cpu_val = cdone / cdt if cdone else None
+    # parity at bench scale: per-bond dimensions of the MPS after the timed window,
+    # CUDA path vs the oracle (only when the oracle covered the whole window)
+    parity = None
+    if cbonds is not None and cdone == args.steps:
+        mine = be.get_bond_dimensions()[1:-1]
+        diff = [abs(int(a) - int(b)) for a, b in zip(mine, cbonds)]
+        parity = {"bonds_compared": len(diff), "bonds_equal": sum(x == 0 for x in diff),
+                  "max_abs_diff": max(diff) if diff else 0,
+                  "max_bond": int(max(cbonds)) if len(cbonds) else 0,
+                  "note": ("bond dimensions after the last timed step, CUDA path vs CPU "
+                           "oracle; differences are truncation-threshold ties "
+                           "(DESIGN.md section 4)")}
 
     line = {
         "metric": "PT-TEMPO steps/s at dkmax=200, epsrel=1e-9",
@@ -309,6 +321,7 @@ def gpu_arm(args):
             "launches": int(k_launches), "jacobi_sweeps": int(k_sweeps),
             "algorithmic_flops": k_flops,
         },
+        "parity": parity,
         "cpu_baseline": None if cpu_val is None else {
             "value": cpu_val, "unit": "steps/s", "cores": host_threads(),
             "kind": "port",
