@@ -165,6 +165,18 @@ int b200_dyn_step(void* stream, int nvec, int chi_l, int chi_r, int d2,
                   const void* t, const void* p1, const void* p2, const void* v,
                   void* v_out, const void* cap, void* rho_out, void* work);
 
+/* The whole loop of compute_dynamics (oqupy/system_dynamics.py:131-170) for ONE
+ * environment in one call: for k = 0..nsteps-1 the fused step above (read-out of step k
+ * included), then the final read-out.  t[k] / caps[k] are HOST arrays of device pointers
+ * to the PT-MPO sites (chi[k], chi[k+1], d2) and cap vectors (chi[k]); p1 / p2 hold the
+ * propagators of step k at element offset k*prop_step_stride (0: time independent), each
+ * (nvec, d2, d2); v0 (nvec, chi[0], d2); rho_out (nsteps+1, nvec, d2). */
+size_t b200_dyn_run_workspace_bytes(int nsteps, int nvec, const int32_t* chi, int d2);
+int b200_dyn_run(void* stream, int nsteps, int nvec, int d2, const int32_t* chi,
+                 const void* const* t, const void* p1, const void* p2,
+                 int64_t prop_step_stride, const void* const* caps, const void* v0,
+                 void* rho_out, void* work);
+
 /* cap_k[l] = sum_{r,x} T[l,r,x] * cap_next[r] * tr2[x]   (oqupy/process_tensor.py:380-406) */
 int b200_caps_step(void* stream, int chi_l, int chi_r, int d2, const void* t,
                    const void* cap_next, const void* tr2, void* cap_out);

@@ -19,7 +19,7 @@ EXPORTS = [
     "b200_profile_enable", "b200_profile_read",
     "b200_zgemm_strided", "b200_svd_workspace_bytes", "b200_svd_factor",
     "b200_svd_emit", "b200_svd_values", "b200_svd_phase_cycles", "b200_dyn_workspace_bytes",
-    "b200_dyn_step", "b200_caps_step",
+    "b200_dyn_step", "b200_caps_step", "b200_dyn_run", "b200_dyn_run_workspace_bytes",
     "b200_chain_create", "b200_chain_destroy", "b200_chain_len", "b200_chain_push",
     "b200_chain_shape", "b200_chain_read", "b200_chain_svd_sweep",
     "b200_chain_pt_zip_up_left", "b200_chain_stats", "b200_chain_log",
@@ -88,6 +88,12 @@ def load_library():
     lib.b200_caps_step.restype = c_int
     lib.b200_caps_step.argtypes = [c_void_p, c_int, c_int, c_int] + \
         [c_void_p] * 4
+    lib.b200_dyn_run_workspace_bytes.restype = c_size_t
+    lib.b200_dyn_run_workspace_bytes.argtypes = [c_int, c_int, POINTER(c_int32), c_int]
+    lib.b200_dyn_run.restype = c_int
+    lib.b200_dyn_run.argtypes = [c_void_p, c_int, c_int, c_int, POINTER(c_int32),
+                                 POINTER(c_void_p), c_void_p, c_void_p, c_int64,
+                                 POINTER(c_void_p), c_void_p, c_void_p, c_void_p]
     lib.b200_chain_create.restype = c_void_p
     lib.b200_chain_create.argtypes = [c_void_p]
     lib.b200_chain_destroy.restype = c_int
@@ -243,6 +249,21 @@ class CudaOps:
             None if rho_out is None else rho_out.data_ptr(),
             self._work.data_ptr())
         self._check(code, "b200_dyn_step")
+
+    def dyn_run(self, nvec, d2, sites, caps, p1, p2, prop_step_stride, v0, rho_out):
+        """The whole compute_dynamics loop in one C call (b200_dyn_run)."""
+        n = len(sites)
+        chi = (c_int32 * (n + 1))(*([int(t.shape[0]) for t in sites]
+                                    + [int(sites[-1].shape[1])]))
+        tp = (c_void_p * n)(*[t.data_ptr() for t in sites])
+        cp = (c_void_p * (n + 1))(*[c.data_ptr() for c in caps])
+        nbytes = self.lib.b200_dyn_run_workspace_bytes(n, nvec, chi, d2)
+        work = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
+        code = self.lib.b200_dyn_run(self._stream(), n, nvec, d2, chi, tp, p1.data_ptr(),
+                                     p2.data_ptr(), int(prop_step_stride), cp,
+                                     v0.data_ptr(), rho_out.data_ptr(), work.data_ptr())
+        self._check(code, "b200_dyn_run")
+        return work        # keep alive until the stream has consumed it
 
     def caps_step(self, chi_l, chi_r, d2, t, cap_next, tr2, cap_out):
         code = self.lib.b200_caps_step(

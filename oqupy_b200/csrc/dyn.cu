@@ -64,7 +64,7 @@ dyn_stream_kernel(int nvec, int chi_l, int chi_r, int d2, int lchunk,
 #pragma unroll
   for (int k = 0; k < EV; ++k) acc[k] = make_double2(0.0, 0.0);
   const cplx* tp = t + (size_t)l0 * ncol + c;
-#pragma unroll 4
+#pragma unroll 8
   for (int l = l0; l < l1; ++l, tp += ncol) {
     const cplx tv = __ldg(tp);
 #pragma unroll
@@ -129,7 +129,9 @@ __global__ void caps_kernel(int chi_l, int chi_r, int d2, const cplx* __restrict
 inline int dyn_splits(int nvec, int chi_l, int chi_r, int d2) {
   const int nx = (chi_r * d2 + DT - 1) / DT;
   const int ne = (nvec + EV - 1) / EV;
-  int ns = (148 * 4 + nx * ne - 1) / (nx * ne);
+  // enough CTAs for ~8 per SM: a streaming kernel needs the bytes in flight
+  const int per_sm = (ne == 1) ? 8 : 4;   // (E > 1: the split costs partial-sum traffic)
+  int ns = (148 * per_sm + nx * ne - 1) / (nx * ne);
   const int max_ns = (chi_l + 15) / 16;
   if (ns > max_ns) ns = max_ns;
   if (ns < 1) ns = 1;
@@ -202,5 +204,73 @@ extern "C" int b200_caps_step(void* stream_, int chi_l, int chi_r, int d2,
       chi_l, chi_r, d2, (const cplx*)t, (const cplx*)cap_next, (const cplx*)tr2,
       (cplx*)cap_out);
   B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+// ---------------------------------------------------------------------------
+// The whole compute_dynamics loop (system_dynamics.py:131-170) in ONE call: the per-step
+// launches are issued back to back from C, so the stream never waits for the interpreter
+// and the PT-MPO sites stream from HBM at close to copy speed.
+namespace {
+struct DynRunLayout { size_t va, vb, step, total; };
+DynRunLayout dyn_run_layout(int nsteps, int nvec, const int32_t* chi, int d2) {
+  int cmax = 1;
+  size_t step_max = 0;
+  for (int k = 0; k <= nsteps; ++k) if (chi[k] > cmax) cmax = chi[k];
+  for (int k = 0; k < nsteps; ++k) {
+    const size_t b = b200_dyn_workspace_bytes(nvec, chi[k], chi[k + 1], d2);
+    if (b > step_max) step_max = b;
+  }
+  const size_t fin = b200_dyn_workspace_bytes(nvec, chi[nsteps], 1, d2);
+  if (fin > step_max) step_max = fin;
+  DynRunLayout L;
+  const size_t vbytes = (((size_t)nvec * cmax * d2 * sizeof(cplx)) + 255) & ~(size_t)255;
+  L.va = 0; L.vb = vbytes; L.step = 2 * vbytes; L.total = 2 * vbytes + step_max;
+  return L;
+}
+}  // namespace
+
+extern "C" size_t b200_dyn_run_workspace_bytes(int nsteps, int nvec, const int32_t* chi,
+                                               int d2) {
+  if (nsteps <= 0 || nvec <= 0 || d2 <= 0 || !chi) return 0;
+  return dyn_run_layout(nsteps, nvec, chi, d2).total;
+}
+
+extern "C" int b200_dyn_run(void* stream_, int nsteps, int nvec, int d2, const int32_t* chi,
+                            const void* const* t, const void* p1, const void* p2,
+                            int64_t prop_step_stride, const void* const* caps,
+                            const void* v0, void* rho_out, void* work) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (nsteps <= 0 || nvec <= 0 || d2 <= 0 || !chi || !t || !p1 || !p2 || !caps || !v0 ||
+      !rho_out || !work) {
+    b200::set_error("b200_dyn_run: invalid argument");
+    return B200_EINVAL;
+  }
+  const DynRunLayout L = dyn_run_layout(nsteps, nvec, chi, d2);
+  unsigned char* base = (unsigned char*)work;
+  cplx* bufs[2] = {(cplx*)(base + L.va), (cplx*)(base + L.vb)};
+  void* step_work = base + L.step;
+  const cplx* v = (const cplx*)v0;
+  cplx* rho = (cplx*)rho_out;
+  const cplx* P1 = (const cplx*)p1;
+  const cplx* P2 = (const cplx*)p2;
+  for (int k = 0; k < nsteps; ++k) {
+    cplx* vo = bufs[k & 1];
+    const int rc = b200_dyn_step(stream_, nvec, chi[k], chi[k + 1], d2, t[k],
+                                 P1 + (size_t)k * prop_step_stride,
+                                 P2 + (size_t)k * prop_step_stride, v, vo, caps[k],
+                                 rho + (size_t)k * nvec * d2, step_work);
+    if (rc != B200_OK) return rc;
+    v = vo;
+  }
+  {   // final read-out rho[N] = sum_l cap_N[l] v[l]  (system_dynamics.py:167-170)
+    const int chi_l = chi[nsteps];
+    int bx = (chi_l * d2 + 255) / 256;
+    if (bx > 64) bx = 64;
+    dyn_pre_kernel<<<dim3(bx, nvec), 256, 0, stream>>>(
+        nvec, chi_l, d2, P1, v, (cplx*)step_work, (const cplx*)caps[nsteps],
+        rho + (size_t)nsteps * nvec * d2);
+    B200_LAUNCH_CHECK();
+  }
   return B200_OK;
 }
