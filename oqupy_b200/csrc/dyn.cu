@@ -64,7 +64,7 @@ dyn_stream_kernel(int nvec, int chi_l, int chi_r, int d2, int lchunk,
 #pragma unroll
   for (int k = 0; k < EV; ++k) acc[k] = make_double2(0.0, 0.0);
   const cplx* tp = t + (size_t)l0 * ncol + c;
-#pragma unroll 8
+#pragma unroll 4
   for (int l = l0; l < l1; ++l, tp += ncol) {
     const cplx tv = __ldg(tp);
 #pragma unroll
