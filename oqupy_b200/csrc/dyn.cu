@@ -105,6 +105,217 @@ __global__ void dyn_post_kernel(int nvec, int chi_r, int d2, int ns,
   }
 }
 
+// ---- TMA (bulk async copy) helpers: the rows of T stream into shared memory through a
+// 4-stage mbarrier pipeline, one cp.async.bulk per row chunk.  (Plain LDG tops out near
+// 2 TB/s here: the per-SM miss queues bound the bytes in flight; a bulk copy is ONE
+// request for kilobytes.)
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+  return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+               ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes,
+                                          unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+
+constexpr int DW = 256;    // columns of T per CTA (4 KB per row chunk)
+constexpr int DST = 4;     // pipeline stages
+constexpr int RPS = 4;     // rows of T per stage (4 bulk copies on one mbarrier): 64 KB in flight
+constexpr int DCPT = DW / DT;   // columns per thread
+
+// One launch per step:  u = P1 v for the CTA's own l-range (shared memory) -> stream T
+// (TMA pipeline) -> partial sums -> the LAST CTA of a column block (atomic ticket) reduces
+// the partials and applies P2.  CTA (0, 0, z) also does the read-out
+// rho = sum_l cap[l] v[l, :].
+template <int EVT>
+__global__ void __launch_bounds__(DT)
+dyn_fused_kernel(int nvec, int chi_l, int chi_r, int d2, int lchunk, int cols_per_cta,
+                 const cplx* __restrict__ t, const cplx* __restrict__ p1,
+                 const cplx* __restrict__ p2, const cplx* __restrict__ v,
+                 cplx* __restrict__ v_out, const cplx* __restrict__ cap,
+                 cplx* __restrict__ rho, cplx* __restrict__ partial,
+                 unsigned int* __restrict__ tickets) {
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
+  cplx* stage = reinterpret_cast<cplx*>(dyn_smem);                 // [DST][RPS][DW]
+  cplx* us = stage + DST * RPS * DW;                               // [EVT][lchunk][d2]
+  __shared__ __align__(8) unsigned long long full[DST];
+  __shared__ int s_last;
+  const int ncol = chi_r * d2;
+  const int s = blockIdx.y, ns = gridDim.y - 1;
+  const int e0 = blockIdx.z * EVT;
+  if (s == ns) {
+    // ---- the extra CTA row: read-out of the INPUT state, rho[e, i] = sum_l cap[l] v[e, l, i]
+    // (system_dynamics.py:143-147); it never delays a streaming CTA
+    if (!cap || !rho || blockIdx.x != 0) return;
+    cplx* red = reinterpret_cast<cplx*>(dyn_smem);                 // [DT]
+    for (int k = 0; k < EVT; ++k) {
+      if (e0 + k >= nvec) break;
+      const cplx* V = v + (size_t)(e0 + k) * chi_l * d2;
+      for (int i = 0; i < d2; ++i) {
+        cplx a = make_double2(0.0, 0.0);
+#pragma unroll 4
+        for (int l = threadIdx.x; l < chi_l; l += DT) a = b200::cfma(cap[l], V[l * d2 + i], a);
+        red[threadIdx.x] = a;
+        __syncthreads();
+        for (int o = DT / 2; o > 0; o >>= 1) {
+          if (threadIdx.x < o) {
+            red[threadIdx.x].x += red[threadIdx.x + o].x;
+            red[threadIdx.x].y += red[threadIdx.x + o].y;
+          }
+          __syncthreads();
+        }
+        if (threadIdx.x == 0) rho[(size_t)(e0 + k) * d2 + i] = red[0];
+        __syncthreads();
+      }
+    }
+    return;
+  }
+  const int c0 = blockIdx.x * cols_per_cta;
+  const int wcols = min(cols_per_cta, ncol - c0);
+  const unsigned row_bytes = (unsigned)wcols * sizeof(cplx);
+  const int l0 = s * lchunk;
+  const int l1 = min(chi_l, l0 + lchunk);
+  const int nl = max(0, l1 - l0);
+  const cplx* tbase = t + (size_t)l0 * ncol + c0;
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < DST; ++q) mbar_init(&full[q], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int ngroups = (nl + RPS - 1) / RPS;       // row groups = pipeline steps
+  auto issue = [&](int grp) {                   // one thread: RPS bulk copies, one barrier
+    const int q = grp % DST;
+    const int r0 = grp * RPS;
+    const int nr = min(RPS, nl - r0);
+    mbar_expect_tx(&full[q], row_bytes * (unsigned)nr);
+    for (int rr = 0; rr < nr; ++rr)
+      bulk_load(stage + ((size_t)q * RPS + rr) * DW, tbase + (size_t)(r0 + rr) * ncol,
+                row_bytes, &full[q]);
+  };
+  if (threadIdx.x == 0)                         // prologue: fill the pipeline
+    for (int grp = 0; grp < DST && grp < ngroups; ++grp) issue(grp);
+  // ---- u[e, l, x] = sum_i P1[e][x, i] v[e, l, i] for l in [l0, l1)  (overlaps the loads)
+  for (int k = 0; k < EVT; ++k) {
+    if (e0 + k >= nvec) break;
+    const cplx* P = p1 + (size_t)(e0 + k) * d2 * d2;
+    const cplx* V = v + ((size_t)(e0 + k) * chi_l + l0) * d2;
+    for (int q = threadIdx.x; q < nl * d2; q += DT) {
+      const int l = q / d2, x = q % d2;
+      cplx acc = make_double2(0.0, 0.0);
+      for (int i = 0; i < d2; ++i) acc = b200::cfma(P[x * d2 + i], V[l * d2 + i], acc);
+      us[((size_t)k * lchunk + l) * d2 + x] = acc;
+    }
+  }
+  __syncthreads();
+  // ---- stream T: partial[s][e][c] = sum_{l in slice} T[l, c] u[e, l, x(c)]
+  cplx acc[DCPT][EVT];
+  int xs[DCPT];
+#pragma unroll
+  for (int j = 0; j < DCPT; ++j) {
+    xs[j] = (c0 + threadIdx.x + j * DT) % d2;
+#pragma unroll
+    for (int k = 0; k < EVT; ++k) acc[j][k] = make_double2(0.0, 0.0);
+  }
+  for (int grp = 0; grp < ngroups; ++grp) {
+    const int q = grp % DST;
+    mbar_wait(&full[q], (unsigned)((grp / DST) & 1));
+    const int r0 = grp * RPS;
+    const int nr = min(RPS, nl - r0);
+#pragma unroll
+    for (int rr = 0; rr < RPS; ++rr) {
+      if (rr < nr) {
+        const cplx* row = stage + ((size_t)q * RPS + rr) * DW;
+        const int l = r0 + rr;
+#pragma unroll
+        for (int j = 0; j < DCPT; ++j) {
+          const int cc = threadIdx.x + j * DT;
+          if (cc < wcols) {
+            const cplx tv = row[cc];
+#pragma unroll
+            for (int k = 0; k < EVT; ++k)
+              acc[j][k] = b200::cfma(tv, us[((size_t)k * lchunk + l) * d2 + xs[j]],
+                                     acc[j][k]);
+          }
+        }
+      }
+    }
+    __syncthreads();                            // everybody has consumed stage q
+    if (threadIdx.x == 0 && grp + DST < ngroups) issue(grp + DST);
+  }
+#pragma unroll
+  for (int j = 0; j < DCPT; ++j) {
+    const int cc = threadIdx.x + j * DT;
+    if (cc < wcols) {
+#pragma unroll
+      for (int k = 0; k < EVT; ++k)
+        if (e0 + k < nvec)
+          partial[((size_t)s * nvec + (e0 + k)) * ncol + c0 + cc] = acc[j][k];
+    }
+  }
+  // ---- the last CTA of this (column block, member group) finishes the step
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int* tk = tickets + (size_t)blockIdx.z * gridDim.x + blockIdx.x;
+    const unsigned int prev = atomicAdd(tk, 1u);
+    s_last = (prev == (unsigned int)(ns - 1));
+    if (s_last) *tk = 0u;                       // self-resetting for the next launch
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // w[e][c] = sum_s partial[s][e][c] (fixed order: deterministic), all loads of an entry
+  // in flight at once; staged in shared memory (the pipeline buffers are free now), then
+  // v_out[e][r, j] = sum_x P2[e][j, x] w[e][r, x]
+  cplx* ws = stage;                                   // [wcols] per member, reused
+  for (int k = 0; k < EVT; ++k) {
+    if (e0 + k >= nvec) break;
+    const cplx* pbase = partial + (size_t)(e0 + k) * ncol + c0;
+    const size_t sstride = (size_t)nvec * ncol;
+    for (int cc = threadIdx.x; cc < wcols; cc += DT) {
+      cplx pv[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q)
+        pv[q] = (q < ns) ? __ldcg(reinterpret_cast<const double2*>(pbase + q * sstride + cc))
+                         : make_double2(0.0, 0.0);
+      cplx w = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) { w.x += pv[q].x; w.y += pv[q].y; }
+      for (int q = 16; q < ns; ++q) {             // (ns <= 16 by construction)
+        const cplx x = __ldcg(reinterpret_cast<const double2*>(pbase + q * sstride + cc));
+        w.x += x.x; w.y += x.y;
+      }
+      ws[cc] = w;
+    }
+    __syncthreads();
+    const cplx* P = p2 + (size_t)(e0 + k) * d2 * d2;
+    for (int cc = threadIdx.x; cc < wcols; cc += DT) {
+      const int rr = cc / d2, j = cc % d2;          // c0 is a multiple of d2
+      cplx a = make_double2(0.0, 0.0);
+      for (int x = 0; x < d2; ++x) a = b200::cfma(P[j * d2 + x], ws[rr * d2 + x], a);
+      v_out[(size_t)(e0 + k) * ncol + c0 + cc] = a;
+    }
+    __syncthreads();
+  }
+}
+
 // cap_out[l] = sum_{r,x} T[l,r,x] cap_next[r] tr2[x] ; one warp per l
 __global__ void caps_kernel(int chi_l, int chi_r, int d2, const cplx* __restrict__ t,
                             const cplx* __restrict__ cap_next,
@@ -126,70 +337,97 @@ __global__ void caps_kernel(int chi_l, int chi_r, int d2, const cplx* __restrict
   if (lane == 0) cap_out[warp] = acc;
 }
 
-inline int dyn_splits(int nvec, int chi_l, int chi_r, int d2) {
-  const int nx = (chi_r * d2 + DT - 1) / DT;
-  const int ne = (nvec + EV - 1) / EV;
-  // enough CTAs for ~8 per SM: a streaming kernel needs the bytes in flight
-  const int per_sm = (ne == 1) ? 8 : 4;   // (E > 1: the split costs partial-sum traffic)
-  int ns = (148 * per_sm + nx * ne - 1) / (nx * ne);
-  const int max_ns = (chi_l + 15) / 16;
+constexpr size_t kTicketBytes = 64 * 1024;   // >= nx * ne tickets (checked)
+
+struct DynGeom { int cols_per_cta, nx, ne, ev, ns, lchunk; size_t smem, part_bytes, ticket_bytes; };
+
+inline DynGeom dyn_geom(int nvec, int chi_l, int chi_r, int d2) {
+  DynGeom g;
+  g.cols_per_cta = (DW / d2) * d2;                 // whole system-leg groups per CTA
+  if (g.cols_per_cta < d2) g.cols_per_cta = d2;    // (d2 > DT is rejected by the caller)
+  g.nx = (chi_r * d2 + g.cols_per_cta - 1) / g.cols_per_cta;
+  g.ev = (nvec == 1) ? 1 : EV;
+  g.ne = (nvec + g.ev - 1) / g.ev;
+  // enough CTAs for ~8 per SM (E = 1): a streaming kernel needs the bytes in flight;
+  // with several members per thread the split costs partial-sum traffic
+  const int per_sm = 2;
+  int ns = (148 * per_sm + g.nx * g.ne - 1) / (g.nx * g.ne);
+  int max_ns = (chi_l + 31) / 32;            // at least 32 rows per CTA: a real pipeline
+  if (max_ns > 16) max_ns = 16;              // the last CTA sums ns partials per entry
   if (ns > max_ns) ns = max_ns;
   if (ns < 1) ns = 1;
-  return ns;
+  g.lchunk = (chi_l + ns - 1) / ns;
+  while ((size_t)g.lchunk * d2 * g.ev * sizeof(cplx) > 40 * 1024) {   // u must fit in smem
+    ++ns;
+    g.lchunk = (chi_l + ns - 1) / ns;
+  }
+  g.ns = (chi_l + g.lchunk - 1) / g.lchunk;
+  g.smem = (size_t)DST * RPS * DW * sizeof(cplx) + (size_t)g.lchunk * d2 * g.ev * sizeof(cplx);
+  g.part_bytes = (((size_t)g.ns * nvec * chi_r * d2 * sizeof(cplx)) + 255) & ~(size_t)255;
+  g.ticket_bytes = kTicketBytes;                   // fixed: tickets live at offset 0
+  return g;
 }
 
 }  // namespace
 
 extern "C" size_t b200_dyn_workspace_bytes(int nvec, int chi_l, int chi_r, int d2) {
-  if (nvec <= 0 || chi_l <= 0 || chi_r <= 0 || d2 <= 0) return 0;
-  const int ns = dyn_splits(nvec, chi_l, chi_r, d2);
-  const size_t u = (size_t)nvec * chi_l * d2 * sizeof(cplx);
-  const size_t part = (size_t)ns * nvec * chi_r * d2 * sizeof(cplx);
-  return ((u + 255) & ~(size_t)255) + part;
+  if (nvec <= 0 || chi_l <= 0 || chi_r <= 0 || d2 <= 0 || d2 > DT) return 0;
+  const DynGeom g = dyn_geom(nvec, chi_l, chi_r, d2);
+  return g.part_bytes + g.ticket_bytes;
 }
 
-extern "C" int b200_dyn_step(void* stream_, int nvec, int chi_l, int chi_r, int d2,
-                             const void* t, const void* p1, const void* p2,
-                             const void* v, void* v_out, const void* cap,
-                             void* rho_out, void* work) {
+static int dyn_step_impl(void* stream_, int nvec, int chi_l, int chi_r, int d2,
+                         const void* t, const void* p1, const void* p2, const void* v,
+                         void* v_out, const void* cap, void* rho_out, void* work,
+                         bool clear_tickets) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (nvec <= 0 || chi_l <= 0 || chi_r <= 0 || d2 <= 0 || !t || !p1 || !p2 || !v ||
       !v_out || !work) {
     b200::set_error("b200_dyn_step: invalid argument");
     return B200_EINVAL;
   }
-  if (nvec > 65535) {
-    b200::set_error("b200_dyn_step: nvec too large");
+  if (nvec > 65535 * EV || d2 > DT) {
+    b200::set_error("b200_dyn_step: nvec or d2 too large");
     return B200_ESIZE;
   }
-  const int ns = dyn_splits(nvec, chi_l, chi_r, d2);
-  const size_t u_bytes = (((size_t)nvec * chi_l * d2 * sizeof(cplx)) + 255) & ~(size_t)255;
-  cplx* u = (cplx*)work;
-  cplx* partial = (cplx*)((unsigned char*)work + u_bytes);
-  {
-    int bx = (chi_l * d2 + 255) / 256;
-    if (bx > 64) bx = 64;
-    dyn_pre_kernel<<<dim3(bx, nvec), 256, 0, stream>>>(
-        nvec, chi_l, d2, (const cplx*)p1, (const cplx*)v, u, (const cplx*)cap,
-        (cplx*)rho_out);
-    B200_LAUNCH_CHECK();
+  const DynGeom g = dyn_geom(nvec, chi_l, chi_r, d2);
+  if ((size_t)g.nx * g.ne * sizeof(unsigned int) > kTicketBytes) {
+    b200::set_error("b200_dyn_step: too many column blocks");
+    return B200_ESIZE;
   }
-  {
-    const int nx = (chi_r * d2 + DT - 1) / DT;
-    const int ne = (nvec + EV - 1) / EV;
-    const int lchunk = (chi_l + ns - 1) / ns;
-    dyn_stream_kernel<<<dim3(nx, ns, ne), DT, 0, stream>>>(
-        nvec, chi_l, chi_r, d2, lchunk, (const cplx*)t, u, partial);
-    B200_LAUNCH_CHECK();
+  unsigned int* tickets = (unsigned int*)work;
+  cplx* partial = (cplx*)((unsigned char*)work + kTicketBytes);
+  static bool attr_set = false;
+  if (!attr_set) {
+    B200_CUDA_CHECK(cudaFuncSetAttribute(dyn_fused_kernel<1>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    B200_CUDA_CHECK(cudaFuncSetAttribute(dyn_fused_kernel<EV>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
   }
-  {
-    int bx = (chi_r * d2 + 255) / 256;
-    if (bx > 64) bx = 64;
-    dyn_post_kernel<<<dim3(bx, nvec), 256, 0, stream>>>(
-        nvec, chi_r, d2, ns, (const cplx*)p2, partial, (cplx*)v_out);
-    B200_LAUNCH_CHECK();
-  }
+  // tickets are self-resetting, but `work` may be fresh memory
+  if (clear_tickets) B200_CUDA_CHECK(cudaMemsetAsync(tickets, 0, kTicketBytes, stream));
+  const dim3 grid(g.nx, g.ns + 1, g.ne);     // +1: the read-out CTA row
+  if (g.ev == 1)
+    dyn_fused_kernel<1><<<grid, DT, g.smem, stream>>>(
+        nvec, chi_l, chi_r, d2, g.lchunk, g.cols_per_cta, (const cplx*)t, (const cplx*)p1,
+        (const cplx*)p2, (const cplx*)v, (cplx*)v_out, (const cplx*)cap, (cplx*)rho_out,
+        partial, tickets);
+  else
+    dyn_fused_kernel<EV><<<grid, DT, g.smem, stream>>>(
+        nvec, chi_l, chi_r, d2, g.lchunk, g.cols_per_cta, (const cplx*)t, (const cplx*)p1,
+        (const cplx*)p2, (const cplx*)v, (cplx*)v_out, (const cplx*)cap, (cplx*)rho_out,
+        partial, tickets);
+  B200_LAUNCH_CHECK();
   return B200_OK;
+}
+
+extern "C" int b200_dyn_step(void* stream_, int nvec, int chi_l, int chi_r, int d2,
+                             const void* t, const void* p1, const void* p2,
+                             const void* v, void* v_out, const void* cap,
+                             void* rho_out, void* work) {
+  return dyn_step_impl(stream_, nvec, chi_l, chi_r, d2, t, p1, p2, v, v_out, cap, rho_out,
+                       work, true);
 }
 
 extern "C" int b200_caps_step(void* stream_, int chi_l, int chi_r, int d2,
@@ -221,7 +459,8 @@ DynRunLayout dyn_run_layout(int nsteps, int nvec, const int32_t* chi, int d2) {
     const size_t b = b200_dyn_workspace_bytes(nvec, chi[k], chi[k + 1], d2);
     if (b > step_max) step_max = b;
   }
-  const size_t fin = b200_dyn_workspace_bytes(nvec, chi[nsteps], 1, d2);
+  // the final read-out (dyn_pre_kernel) needs room for u = P1 v of the last state
+  const size_t fin = (size_t)nvec * chi[nsteps] * d2 * sizeof(cplx) + 256;
   if (fin > step_max) step_max = fin;
   DynRunLayout L;
   const size_t vbytes = (((size_t)nvec * cmax * d2 * sizeof(cplx)) + 255) & ~(size_t)255;
@@ -254,12 +493,13 @@ extern "C" int b200_dyn_run(void* stream_, int nsteps, int nvec, int d2, const i
   cplx* rho = (cplx*)rho_out;
   const cplx* P1 = (const cplx*)p1;
   const cplx* P2 = (const cplx*)p2;
+  B200_CUDA_CHECK(cudaMemsetAsync(step_work, 0, kTicketBytes, stream));
   for (int k = 0; k < nsteps; ++k) {
     cplx* vo = bufs[k & 1];
-    const int rc = b200_dyn_step(stream_, nvec, chi[k], chi[k + 1], d2, t[k],
+    const int rc = dyn_step_impl(stream_, nvec, chi[k], chi[k + 1], d2, t[k],
                                  P1 + (size_t)k * prop_step_stride,
                                  P2 + (size_t)k * prop_step_stride, v, vo, caps[k],
-                                 rho + (size_t)k * nvec * d2, step_work);
+                                 rho + (size_t)k * nvec * d2, step_work, false);
     if (rc != B200_OK) return rc;
     v = vo;
   }
