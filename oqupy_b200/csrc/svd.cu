@@ -251,6 +251,7 @@ __device__ void inner_sweep(InnerShared& S, unsigned mask, double floor2, double
   const int t = threadIdx.x;
   const bool gthread = t < 256;
   const bool jthread = (t >= 256) && (t < 384);
+  const bool rthread = (t >= 384) && (t < 384 + BC);
   const int a = (t >> 4) & 15, b = t & 15;
   const int lane = t & 31, jrow0 = ((t - 256) >> 5) * 8;
   cplx jv[8];
@@ -266,22 +267,27 @@ __device__ void inner_sweep(InnerShared& S, unsigned mask, double floor2, double
     if (gthread) {
       g00r = S.gr[pa][pb]; g00i = S.gi[pa][pb]; g01r = S.gr[pa][qb]; g01i = S.gi[pa][qb];
       g10r = S.gr[qa][pb]; g10i = S.gi[qa][pb]; g11r = S.gr[qa][qb]; g11i = S.gi[qa][qb];
-      if (a == b) {
-        // straight-line: the rotation and the test are independent dependency chains
-        const double mag2 = fma(g01r, g01r, g01i * g01i);
-        const double thr = inner_threshold(g00r, g11r, floor2, neg2);
-        // cos(2t) = |h|/r, c = sqrt((1+cos 2t)/2), s e^{i phi} = sign(h) g/(2 r c)
-        const double h = 0.5 * (g11r - g00r);
-        const double inv_r = rsqrt(fma(h, h, mag2) + 1e-300);
-        const double w = fma(0.5 * fabs(h), inv_r, 0.5);
-        const double ic = rsqrt(w);            // two rsqrt: no sqrt, no division
-        const double kk = ((h >= 0.0) ? 0.5 : -0.5) * inv_r * ic;
-        const bool act = (mag2 > thr) && (fmax(g00r, g11r) > 0.0);
-        S.ract[a] = act ? 1 : 0;
-        S.rc[a] = act ? w * ic : 1.0;
-        S.rsr[a] = act ? g01r * kk : 0.0;
-        S.rsi[a] = act ? g01i * kk : 0.0;
-      }
+    } else if (rthread) {
+      // the 16 rotations of the round in ONE warp (lanes 0..15 of warp 12): the FP64
+      // pipe issues 8 lanes per clock, so 16 rotations scattered over 8 warps would cost
+      // 8 times the issue slots
+      const int p = pair_first(lane, hb), q = p ^ k;
+      const double gpp = S.gr[p][p], gqq = S.gr[q][q];
+      const double xr = S.gr[p][q], xi = S.gi[p][q];
+      // straight-line: the rotation and the test are independent dependency chains
+      const double mag2 = fma(xr, xr, xi * xi);
+      const double thr = inner_threshold(gpp, gqq, floor2, neg2);
+      // cos(2t) = |h|/r, c = sqrt((1+cos 2t)/2), s e^{i phi} = sign(h) g/(2 r c)
+      const double h = 0.5 * (gqq - gpp);
+      const double inv_r = rsqrt(fma(h, h, mag2) + 1e-300);
+      const double w = fma(0.5 * fabs(h), inv_r, 0.5);
+      const double ic = rsqrt(w);            // two rsqrt: no sqrt, no division
+      const double kk = ((h >= 0.0) ? 0.5 : -0.5) * inv_r * ic;
+      const bool act = (mag2 > thr) && (fmax(gpp, gqq) > 0.0);
+      S.ract[lane] = act ? 1 : 0;
+      S.rc[lane] = act ? w * ic : 1.0;
+      S.rsr[lane] = act ? xr * kk : 0.0;
+      S.rsi[lane] = act ? xi * kk : 0.0;
     }
     __syncthreads();
     if (gthread) {
