@@ -7,6 +7,8 @@
 // host round trip a dependent chain of exact-size sites needs), allocates the exact-size
 // outputs and launches b200_svd_emit.  Doing the loop here instead of in Python removes
 // ~70 us of interpreter time per SVD from a ~400-SVD dependency chain.
+#include <stdlib.h>
+
 #include <vector>
 
 #include "common.cuh"
@@ -123,6 +125,16 @@ void* b200_chain_create(void* stream) {
       uint64_t keep_all = ~0ull;
       cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep_all);
     }
+  }
+  {   // optional: reserve pool memory up front (B200_POOL_RESERVE_MB; measured: no gain
+      // for the config-2 build, the pool's release threshold above is what matters)
+    size_t mb = 0;
+    if (const char* e = getenv("B200_POOL_RESERVE_MB")) mb = (size_t)atoll(e);
+    void* p = nullptr;
+    if (mb > 0 && cudaMallocAsync(&p, mb << 20, c->stream) == cudaSuccess)
+      cudaFreeAsync(p, c->stream);
+    else
+      (void)cudaGetLastError();
   }
   const cplx h1 = make_double2(1.0, 0.0);
   cudaMemcpyAsync(c->one, &h1, sizeof(cplx), cudaMemcpyHostToDevice, c->stream);
