@@ -130,6 +130,11 @@ typedef struct {
   int kind;
   int rows, cols;
   const void* mat; /* device, complex128, row-major */
+  /* kind FIRST with degeneracy maps (unique=True, pt_tempo_backend.py:125-137), else NULL:
+   * HOST arrays of `cols` entries; B[w,y,n] = [w = west_map[y]] [n = north_map[y]] vec[n],
+   * mat = vec (rows = number of distinct north values) */
+  const int32_t* north_map;
+  const int32_t* west_map;
 } b200_pt_site;
 
 void* b200_chain_create(void* stream);

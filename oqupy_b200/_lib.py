@@ -36,7 +36,8 @@ class _Operand(Structure):
 
 
 class _PtSite(Structure):
-    _fields_ = [("kind", c_int), ("rows", c_int), ("cols", c_int), ("mat", c_void_p)]
+    _fields_ = [("kind", c_int), ("rows", c_int), ("cols", c_int), ("mat", c_void_p),
+                ("north_map", POINTER(c_int32)), ("west_map", POINTER(c_int32))]
 
 
 PT_KINDS = {"first": 0, "mid": 1, "last": 2, "closed": 3}
@@ -341,6 +342,7 @@ class NativeChain:
     def pt_zip_up_left(self, mpo, eps):
         """mpo: list of chain.PtSite (kind, device matrix)."""
         arr = (_PtSite * len(mpo))()
+        keep = []           # host map arrays stay alive for the call
         for k, site in enumerate(mpo):
             arr[k].kind = PT_KINDS[site.kind]
             m = site.mat
@@ -349,6 +351,12 @@ class NativeChain:
             else:
                 arr[k].rows, arr[k].cols = int(m.shape[0]), int(m.shape[1])
             arr[k].mat = m.data_ptr()
+            if getattr(site, "maps", None) is not None:
+                nmap, wmap = site.maps
+                keep += [(c_int32 * len(nmap))(*[int(x) for x in nmap]),
+                         (c_int32 * len(wmap))(*[int(x) for x in wmap])]
+                arr[k].north_map, arr[k].west_map = keep[-2], keep[-1]
+                arr[k].cols = len(nmap)
         self.ops._check(self.lib.b200_chain_pt_zip_up_left(c_void_p(self.h), arr, len(mpo),
                                                            float(eps)),
                         "b200_chain_pt_zip_up_left")

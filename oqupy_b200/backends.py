@@ -23,11 +23,17 @@ from .chain import PtSite, TempoSite
 CDTYPE = np.complex128
 
 
-def _check_unique(degeneracy_maps):
-    if degeneracy_maps is not None:
-        raise NotImplementedError(
-            "oqupy_b200: degeneracy maps (unique=True) are not supported yet "
-            "(SURVEY.md 8f row 4); use unique=False.")
+def _check_maps(degeneracy_maps, d2, n_north, n_west):
+    """[north_map, west_map] of unique=True (oqupy/bath.py:87-89, 158-164) as int arrays,
+    or None.  The reduced legs carry n_north / n_west distinct values."""
+    if degeneracy_maps is None:
+        return None
+    nmap, wmap = (np.asarray(m).astype(np.int64).reshape(-1) for m in degeneracy_maps)
+    assert nmap.size == d2 and wmap.size == d2, "degeneracy maps must have dim**2 entries"
+    assert nmap.min() >= 0 and wmap.min() >= 0
+    assert int(nmap.max()) + 1 == n_north, "north map does not match sum_north"
+    assert int(wmap.max()) + 1 == n_west, "west map does not match sum_west"
+    return nmap, wmap
 
 
 class PtTempoBackend:
@@ -36,7 +42,8 @@ class PtTempoBackend:
     def __init__(self, dimension, influence, process_tensor, sum_north,
                  sum_west, num_steps, dkmax, epsrel, config=None,
                  degeneracy_maps=None, ops=None):
-        _check_unique(degeneracy_maps)
+        self._maps = _check_maps(degeneracy_maps, dimension ** 2, len(sum_north),
+                                 len(sum_west))
         self._dimension = dimension
         self._influence = influence
         self._process_tensor = process_tensor
@@ -79,18 +86,25 @@ class PtTempoBackend:
         mpo, mps = [], []
         for i in range(self._num_infl):
             infl = np.asarray(self._influence(i), dtype=CDTYPE)
-            if i == 0:                                      # :122-143
+            if i == 0 and self._maps is not None:           # :125-137 (unique=True)
+                nmap, wmap = self._maps
+                vec = infl.reshape(-1) / d                  # n_north distinct values
+                mpo.append(PtSite("first", ops.from_host(vec), maps=(nmap, wmap)))
+                a = np.zeros((1, d2, vec.size), dtype=CDTYPE)
+                a[0, np.arange(d2), nmap] = vec[nmap] / d
+            elif i == 0:                                    # :122-143
                 vec = np.diag(infl) / d
                 mpo.append(PtSite("first", ops.from_host(vec)))
                 a = np.zeros((1, d2, d2), dtype=CDTYPE)
                 a[0, np.arange(d2), np.arange(d2)] = vec / d
             elif i == self._num_infl - 1:                   # :144-148
                 mpo.append(PtSite("last", ops.from_host(infl)))
-                a = infl.reshape(d2, d2, 1)
+                a = infl.reshape(infl.shape[0], infl.shape[1], 1)
             else:                                           # :149-152
                 mpo.append(PtSite("mid", ops.from_host(infl)))
-                a = np.zeros((d2, d2, d2), dtype=CDTYPE)
-                idx = np.arange(d2)
+                nn = infl.shape[0]          # (north, west): d2 x d2 unless unique=True
+                a = np.zeros((nn, infl.shape[1], nn), dtype=CDTYPE)
+                idx = np.arange(nn)
                 a[idx, :, idx] = infl / d
             mps.append(ops.from_host(a))
         self._mpo, self._mps = mpo, mps
@@ -117,7 +131,7 @@ class PtTempoBackend:
             last = self._mpo[-1]
             if last.kind == "first":
                 vec = ops.to_host(last.mat) * self._closing
-                self._mpo[-1] = PtSite("first", ops.from_host(vec))
+                self._mpo[-1] = PtSite("first", ops.from_host(vec), maps=last.maps)
             else:
                 mat = ops.to_host(last.mat) * self._closing[:, None]
                 self._mpo[-1] = PtSite("closed", ops.from_host(mat))
@@ -188,7 +202,8 @@ class BaseTempoBackend:
     def __init__(self, initial_state, influence, unitary_transform, sum_north,
                  sum_west, dkmax, epsrel, config=None, degeneracy_maps=None,
                  dim=None, ops=None):
-        _check_unique(degeneracy_maps)
+        self._maps = _check_maps(degeneracy_maps, np.asarray(initial_state).size,
+                                 len(sum_north), len(sum_west))
         self._initial_state = initial_state
         self._influence = influence
         self._unitary_transform = np.asarray(unitary_transform, dtype=CDTYPE)
@@ -225,16 +240,25 @@ class BaseTempoBackend:
         # dk = 0 site: B[w,n,s,e] = d_we d_ns infl0[n,w], then the unitary
         # transform on legs n and e (:419-424)
         infl0 = self._infl[0]
-        b0 = np.zeros((d2, d2, d2, d2), dtype=CDTYPE)
-        for n in range(d2):
-            for w in range(d2):
-                b0[w, n, n, w] = infl0[n, w]
+        if self._maps is not None:           # :408-417 (unique=True): reduced w and s legs
+            nmap, wmap = self._maps
+            nn, nw = self._sum_north.size, self._sum_west.size
+            b0 = np.zeros((nw, d2, nn, d2), dtype=CDTYPE)
+            idx = np.arange(d2)
+            b0[wmap, idx, nmap, idx] = infl0.reshape(-1)[nmap]
+        else:
+            nn = nw = d2
+            b0 = np.zeros((d2, d2, d2, d2), dtype=CDTYPE)
+            for n in range(d2):
+                for w in range(d2):
+                    b0[w, n, n, w] = infl0[n, w]
         b0 = np.einsum("wnse,nm->wmse", b0, super_u_dagg)
         b0 = np.einsum("wmse,fe->wmsf", b0, super_u)
         self._dense0 = b0
-        self._dense0_dev = ops.from_host(b0.reshape(d2 * d2, d2 * d2))
+        self._nn, self._nw = nn, nw
+        self._dense0_dev = ops.from_host(b0.reshape(nw * d2, nn * d2))
         self._dense0_west = ops.from_host(
-            np.tensordot(self._sum_west, b0, (0, 0)).reshape(d2, d2 * d2))
+            np.tensordot(self._sum_west, b0, (0, 0)).reshape(d2, nn * d2))
         self._infl_dev = {}
         self._sn_dev = ops.from_host(self._sum_north)
         self._d2 = d2
@@ -268,9 +292,10 @@ class BaseTempoBackend:
         for pos, dk in enumerate(dks):
             if dk == 0:
                 if pos == 0:
-                    mpo.append(TempoSite("dense", self._dense0_west, nw=1))
+                    mpo.append(TempoSite("dense", self._dense0_west, nw=1, ns=self._nn))
                 else:
-                    mpo.append(TempoSite("dense", self._dense0_dev, nw=d2))
+                    mpo.append(TempoSite("dense", self._dense0_dev, nw=self._nw,
+                                         ns=self._nn))
             elif pos == 0 and override is not None:
                 mat = np.asarray(override, dtype=CDTYPE) * self._sum_west[None, :]
                 mpo.append(TempoSite("start", ops.from_host(mat)))

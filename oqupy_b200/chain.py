@@ -22,15 +22,18 @@ class PtSite:
     """One PT-TEMPO influence MPO site in implicit (delta-structured) form.
 
     kind: 'first'  B[x,y,r]   = d_xy d_xr vec[x]                (dk = 0)
+                   with ``maps = (north_map, west_map)`` (unique=True,
+                   pt_tempo_backend.py:125-137):
+                   B[w,y,n] = [w = west_map[y]] [n = north_map[y]] vec[n]
           'mid'    B[l,x,y,r] = d_lr d_xy mat[l,x]
           'last'   B[l,0,y,0] = mat[l,y]          (newest site, array dim 1)
           'closed' B[l,x,y,0] = d_xy mat[l,x]     (mat already times the closing
                                                    vector, end phase)
     """
-    __slots__ = ("kind", "mat")
+    __slots__ = ("kind", "mat", "maps")
 
-    def __init__(self, kind, mat):
-        self.kind, self.mat = kind, mat
+    def __init__(self, kind, mat, maps=None):
+        self.kind, self.mat, self.maps = kind, mat, maps
 
 
 def _split(ops, theta, m, n, rs, cs, eps):
@@ -53,6 +56,28 @@ def pt_zip_up_left(ops, mps, mpo, eps):
         nl, nx, nr = a.shape
         site = mpo[ib]
         mat = site.mat
+        if site.kind == "first" and site.maps is not None:
+            nmap, wmap = site.maps          # one small product per array value y
+            ny = len(nmap)
+            if carry is None:       # out[l,y,0] = vec[n(y)] A[l,w(y),0]
+                assert nr == 1
+                out = ops.empty(nl, ny, 1)
+                for y in range(ny):
+                    ops.gemm(nl, 1, 1, View(a, row=nx * nr, off=int(wmap[y]) * nr),
+                             View(ops.one), View(out, row=ny, off=y),
+                             scale=View(mat, off=int(nmap[y])))
+            else:                   # out[l,y,k] = vec[n(y)] sum_r A[l,w(y),r] C[k,r,n(y)]
+                nk, _, ne = carry.shape
+                out = ops.empty(nl, ny, nk)
+                for y in range(ny):
+                    ops.gemm(nl, nk, nr,
+                             View(a, row=nx * nr, col=1, off=int(wmap[y]) * nr),
+                             View(carry, row=ne, col=nr * ne, off=int(nmap[y])),
+                             View(out, row=ny * nk, col=1, off=y * nk),
+                             scale=View(mat, off=int(nmap[y])))
+            mps[ia] = out
+            assert ib == 0
+            break
         if site.kind == "first":
             ny = nx
             if carry is None:       # closed single-site MPO: out[l,y,0] = vec[y] A[l,y,0]
@@ -145,10 +170,10 @@ class TempoSite:
           'mid'   mat[s,e] = infl[s,e]
           'dense' last aligned site (dk=0), explicit tensor mat[(w,n),(s,e)]
     """
-    __slots__ = ("kind", "mat", "nw")
+    __slots__ = ("kind", "mat", "nw", "ns")
 
-    def __init__(self, kind, mat, nw=None):
-        self.kind, self.mat, self.nw = kind, mat, nw
+    def __init__(self, kind, mat, nw=None, ns=None):
+        self.kind, self.mat, self.nw, self.ns = kind, mat, nw, ns
 
 
 def tempo_zip_up_right(ops, mps, mpo, eps):
@@ -177,7 +202,8 @@ def tempo_zip_up_right(ops, mps, mpo, eps):
             tmp = ops.empty(nk, nw, nn)      # T[k,w,n] = sum_l C[k,l,w] A[l,n]
             ops.gemm(nk, nn, nl, cview, View(a, row=nn * nr, col=nr),
                      View(tmp, row=nw * nn, col=1, b1=nn), nb1=nw)
-            out = ops.empty(nk, nn, nse // nn)        # (k, s, e): e dangles right
+            ns = nn if site.ns is None else site.ns   # unique=True: s is the reduced leg
+            out = ops.empty(nk, ns, nse // ns)        # (k, s, e): e dangles right
             ops.gemm(nk, nse, nw * nn, View(tmp, row=nw * nn, col=1),
                      View(mat, row=nse, col=1), View(out, row=nse, col=1))
             mps[ib] = out

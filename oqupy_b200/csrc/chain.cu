@@ -295,6 +295,38 @@ int b200_chain_pt_zip_up_left(void* h, const b200_pt_site* mpo, int nb, double e
     const int nl = a.dl, nx = a.da, nr = a.dr;
     const b200_pt_site& site = mpo[ib];
     const cplx* mat = (const cplx*)site.mat;
+    if (site.kind == B200_PT_FIRST && site.north_map && site.west_map) {
+      // unique=True (pt_tempo_backend.py:125-137): B[w,y,n] = [w=wmap[y]] [n=nmap[y]] vec[n];
+      // one small product per array value y
+      const int ny = site.cols;
+      const int32_t *nm = site.north_map, *wm = site.west_map;
+      for (int y = 0; y < ny; ++y)
+        if (wm[y] < 0 || wm[y] >= nx || nm[y] < 0 || nm[y] >= site.rows ||
+            (carry && nm[y] >= ce)) {
+          b200::set_error("pt_zip_up_left: degeneracy map out of range");
+          return B200_EINVAL;
+        }
+      cplx* out = nullptr;
+      if (!carry) {       // out[l,y,0] = vec[n(y)] A[l,w(y),0]
+        if (nr != 1) { b200::set_error("pt_zip_up_left: bad first site"); return B200_EINVAL; }
+        B200_TRY(dev_alloc(c, &out, (size_t)nl * ny));
+        for (int y = 0; y < ny; ++y)
+          B200_TRY(gemm(c, nl, 1, 1, 1, 1, op(a.p + (size_t)wm[y] * nr, (int64_t)nx * nr, 0),
+                        op(c->one, 0, 0), out + y, ny, 0, 0, 0, mat + nm[y], 0, 0));
+        c->sites[ia] = Site{out, nl, ny, 1};
+      } else {            // out[l,y,k] = vec[n(y)] sum_r A[l,w(y),r] C[k,r,n(y)]
+        if (cr != nr) { b200::set_error("pt_zip_up_left: carry mismatch"); return B200_EINVAL; }
+        B200_TRY(dev_alloc(c, &out, (size_t)nl * ny * ck));
+        for (int y = 0; y < ny; ++y)
+          B200_TRY(gemm(c, nl, ck, nr, 1, 1, op(a.p + (size_t)wm[y] * nr, (int64_t)nx * nr, 1),
+                        op(carry + nm[y], ce, (int64_t)nr * ce), out + (size_t)y * ck,
+                        (int64_t)ny * ck, 1, 0, 0, mat + nm[y], 0, 0));
+        c->sites[ia] = Site{out, nl, ny, ck};
+      }
+      B200_TRY(dev_free(c, a.p));
+      if (ib != 0) { b200::set_error("pt_zip_up_left: 'first' site must be leftmost"); return B200_EINVAL; }
+      break;
+    }
     if (site.kind == B200_PT_FIRST) {
       const int ny = nx;
       cplx* out = nullptr;

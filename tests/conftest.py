@@ -82,3 +82,18 @@ def check_mean_field_run(backend, g, seen):
     np.testing.assert_array_equal(np.array([s[1] for s in seen]), g["fields_in"])
     np.testing.assert_array_equal(np.array([s[2] for s in seen]), g["dfields_in"])
     return out
+
+
+def unique_callables(g):
+    """(influence(dk), propagators(step)) from a ``*_unique_*`` fixture: dk = 0 gives the
+    n_north reduced values, dk > 0 the reduced (n_north, n_west) matrices
+    (oqupy/tempo.py:969-1020 with the degeneracy maps of oqupy/bath.py:87-89)."""
+    infl0, infl = g["influence_0"], g["influences"]
+
+    def influence(dk):
+        if dk < 0:
+            return None
+        return infl0 if dk == 0 else infl[dk - 1]
+
+    p1, p2 = g["prop_1"], g["prop_2"]
+    return influence, (lambda step: (p1, p2))

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from conftest import (check_mean_field_run, golden_callables, load_golden,
-                      mean_field_callables)
+                      mean_field_callables, unique_callables)
 from host_model_ops import HostModelOps
 from oracle import tempo_np as onp
 import oqupy_b200 as ob
@@ -82,10 +82,60 @@ def test_tempo_backend_host_logic(name):
     np.testing.assert_allclose(states[:5], g["states"][:5], atol=1e-9, rtol=0)
 
 
-def test_unique_is_rejected_loudly():
-    with pytest.raises(NotImplementedError):
+def run_unique_pt(g, ops):
+    """PT-TEMPO with degeneracy maps (unique=True, pt_tempo_backend.py:114-140)."""
+    influence, propagators = unique_callables(g)
+    maps = [g["north_map"], g["west_map"]]
+    nn, nw = int(maps[0].max()) + 1, int(maps[1].max()) + 1
+    d = int(g["dim"])
+    pt = ob.DeviceProcessTensor(d, dt=float(g["dt"]), ops=ops)
+    be = ob.PtTempoBackend(d, influence, pt, np.ones(nn), np.ones(nw), int(g["num_steps"]),
+                           int(g["dkmax"]), float(g["epsrel"]), degeneracy_maps=maps,
+                           ops=ops)
+    be.initialize()
+    while be.compute_step():
+        pass
+    be.update_process_tensor()
+    return pt, ob.dynamics_device(pt, propagators, g["initial_state"], ops=ops)
+
+
+def run_unique_tempo(g, ops):
+    """TEMPO with degeneracy maps (unique=True, tempo_backend.py:400-417)."""
+    influence, propagators = unique_callables(g)
+    maps = [g["north_map"], g["west_map"]]
+    nn, nw = int(maps[0].max()) + 1, int(maps[1].max()) + 1
+    d = int(g["dim"])
+    be = ob.TempoBackend(g["initial_state"], influence, g["unitary"], propagators,
+                         np.ones(nn), np.ones(nw), int(g["dkmax"]), float(g["epsrel"]),
+                         degeneracy_maps=maps, dim=d, ops=ops)
+    _, s0 = be.initialize()
+    states = [s0]
+    for _ in range(int(g["num_steps"])):
+        states.append(be.compute_step()[1])
+    return be, np.array(states).reshape(-1, d, d)
+
+
+@pytest.mark.parametrize("tag", ["spin12", "spin1"])
+def test_unique_pt_host_logic(tag):
+    g = load_golden(f"pt_unique_{tag}")
+    pt, states = run_unique_pt(g, HostModelOps())
+    assert list(pt.get_bond_dimensions()) == list(g["bond_dims"])
+    np.testing.assert_allclose(states, g["states"], atol=1e-10, rtol=0)
+
+
+@pytest.mark.parametrize("tag", ["spin12", "spin1"])
+def test_unique_tempo_host_logic(tag):
+    g = load_golden(f"tempo_unique_{tag}")
+    be, states = run_unique_tempo(g, HostModelOps())
+    assert be.get_bond_dimensions() == list(g["bond_dims"])
+    np.testing.assert_allclose(states, g["states"], atol=50 * float(g["epsrel"]), rtol=0)
+    np.testing.assert_allclose(states[:3], g["states"][:3], atol=1e-9, rtol=0)
+
+
+def test_bad_degeneracy_maps_are_rejected():
+    with pytest.raises(AssertionError):
         ob.PtTempoBackend(2, lambda k: None, None, np.ones(4), np.ones(4), 10, 5,
-                          1e-6, degeneracy_maps=[np.arange(4), np.arange(4)],
+                          1e-6, degeneracy_maps=[np.arange(3), np.arange(4)],
                           ops=HostModelOps())
 
 

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from conftest import (check_mean_field_run, golden_callables, load_golden,
-                      mean_field_callables)
+                      mean_field_callables, unique_callables)
 from oracle import tempo_np as onp
 
 PT_CASES = ["pt_k12_eps7_n30", "pt_k8_eps9_n24", "pt_refA", "pt_refC"]
@@ -131,3 +131,46 @@ def test_multi_environment_oracle_matches_reference():
     props = lambda step: (g["prop_1"], g["prop_2"])   # noqa: E731
     states = onp.compute_dynamics(mpos, caps, props, g["initial_state"])
     np.testing.assert_allclose(states, g["states"], atol=1e-10, rtol=0)
+
+
+UNIQUE_TAGS = ["spin12", "spin1"]
+
+
+@pytest.mark.parametrize("tag", UNIQUE_TAGS)
+def test_pt_oracle_unique(tag):
+    """unique=True (pt_tempo_backend.py:114-140): reduced north / west legs."""
+    g = load_golden(f"pt_unique_{tag}")
+    influence, propagators = unique_callables(g)
+    maps = [g["north_map"], g["west_map"]]
+    pt = onp.PtTempoOracle(int(g["dim"]), influence, int(g["num_steps"]), int(g["dkmax"]),
+                           float(g["epsrel"]), sum_north=np.ones(int(maps[0].max()) + 1),
+                           degeneracy_maps=maps)
+    pt.compute()
+    mpos = pt.mpo_tensors()
+    caps = onp.compute_caps(mpos, int(g["dim"]))
+    states = onp.compute_dynamics([mpos], [caps], propagators, g["initial_state"])
+    assert [1] + pt.bond_dimensions() + [1] == list(g["bond_dims"])
+    np.testing.assert_allclose(states, g["states"], atol=1e-10, rtol=0)
+
+
+@pytest.mark.parametrize("tag", UNIQUE_TAGS)
+def test_tempo_oracle_unique(tag):
+    """unique=True (tempo_backend.py:400-417)."""
+    g = load_golden(f"tempo_unique_{tag}")
+    influence, propagators = unique_callables(g)
+    maps = [g["north_map"], g["west_map"]]
+    nn, nw = int(maps[0].max()) + 1, int(maps[1].max()) + 1
+    tb = onp.TempoOracle(g["initial_state"], influence, g["unitary"], propagators,
+                         np.ones(nn), np.ones(nw), int(g["dkmax"]), float(g["epsrel"]),
+                         degeneracy_maps=maps)
+    _, s0 = tb.initialize()
+    states = [s0]
+    for _ in range(int(g["num_steps"])):
+        states.append(tb.compute_step()[1])
+    d = int(g["dim"])
+    states = np.array(states).reshape(-1, d, d)
+    assert tb.bond_dimensions() == list(g["bond_dims"])
+    # spin-1 truncates from step 3 on (d2 = 9): 2.5e-8 there, the TEMPO reproducibility
+    # floor at eps = 1e-7 (see test_tempo_oracle_matches_reference); exact before
+    np.testing.assert_allclose(states, g["states"], atol=50 * float(g["epsrel"]), rtol=0)
+    np.testing.assert_allclose(states[:3], g["states"][:3], atol=1e-9, rtol=0)
