@@ -97,3 +97,22 @@ def unique_callables(g):
 
     p1, p2 = g["prop_1"], g["prop_2"]
     return influence, (lambda step: (p1, p2))
+
+
+def tebd_fixture(g):
+    """(gammas, lambdas, gate layers [[(sites, (gate_l, gate_r))]], pt sites / caps per
+    chain site or None) from a ``pt_tebd_F*`` fixture (tests/golden/make_golden_tebd.py)."""
+    n = int(g["n"])
+    gammas = [g[f"gamma_{i}"] for i in range(n)]
+    lambdas = [g[f"lambda_{i}"] for i in range(n - 1)]
+    layers = []
+    for li, size in enumerate(g["layer_sizes"]):
+        layers.append([(tuple(int(x) for x in g[f"gate_{li}_{gi}_sites"]),
+                        (g[f"gate_{li}_{gi}_l"], g[f"gate_{li}_{gi}_r"]))
+                       for gi in range(int(size))])
+    pt_sites = set(int(x) for x in g["pt_sites"])
+    mpos = caps = None
+    if pt_sites:
+        mpos = [g[f"pt_mpo_{k}"] for k in range(int(g["pt_len"]))]
+        caps = [g[f"pt_cap_{k}"] for k in range(int(g["pt_len"]) + 1)]
+    return gammas, lambdas, layers, pt_sites, mpos, caps
