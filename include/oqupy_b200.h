@@ -85,6 +85,14 @@ int b200_zgemm_strided(void* stream, int m, int n, int k, int nb1, int nb2,
  *
  * b200_svd_values: copies the min(m,n) sorted singular values (doubles) to s_out.
  *
+ * b200_svd_factor2: as b200_svd_factor with two-level row and column indices,
+ *   theta[i][j] at (i / rin)*rso + (i % rin)*rsi + (j / cin)*cso + (j % cin)*csi, so that
+ *   any leg grouping of a rank-4 tensor is factorised in place -- the PT-TEBD splits
+ *   (left_edges / right_edges of oqupy/backends/pt_tebd_backend.py:487-531).
+ * b200_svd_emit_parts: as b200_svd_emit; `vh` receives S*Vh (vh_unscaled = 0) or Vh
+ *   (vh_unscaled = 1), `lam` / `inv_lam` (complex128[keep], may be NULL) the kept singular
+ *   values and their inverses (the lambda matrices of pt_tebd_backend.py:526, 573-578).
+ *
  * Replaces: tn.split_node_full_svd(node, left_edges, right_edges,
  *             max_truncation_err=eps, relative=True)   oqupy/backends/node_array.py:262,285,541
  *           and `s @ vh` at node_array.py:272,295,552; truncation rule mirrored at
@@ -93,6 +101,12 @@ int b200_zgemm_strided(void* stream, int m, int n, int k, int nb1, int nb2,
 size_t b200_svd_workspace_bytes(int m, int n);
 int b200_svd_factor(void* stream, const void* theta, int m, int n, int64_t rs,
                     int64_t cs, double eps, void* work, int32_t* info_host);
+int b200_svd_factor2(void* stream, const void* theta, int m, int n, int rin, int64_t rso,
+                     int64_t rsi, int cin, int64_t cso, int64_t csi, double eps, void* work,
+                     int32_t* info_host);
+int b200_svd_emit_parts(void* stream, const void* work, int m, int n, int keep, void* u,
+                        int u_na, int64_t u_so, int64_t u_sa, int64_t u_sj, void* vh,
+                        int vh_unscaled, void* lam, void* inv_lam);
 int b200_svd_emit(void* stream, const void* work, const void* theta, int m, int n,
                   int64_t rs, int64_t cs, int keep, void* u, int u_na, int64_t u_so,
                   int64_t u_sa, int64_t u_sj, void* svh);

@@ -7,10 +7,12 @@ the compute_dynamics loop.  Everything reaches the GPU through the C-ABI library
 """
 from .backends import (BaseTempoBackend, MeanFieldTempoBackend, PtTempoBackend,
                        TempoBackend)
+from .tebd import PtTebdBackend
 from .process_tensor import DeviceProcessTensor, dynamics_device, gradient_device
 from ._lib import B200Error, CudaOps, default_ops, load_library
 
 __all__ = ["BaseTempoBackend", "MeanFieldTempoBackend", "PtTempoBackend", "TempoBackend",
+           "PtTebdBackend",
            "DeviceProcessTensor", "dynamics_device", "gradient_device", "B200Error", "CudaOps",
            "default_ops", "load_library"]
 __version__ = "0.1.0"

@@ -18,7 +18,7 @@ EXPORTS = [
     "b200_last_error", "b200_abi_version", "b200_launch_count",
     "b200_profile_enable", "b200_profile_read",
     "b200_zgemm_strided", "b200_svd_workspace_bytes", "b200_svd_factor",
-    "b200_svd_emit", "b200_svd_values", "b200_svd_phase_cycles", "b200_dyn_workspace_bytes",
+    "b200_svd_emit", "b200_svd_factor2", "b200_svd_emit_parts", "b200_svd_values", "b200_svd_phase_cycles", "b200_dyn_workspace_bytes",
     "b200_dyn_step", "b200_caps_step", "b200_dyn_run", "b200_dyn_run_workspace_bytes",
     "b200_chain_create", "b200_chain_destroy", "b200_chain_len", "b200_chain_push",
     "b200_chain_shape", "b200_chain_read", "b200_chain_svd_sweep",
@@ -77,6 +77,14 @@ def load_library():
     lib.b200_svd_emit.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int,
                                   c_int64, c_int64, c_int, c_void_p, c_int,
                                   c_int64, c_int64, c_int64, c_void_p]
+    lib.b200_svd_factor2.restype = c_int
+    lib.b200_svd_factor2.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int64,
+                                     c_int64, c_int, c_int64, c_int64, c_double, c_void_p,
+                                     c_void_p]
+    lib.b200_svd_emit_parts.restype = c_int
+    lib.b200_svd_emit_parts.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
+                                        c_int, c_int64, c_int64, c_int64, c_void_p, c_int,
+                                        c_void_p, c_void_p]
     lib.b200_svd_phase_cycles.restype = c_int
     lib.b200_svd_phase_cycles.argtypes = [c_void_p, c_void_p, c_void_p]
     lib.b200_svd_values.restype = c_int
@@ -195,11 +203,12 @@ class CudaOps:
             sp, s1, s2, 1 if accumulate else 0)
         self._check(code, "b200_zgemm_strided")
 
-    def svd_factor(self, theta, m, n, rs, cs, eps, off=0):
+    def svd_factor(self, theta, m, n, rs, cs, eps, off=0, rin=1, rsi=0, cin=1, csi=0):
+        """theta[i][j] at (i // rin)*rs + (i % rin)*rsi + (j // cin)*cs + (j % cin)*csi."""
         nbytes = self.lib.b200_svd_workspace_bytes(m, n)
         work = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-        code = self.lib.b200_svd_factor(
-            self._stream(), self._ptr(theta, off), m, n, rs, cs,
+        code = self.lib.b200_svd_factor2(
+            self._stream(), self._ptr(theta, off), m, n, rin, rs, rsi, cin, cs, csi,
             -1.0 if eps is None else float(eps), work.data_ptr(),
             self._info.data_ptr())
         self._check(code, "b200_svd_factor")
@@ -216,12 +225,19 @@ class CudaOps:
             self.svd_log.append((m, n, h.keep, h.sweeps))
         return h
 
-    def svd_emit(self, h, u=None, u_na=1, u_so=0, u_sa=0, u_sj=0, svh=None):
-        code = self.lib.b200_svd_emit(
-            self._stream(), h.work.data_ptr(), h.theta_ptr, h.m, h.n, h.rs, h.cs,
-            h.keep, None if u is None else u.data_ptr(), u_na, u_so, u_sa, u_sj,
-            None if svh is None else svh.data_ptr())
-        self._check(code, "b200_svd_emit")
+    def svd_emit(self, h, u=None, u_na=1, u_so=0, u_sa=0, u_sj=0, svh=None, vh=None,
+                 lam=None, inv_lam=None):
+        """U, and either S*Vh (``svh``) or Vh (``vh``); ``lam`` / ``inv_lam``: the kept
+        singular values and their inverses as complex128 vectors."""
+        assert svh is None or vh is None
+        right = svh if vh is None else vh
+        code = self.lib.b200_svd_emit_parts(
+            self._stream(), h.work.data_ptr(), h.m, h.n, h.keep,
+            None if u is None else u.data_ptr(), u_na, u_so, u_sa, u_sj,
+            None if right is None else right.data_ptr(), 0 if vh is None else 1,
+            None if lam is None else lam.data_ptr(),
+            None if inv_lam is None else inv_lam.data_ptr())
+        self._check(code, "b200_svd_emit_parts")
 
     def svd_phase_cycles(self, h):
         out = (ctypes.c_longlong * 16)()

@@ -530,7 +530,8 @@ jacobi_kernel(const cplx* __restrict__ theta, long long rs, long long cs,
               double* __restrict__ sval, int* __restrict__ perm,
               Header* __restrict__ hdr, int32_t* __restrict__ info, int p, int q, int nb,
               int Rx, int Rw, int RSx, int RSw, int SE, int transposed, int minmn,
-              double tol, double eps, double neg_rel) {
+              double tol, double eps, double neg_rel, int rin, long long rsi, int cin,
+              long long csi) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ InnerShared S;
   __shared__ double s_red[JT / 32];
@@ -567,12 +568,13 @@ jacobi_kernel(const cplx* __restrict__ theta, long long rs, long long cs,
       cplx v = make_double2(0.0, 0.0);
       if (row < p) {
         if (col < q) {
-          if (!transposed) {
-            v = theta[row * rs + col * cs];
-          } else {           // X = theta^H : X[row][col] = conj(theta[col][row])
-            v = theta[col * rs + row * cs];
-            v.y = -v.y;
-          }
+          // theta[i][j] lives at (i / rin) rs + (i % rin) rsi + (j / cin) cs + (j % cin) csi:
+          // two-level row and column indices, so that any leg grouping of a rank-4 tensor
+          // is factorised in place (rin = cin = 1: plain strides)
+          const int ti = transposed ? col : row, tj = transposed ? row : col;
+          v = theta[(long long)(ti / rin) * rs + (long long)(ti % rin) * rsi +
+                    (long long)(tj / cin) * cs + (long long)(tj % cin) * csi];
+          if (transposed) v.y = -v.y;   // X = theta^H
         }
         local = fma(v.x, v.x, local);
         local = fma(v.y, v.y, local);
@@ -881,10 +883,18 @@ __global__ void emit_kernel(const cplx* __restrict__ y, const double* __restrict
                             const int* __restrict__ perm, int m, int n, int p, int q,
                             int transposed, int keep, cplx* __restrict__ u, int u_na,
                             long long u_so, long long u_sa, long long u_sj,
-                            cplx* __restrict__ svh) {
+                            cplx* __restrict__ svh, int vh_unscaled,
+                            cplx* __restrict__ lam, cplx* __restrict__ inv_lam) {
   // element space: [0, m*keep) -> U ; [m*keep, (m+n)*keep) -> SVh
   const long long nu = (long long)m * keep, nv = (long long)n * keep;
   const size_t T = (size_t)p + q;
+  if (blockIdx.x == 0) {       // singular values as complex vectors (lambda, 1/lambda)
+    for (int j = threadIdx.x; j < keep; j += blockDim.x) {
+      const double s = sval[j];
+      if (lam) lam[j] = make_double2(s, 0.0);
+      if (inv_lam) inv_lam[j] = make_double2(1.0 / s, 0.0);
+    }
+  }
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < nu + nv;
        e += (long long)gridDim.x * blockDim.x) {
     if (e < nu) {
@@ -913,11 +923,16 @@ __global__ void emit_kernel(const cplx* __restrict__ y, const double* __restrict
       cplx v;
       if (!transposed) {         // S Vh[j, col] = sigma_j * conj(W[col, c])
         v = y[(blk * T + p + col) * BC + c16];
-        const double s = sval[j];
+        const double s = vh_unscaled ? 1.0 : sval[j];
         v = make_double2(v.x * s, -v.y * s);
       } else {                   // S Vh[j, col] = conj(Y[col, c])
         v = y[(blk * T + col) * BC + c16];
         v.y = -v.y;
+        if (vh_unscaled) {
+          const double s = sval[j];
+          const double inv = (s > 0.0) ? 1.0 / s : 0.0;
+          v.x *= inv; v.y *= inv;
+        }
       }
       svh[(long long)j * n + col] = v;
     }
@@ -937,8 +952,15 @@ extern "C" size_t b200_svd_workspace_bytes(int m, int n) {
 extern "C" int b200_svd_factor(void* stream_, const void* theta, int m, int n,
                                int64_t rs, int64_t cs, double eps, void* work,
                                int32_t* info_host) {
+  return b200_svd_factor2(stream_, theta, m, n, 1, rs, 0, 1, cs, 0, eps, work, info_host);
+}
+
+extern "C" int b200_svd_factor2(void* stream_, const void* theta, int m, int n, int rin,
+                                int64_t rso, int64_t rsi, int cin, int64_t cso, int64_t csi,
+                                double eps, void* work, int32_t* info_host) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (!theta || !work || !info_host || m <= 0 || n <= 0) {
+  const int64_t rs = rso, cs = cso;
+  if (!theta || !work || !info_host || m <= 0 || n <= 0 || rin < 1 || cin < 1) {
     b200::set_error("b200_svd_factor: invalid argument");
     return B200_EINVAL;
   }
@@ -983,9 +1005,10 @@ extern "C" int b200_svd_factor(void* stream_, const void* theta, int m, int n,
   if (tol < 1e-11) tol = 1e-11;
   // columns below 1e-2*eps*||X||_F can never be kept nor change the rank decision
   double neg_rel = (eps > 0.0) ? 1e-2 * eps : 0.0;
+  long long rsi_ = rsi, csi_ = csi;
   void* args[] = {&th, &rs_, &cs_, &y, &gpart, &ctrl, &sig2, &sval, &perm, &hdr,
                   &info_host, &p, &q, &nb, &Rx, &Rw, &RSx, &RSw, &SE, &tr, &minmn, &tol, &eps,
-                  &neg_rel};
+                  &neg_rel, &rin, &rsi_, &cin, &csi_};
   const int grid = L.SE * L.R;
   b200::profile_begin(stream);
   B200_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)jacobi_kernel, dim3(grid), dim3(JT),
@@ -1002,7 +1025,17 @@ extern "C" int b200_svd_factor(void* stream_, const void* theta, int m, int n,
 extern "C" int b200_svd_emit(void* stream_, const void* work, const void* theta, int m,
                              int n, int64_t rs, int64_t cs, int keep, void* u, int u_na,
                              int64_t u_so, int64_t u_sa, int64_t u_sj, void* svh) {
+  (void)theta; (void)rs; (void)cs;
+  return b200_svd_emit_parts(stream_, work, m, n, keep, u, u_na, u_so, u_sa, u_sj, svh, 0,
+                             nullptr, nullptr);
+}
+
+extern "C" int b200_svd_emit_parts(void* stream_, const void* work, int m, int n, int keep,
+                                   void* u, int u_na, int64_t u_so, int64_t u_sa,
+                                   int64_t u_sj, void* vh, int vh_unscaled, void* lam,
+                                   void* inv_lam) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  void* svh = vh;
   if (!work || m <= 0 || n <= 0 || keep < 0 || u_na < 1) {
     b200::set_error("b200_svd_emit: invalid argument");
     return B200_EINVAL;
@@ -1013,11 +1046,10 @@ extern "C" int b200_svd_emit(void* stream_, const void* work, const void* theta,
   const long long total = (long long)(m + n) * keep;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  (void)theta; (void)rs; (void)cs;
   emit_kernel<<<blocks, 256, 0, stream>>>(
       (const cplx*)(base + L.y), (const double*)(base + L.sval),
       (const int*)(base + L.perm), m, n, L.p, L.q, L.transposed, keep, (cplx*)u, u_na,
-      u_so, u_sa, u_sj, (cplx*)svh);
+      u_so, u_sa, u_sj, (cplx*)svh, vh_unscaled, (cplx*)lam, (cplx*)inv_lam);
   B200_LAUNCH_CHECK();
   return B200_OK;
 }

@@ -11,11 +11,13 @@ The key is consumed here because the reference forwards ``config["backend"]`` to
 tensornetwork (oqupy/backends/pt_tempo_backend.py:81-84).
 """
 from . import backends as _b200
+from . import tebd as _tebd
 
 _ORIGINALS = {}
+_FORCE = {"tebd": False}     # PtTebd has no module-level config dictionary to mutate
 
 
-def _dispatch(b200_cls, original_cls):
+def _dispatch(b200_cls, original_cls, force_key=None):
     def factory(*args, **kwargs):
         config = kwargs.get("config")
         if config is None:
@@ -23,6 +25,9 @@ def _dispatch(b200_cls, original_cls):
                 if isinstance(a, dict):
                     config = a
         if isinstance(config, dict) and config.get("backend") == "b200":
+            return b200_cls(*args, **kwargs)
+        if force_key is not None and _FORCE[force_key] and not (
+                isinstance(config, dict) and "backend" in config):
             return b200_cls(*args, **kwargs)
         return original_cls(*args, **kwargs)
     factory.__name__ = original_cls.__name__
@@ -35,10 +40,12 @@ def install(default=False):
     also mutated in place so that every Tempo / PtTempo uses the B200 backend."""
     import oqupy  # pylint: disable=import-outside-toplevel
     import oqupy.backends.tempo_backend as tb  # pylint: disable=import-outside-toplevel
+    import oqupy.pt_tebd as tebdm  # pylint: disable=import-outside-toplevel
     import oqupy.pt_tempo as ptm  # pylint: disable=import-outside-toplevel
     import oqupy.tempo as tm  # pylint: disable=import-outside-toplevel
     if not _ORIGINALS:
-        _ORIGINALS.update(TempoBackend=tm.TempoBackend,
+        _ORIGINALS.update(PtTebdBackend=tebdm.PtTebdBackend,
+                          TempoBackend=tm.TempoBackend,
                           BaseTempoBackend=tb.BaseTempoBackend,
                           MeanFieldTempoBackend=tm.MeanFieldTempoBackend,
                           PtTempoBackend=ptm.PtTempoBackend)
@@ -49,6 +56,10 @@ def install(default=False):
                                          _ORIGINALS["MeanFieldTempoBackend"])
     ptm.PtTempoBackend = _dispatch(_b200.PtTempoBackend,
                                    _ORIGINALS["PtTempoBackend"])
+    # oqupy/pt_tebd.py:26, 244: PtTebd(..., backend_config={"backend": "b200"})
+    tebdm.PtTebdBackend = _dispatch(_tebd.PtTebdBackend, _ORIGINALS["PtTebdBackend"],
+                                    force_key="tebd")
+    _FORCE["tebd"] = bool(default)
     if default:
         oqupy.config.TEMPO_BACKEND_CONFIG["backend"] = "b200"
         oqupy.config.PT_TEMPO_BACKEND_CONFIG["backend"] = "b200"
@@ -60,8 +71,11 @@ def uninstall():
         return
     import oqupy  # pylint: disable=import-outside-toplevel
     import oqupy.backends.tempo_backend as tb  # pylint: disable=import-outside-toplevel
+    import oqupy.pt_tebd as tebdm  # pylint: disable=import-outside-toplevel
     import oqupy.pt_tempo as ptm  # pylint: disable=import-outside-toplevel
     import oqupy.tempo as tm  # pylint: disable=import-outside-toplevel
+    tebdm.PtTebdBackend = _ORIGINALS["PtTebdBackend"]
+    _FORCE["tebd"] = False
     tm.TempoBackend = _ORIGINALS["TempoBackend"]
     tb.BaseTempoBackend = _ORIGINALS["BaseTempoBackend"]
     tm.MeanFieldTempoBackend = _ORIGINALS["MeanFieldTempoBackend"]

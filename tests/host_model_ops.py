@@ -61,10 +61,11 @@ class HostModelOps:
         else:
             cv.copy_(res)
 
-    def svd_factor(self, theta, m, n, rs, cs, eps, off=0):
+    def svd_factor(self, theta, m, n, rs, cs, eps, off=0, rin=1, rsi=0, cin=1, csi=0):
         self.launches += 4
-        mat = torch.as_strided(theta, (m, n), (rs, cs),
-                               theta.storage_offset() + off).numpy()
+        assert m % rin == 0 and n % cin == 0
+        mat = torch.as_strided(theta, (m // rin, rin, n // cin, cin), (rs, rsi, cs, csi),
+                               theta.storage_offset() + off).reshape(m, n).numpy()
         u, s, vh = np.linalg.svd(mat, full_matrices=False)
         if eps is None:
             keep = s.size
@@ -77,9 +78,16 @@ class HostModelOps:
         self.svd_log.append((m, n, keep, 0))
         return h
 
-    def svd_emit(self, h, u=None, u_na=1, u_so=0, u_sa=0, u_sj=0, svh=None):
+    def svd_emit(self, h, u=None, u_na=1, u_so=0, u_sa=0, u_sj=0, svh=None, vh=None,
+                 lam=None, inv_lam=None):
         self.launches += 1
         k = h.keep
+        if vh is not None:
+            vh.view(k, h.n).copy_(torch.from_numpy(np.ascontiguousarray(h.vh[:k])))
+        if lam is not None:
+            lam.copy_(torch.from_numpy(h.s[:k].astype(np.complex128)))
+        if inv_lam is not None:
+            inv_lam.copy_(torch.from_numpy((1.0 / h.s[:k]).astype(np.complex128)))
         if u is not None:
             no = h.m // u_na
             uv = torch.as_strided(u, (no, u_na, k), (u_so, u_sa, u_sj),

@@ -90,3 +90,75 @@ def test_install_dispatch_mean_field(monkeypatch):
                                    dr.system_dynamics[0].states, atol=1e-8)
     finally:
         install.uninstall()
+
+
+def test_install_dispatch_pt_tebd_and_unique(monkeypatch):
+    """oqupy.PtTebd (reference front-end: gate layers, TrivialProcessTensor, host
+    SimpleProcessTensor) on the rebound PtTebdBackend; oqupy.PtTempo / Tempo with
+    unique=True on the rebound TEMPO backends."""
+    oqupy = load_reference()
+    from oqupy_b200 import backends, install, tebd
+    from host_model_ops import HostModelOps
+    ops = HostModelOps()
+    monkeypatch.setattr(backends, "default_ops", lambda: ops)
+    monkeypatch.setattr(tebd, "default_ops", lambda: ops)
+    sig = oqupy.operators.sigma
+    corr = oqupy.PowerLawSD(alpha=0.3, zeta=3, cutoff=3.0, cutoff_type="exponential",
+                            temperature=0.8)
+    bath = oqupy.Bath(0.5 * sig("z"), corr)
+    tparams = oqupy.TempoParameters(dt=0.1, dkmax=5, epsrel=1e-6)
+    n = 4
+    chain = oqupy.SystemChain(hilbert_space_dimensions=[2] * n)
+    for s in range(n):
+        chain.add_site_hamiltonian(site=s, hamiltonian=0.3 * (s + 1) * sig("x"))
+    for s in range(n - 1):
+        for i, xyz in enumerate("xyz"):
+            chain.add_nn_hamiltonian(site=s, hamiltonian_l=0.5 * (1.0 + 0.2 * i) * sig(xyz),
+                                     hamiltonian_r=0.5 * sig(xyz))
+    params = oqupy.PtTebdParameters(dt=0.1, order=2, epsrel=1e-7)
+    amps = oqupy.AugmentedMPS([oqupy.operators.spin_dm("z-")] * n)
+    install.install()
+    try:
+        pt = oqupy.pt_tempo_compute(bath=bath, start_time=0.0, end_time=1.0,
+                                    parameters=tparams, progress_type="silent")
+        pts = [pt, None, pt, None]
+        kw = dict(initial_augmented_mps=amps, system_chain=chain, process_tensors=pts,
+                  parameters=params, dynamics_sites=[0, 1, 2, 3, (0, 2)])
+        ref = oqupy.PtTebd(**kw)
+        new = oqupy.PtTebd(backend_config={"backend": "b200"}, **kw)
+        r_ref = ref.compute(6, progress_type="silent")
+        r_new = new.compute(6, progress_type="silent")
+        assert isinstance(new._t_mps, tebd.PtTebdBackend)
+        assert not isinstance(ref._t_mps, tebd.PtTebdBackend)
+        np.testing.assert_array_equal(r_new["bond_dimensions"], r_ref["bond_dimensions"])
+        np.testing.assert_allclose(r_new["norm"], r_ref["norm"], atol=1e-9)
+        for key in [0, 1, 2, 3, (0, 2)]:
+            np.testing.assert_allclose(r_new["dynamics"][key].states,
+                                       r_ref["dynamics"][key].states, atol=1e-9)
+        a_ref, a_new = ref.get_augmented_mps(), new.get_augmented_mps()
+        for lr, ln in zip(a_ref.lambdas, a_new.lambdas):
+            np.testing.assert_allclose(np.abs(np.diag(ln) if ln.ndim == 2 else ln),
+                                       np.abs(np.diag(lr) if lr.ndim == 2 else lr), atol=1e-9)
+        # unique=True through the front-ends (degeneracy maps handed to the backends)
+        system = oqupy.System(0.5 * sig("x"))
+        rho0 = oqupy.operators.spin_dm("z+")
+        t_ref = oqupy.Tempo(system, bath, tparams, rho0, 0.0, unique=True)
+        t_new = oqupy.Tempo(system, bath, tparams, rho0, 0.0, unique=True,
+                            backend_config={"backend": "b200"})
+        assert isinstance(t_new._backend_instance, backends.TempoBackend)
+        t_ref.compute(1.0, progress_type="silent")
+        t_new.compute(1.0, progress_type="silent")
+        np.testing.assert_allclose(t_new.get_dynamics().states, t_ref.get_dynamics().states,
+                                   atol=1e-8)
+        p_ref = oqupy.PtTempo(bath, 0.0, 1.0, tparams, unique=True)
+        p_new = oqupy.PtTempo(bath, 0.0, 1.0, tparams, unique=True,
+                              backend_config={"backend": "b200"})
+        assert isinstance(p_new._backend_instance, backends.PtTempoBackend)
+        d_ref = oqupy.compute_dynamics(system, process_tensor=p_ref.get_process_tensor(
+            progress_type="silent"), initial_state=rho0, progress_type="silent")
+        d_new = oqupy.compute_dynamics(system, process_tensor=p_new.get_process_tensor(
+            progress_type="silent"), initial_state=rho0, progress_type="silent")
+        np.testing.assert_allclose(d_new.states, d_ref.states, atol=1e-9)
+    finally:
+        install.uninstall()
+    assert oqupy.pt_tebd.PtTebdBackend is install._ORIGINALS["PtTebdBackend"]

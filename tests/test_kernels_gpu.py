@@ -183,3 +183,35 @@ def test_trunc_svd_large_multichunk(m, n):
     u, svh = ops.to_host(u), ops.to_host(svh)
     ur, sr, vhr = np.linalg.svd(mat, full_matrices=False)
     np.testing.assert_allclose(u @ svh, (ur[:, :kk] * sr[:kk]) @ vhr[:kk], atol=1e-12)
+
+
+@pytest.mark.parametrize("shape,rows", [((6, 4, 5, 7), (0, 2)), ((5, 4, 9, 3), (0, 1)),
+                                        ((13, 4, 11, 17), (0, 2)), ((3, 4, 40, 30), (2, 3))])
+def test_svd_split_strides_and_parts(shape, rows):
+    """b200_svd_factor2 / b200_svd_emit_parts: a rank-4 tensor factorised in place with
+    rows = two of its legs, columns = the other two (the PT-TEBD splits,
+    pt_tebd_backend.py:487-531); U, Vh, lambda, 1/lambda separately."""
+    ops = default_ops()
+    rng = np.random.default_rng(sum(shape))
+    t = rnd(rng, *shape)
+    cols = tuple(a for a in range(4) if a not in rows)
+    strides = [int(np.prod(shape[a + 1:])) for a in range(4)]
+    m = shape[rows[0]] * shape[rows[1]]
+    n = shape[cols[0]] * shape[cols[1]]
+    mat = t.transpose(rows + cols).reshape(m, n)
+    dt = ops.from_host(t)
+    h = ops.svd_factor(dt, m, n, strides[rows[0]], strides[cols[0]], 1e-9,
+                       rin=shape[rows[1]], rsi=strides[rows[1]],
+                       cin=shape[cols[1]], csi=strides[cols[1]])
+    s_ref = np.linalg.svd(mat, compute_uv=False)
+    k = h.keep
+    assert k == ref_keep(s_ref, 1e-9)
+    u, vh = ops.empty(m, k), ops.empty(k, n)
+    lam, inv = ops.empty(k), ops.empty(k)
+    ops.svd_emit(h, u=u, u_na=1, u_so=k, u_sa=0, u_sj=1, vh=vh, lam=lam, inv_lam=inv)
+    hu, hvh, hl, hi = (ops.to_host(x) for x in (u, vh, lam, inv))
+    np.testing.assert_allclose(hl.real, s_ref[:k], atol=1e-12 * s_ref[0])
+    np.testing.assert_allclose(hl * hi, np.ones(k), atol=1e-13)
+    np.testing.assert_allclose((hu * hl) @ hvh, mat, atol=1e-11 * s_ref[0])
+    np.testing.assert_allclose(hu.conj().T @ hu, np.eye(k), atol=1e-10)
+    np.testing.assert_allclose(hvh @ hvh.conj().T, np.eye(k), atol=1e-10)
