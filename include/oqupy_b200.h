@@ -88,7 +88,11 @@ int b200_zgemm_strided(void* stream, int m, int n, int k, int nb1, int nb2,
  * b200_svd_factor2: as b200_svd_factor with two-level row and column indices,
  *   theta[i][j] at (i / rin)*rso + (i % rin)*rsi + (j / cin)*cso + (j % cin)*csi, so that
  *   any leg grouping of a rank-4 tensor is factorised in place -- the PT-TEBD splits
- *   (left_edges / right_edges of oqupy/backends/pt_tebd_backend.py:487-531).
+ *   (left_edges / right_edges of oqupy/backends/pt_tebd_backend.py:487-531).  cos_tol > 0
+ *   sets the orthogonality target |cos| of the Jacobi iteration (default 1e-11, never below
+ *   the rounding level 2 sqrt(max(m,n)) eps_mach): PT-TEBD multiplies the factors by
+ *   inverse singular values (pt_tebd_backend.py:533-559), which amplifies a residual
+ *   non-orthogonality by 1/lambda, and asks for 1e-15.
  * b200_svd_emit_parts: as b200_svd_emit; `vh` receives S*Vh (vh_unscaled = 0) or Vh
  *   (vh_unscaled = 1), `lam` / `inv_lam` (complex128[keep], may be NULL) the kept singular
  *   values and their inverses (the lambda matrices of pt_tebd_backend.py:526, 573-578).
@@ -102,8 +106,8 @@ size_t b200_svd_workspace_bytes(int m, int n);
 int b200_svd_factor(void* stream, const void* theta, int m, int n, int64_t rs,
                     int64_t cs, double eps, void* work, int32_t* info_host);
 int b200_svd_factor2(void* stream, const void* theta, int m, int n, int rin, int64_t rso,
-                     int64_t rsi, int cin, int64_t cso, int64_t csi, double eps, void* work,
-                     int32_t* info_host);
+                     int64_t rsi, int cin, int64_t cso, int64_t csi, double eps, double cos_tol,
+                     void* work, int32_t* info_host);
 int b200_svd_emit_parts(void* stream, const void* work, int m, int n, int keep, void* u,
                         int u_na, int64_t u_so, int64_t u_sa, int64_t u_sj, void* vh,
                         int vh_unscaled, void* lam, void* inv_lam);

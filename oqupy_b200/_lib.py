@@ -79,8 +79,8 @@ def load_library():
                                   c_int64, c_int64, c_int64, c_void_p]
     lib.b200_svd_factor2.restype = c_int
     lib.b200_svd_factor2.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int64,
-                                     c_int64, c_int, c_int64, c_int64, c_double, c_void_p,
-                                     c_void_p]
+                                     c_int64, c_int, c_int64, c_int64, c_double, c_double,
+                                     c_void_p, c_void_p]
     lib.b200_svd_emit_parts.restype = c_int
     lib.b200_svd_emit_parts.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                         c_int, c_int64, c_int64, c_int64, c_void_p, c_int,
@@ -203,13 +203,15 @@ class CudaOps:
             sp, s1, s2, 1 if accumulate else 0)
         self._check(code, "b200_zgemm_strided")
 
-    def svd_factor(self, theta, m, n, rs, cs, eps, off=0, rin=1, rsi=0, cin=1, csi=0):
-        """theta[i][j] at (i // rin)*rs + (i % rin)*rsi + (j // cin)*cs + (j % cin)*csi."""
+    def svd_factor(self, theta, m, n, rs, cs, eps, off=0, rin=1, rsi=0, cin=1, csi=0,
+                   cos_tol=0.0):
+        """theta[i][j] at (i // rin)*rs + (i % rin)*rsi + (j // cin)*cs + (j % cin)*csi;
+        ``cos_tol`` > 0: orthogonality target of the iteration (default 1e-11)."""
         nbytes = self.lib.b200_svd_workspace_bytes(m, n)
         work = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         code = self.lib.b200_svd_factor2(
             self._stream(), self._ptr(theta, off), m, n, rin, rs, rsi, cin, cs, csi,
-            -1.0 if eps is None else float(eps), work.data_ptr(),
+            -1.0 if eps is None else float(eps), float(cos_tol), work.data_ptr(),
             self._info.data_ptr())
         self._check(code, "b200_svd_factor")
         torch.cuda.current_stream(self.device).synchronize()

@@ -32,6 +32,7 @@
 //     U[:, :keep] and S*Vh[:keep] in the layouts the MPS engine asks for.
 #include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -219,6 +220,7 @@ __device__ __forceinline__ int pair_index(int col, int hb) {
 struct InnerShared {
   double gr[PB][GP], gi[PB][GP];   // Hermitian working matrix
   double rc[BC], rsr[BC], rsi[BC]; // per pair of the round: c, s e^{i phi}
+  double rdel[BC];                 // t |g_pq|: what the rotation moves between the two norms
   int ract[BC];
   int rank[PB];                    // position of column c after sorting by norm
   unsigned mask;                   // rounds that hold a violating pair
@@ -288,6 +290,10 @@ __device__ void inner_sweep(InnerShared& S, unsigned mask, double floor2, double
       S.rc[lane] = act ? w * ic : 1.0;
       S.rsr[lane] = act ? xr * kk : 0.0;
       S.rsi[lane] = act ? xi * kk : 0.0;
+      // g_pp' = g_pp - d, g_qq' = g_qq + d with d = sign(h) |g_pq|^2 / (r + |h|)
+      // (Rutishauser's form: no cancellation against the larger norm, so a small column
+      // keeps its RELATIVE accuracy next to a large one)
+      S.rdel[lane] = act ? ((h >= 0.0) ? 0.5 : -0.5) * mag2 * inv_r * ic * ic : 0.0;
     }
     __syncthreads();
     if (gthread) {
@@ -314,6 +320,8 @@ __device__ void inner_sweep(InnerShared& S, unsigned mask, double floor2, double
         double n11r = ca * t11r + (sar * t01r + sai * t01i);
         double n11i = ca * t11i + (sar * t01i - sai * t01r);
         if (a == b) {            // diagonal block: real diagonal, annihilated off-diagonal
+          const double d = S.rdel[a];
+          n00r = g00r - d; n11r = g11r + d;
           n00i = 0.0; n11i = 0.0;
           n01r = 0.0; n01i = 0.0; n10r = 0.0; n10i = 0.0;
         }
@@ -531,7 +539,7 @@ jacobi_kernel(const cplx* __restrict__ theta, long long rs, long long cs,
               Header* __restrict__ hdr, int32_t* __restrict__ info, int p, int q, int nb,
               int Rx, int Rw, int RSx, int RSw, int SE, int transposed, int minmn,
               double tol, double eps, double neg_rel, int rin, long long rsi, int cin,
-              long long csi) {
+              long long csi, double kappa0) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ InnerShared S;
   __shared__ double s_red[JT / 32];
@@ -616,7 +624,7 @@ jacobi_kernel(const cplx* __restrict__ theta, long long rs, long long cs,
     int my_rot = 0;
     // absolute floor: 8 eps ||X||_F, doubled every sweep after FLOOR_GROW_AFTER so that
     // the iteration always terminates
-    double kappa = 8.0;
+    double kappa = kappa0;
     for (int k = FLOOR_GROW_AFTER; k < sweep; ++k) kappa *= 2.0;
     const double floor_ = kappa * 2.220446049250313e-16 * fro;
     const double floor2 = floor_ * floor_;
@@ -952,12 +960,12 @@ extern "C" size_t b200_svd_workspace_bytes(int m, int n) {
 extern "C" int b200_svd_factor(void* stream_, const void* theta, int m, int n,
                                int64_t rs, int64_t cs, double eps, void* work,
                                int32_t* info_host) {
-  return b200_svd_factor2(stream_, theta, m, n, 1, rs, 0, 1, cs, 0, eps, work, info_host);
+  return b200_svd_factor2(stream_, theta, m, n, 1, rs, 0, 1, cs, 0, eps, 0.0, work, info_host);
 }
 
 extern "C" int b200_svd_factor2(void* stream_, const void* theta, int m, int n, int rin,
                                 int64_t rso, int64_t rsi, int cin, int64_t cso, int64_t csi,
-                                double eps, void* work, int32_t* info_host) {
+                                double eps, double cos_tol, void* work, int32_t* info_host) {
   cudaStream_t stream = (cudaStream_t)stream_;
   const int64_t rs = rso, cs = cso;
   if (!theta || !work || !info_host || m <= 0 || n <= 0 || rin < 1 || cin < 1) {
@@ -1001,14 +1009,27 @@ extern "C" int b200_svd_factor2(void* stream_, const void* theta, int m, int n, 
   int minmn = (m < n) ? m : n;
   // relative orthogonality target |cos| <= 1e-11 (singular values are second order in
   // it); never tighter than the rounding level of a length-p dot product
+  // (cos_tol > 0 overrides the 1e-11: PT-TEBD multiplies the factors by inverse singular
+  // values, which amplifies the residual non-orthogonality of U by 1/lambda)
   double tol = 2.0 * sqrt((double)L.p) * 2.220446049250313e-16;
-  if (tol < 1e-11) tol = 1e-11;
+  const double want = (cos_tol > 0.0) ? cos_tol : 1e-11;
+  if (tol < want) tol = want;
   // columns below 1e-2*eps*||X||_F can never be kept nor change the rank decision
   double neg_rel = (eps > 0.0) ? 1e-2 * eps : 0.0;
   long long rsi_ = rsi, csi_ = csi;
+  // absolute floor of the convergence test, kappa0 * eps_mach * ||X||_F.  TEMPO only needs
+  // absolute accuracy (8).  With cos_tol > 0 (PT-TEBD) the factors are later multiplied by
+  // inverse singular values, so small kept columns need RELATIVE accuracy: floor 0.01 (pure
+  // rounding noise only) and no loosely-orthogonalised negligible columns.  Measured on the
+  // config-4 shape at eps = 1e-5: deviation from the LAPACK oracle 6.6e-6 (8), 5.8e-8 (0.125),
+  // 5e-10 (0.01) = the oracle's own reproducibility.
+  double kappa0 = (cos_tol > 0.0) ? 0.01 : 8.0;
+  if (cos_tol > 0.0) neg_rel = 0.0;
+  if (const char* e = getenv("B200_SVD_KAPPA")) kappa0 = atof(e);
+  if (const char* e = getenv("B200_SVD_NEGREL")) neg_rel = atof(e) * ((eps > 0.0) ? eps : 0.0);
   void* args[] = {&th, &rs_, &cs_, &y, &gpart, &ctrl, &sig2, &sval, &perm, &hdr,
                   &info_host, &p, &q, &nb, &Rx, &Rw, &RSx, &RSw, &SE, &tr, &minmn, &tol, &eps,
-                  &neg_rel, &rin, &rsi_, &cin, &csi_};
+                  &neg_rel, &rin, &rsi_, &cin, &csi_, &kappa0};
   const int grid = L.SE * L.R;
   b200::profile_begin(stream);
   B200_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)jacobi_kernel, dim3(grid), dim3(JT),

@@ -19,6 +19,10 @@ import numpy as np
 from ._lib import View, default_ops
 
 CDTYPE = np.complex128
+# Orthogonality target of the truncated SVDs.  The gate update multiplies the factors by
+# inverse singular values (pt_tebd_backend.py:533-559): a residual |cos| between columns of U
+# is amplified by 1/lambda <= 1/eps, so the TEMPO default (1e-11) is not enough here.
+COS_TOL = 1e-15
 
 
 def _isqrt(x):
@@ -143,7 +147,7 @@ class PtTebdBackend:
         #    (lam_l Gam_l)[(L,b),(p,M)] = U1 [(L,b),k1] . S1 Vh1 [k1,(p,M)]
         left = self._scale_rows(gam_l, self._lams[sl], nl, d2l * pl * nm)
         h1 = ops.svd_factor(left, nl * pl, d2l * nm, d2l * pl * nm, pl * nm, eps,
-                            rin=pl, rsi=nm, cin=nm, csi=1)
+                            rin=pl, rsi=nm, cin=nm, csi=1, cos_tol=COS_TOL)
         k1 = h1.keep
         u1 = ops.empty(nl, pl, k1)
         svh1 = ops.empty(k1, d2l, nm)
@@ -152,7 +156,7 @@ class PtTebdBackend:
         # -- and off the right site (:498-507): (Gam_r lam_r)[(M,p),(b,R)] = U2 S2 . Vh2.
         #    The transposed matrix is factorised, so that U' = Vh2^T and S Vh' = (U2 S2)^T
         right = self._scale_cols(gam_r, self._lams[sr + 1], nm * d2r * pr, nr)
-        h2 = ops.svd_factor(right, pr * nr, nm * d2r, 1, pr * nr, eps)
+        h2 = ops.svd_factor(right, pr * nr, nm * d2r, 1, pr * nr, eps, cos_tol=COS_TOL)
         k2 = h2.keep
         right_temp = ops.empty(k2, pr, nr)
         us2t = ops.empty(k2, nm, d2r)
@@ -167,7 +171,7 @@ class PtTebdBackend:
                  View(x, row=k2, col=1, b1=d2l * d2r * k2),
                  View(theta, row=k2, col=1, b1=na * nb * k2), nb1=k1)
         # -- split theta (:521-531): rows (k1, a), columns (b, k2)
-        h3 = ops.svd_factor(theta, k1 * na, nb * k2, nb * k2, 1, eps)
+        h3 = ops.svd_factor(theta, k1 * na, nb * k2, nb * k2, 1, eps, cos_tol=COS_TOL)
         nj = h3.keep
         u3 = ops.empty(k1, na, nj)
         vh3 = ops.empty(nj, nb, k2)

@@ -61,7 +61,8 @@ class HostModelOps:
         else:
             cv.copy_(res)
 
-    def svd_factor(self, theta, m, n, rs, cs, eps, off=0, rin=1, rsi=0, cin=1, csi=0):
+    def svd_factor(self, theta, m, n, rs, cs, eps, off=0, rin=1, rsi=0, cin=1, csi=0,
+                   cos_tol=0.0):
         self.launches += 4
         assert m % rin == 0 and n % cin == 0
         mat = torch.as_strided(theta, (m // rin, rin, n // cin, cin), (rs, rsi, cs, csi),

@@ -15,8 +15,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import oqupy_b200 as ob  # noqa: E402
-from conftest import golden_callables, load_golden  # noqa: E402
+from conftest import golden_callables, load_golden, tebd_fixture  # noqa: E402
 from oracle import tempo_np as onp  # noqa: E402
+from oracle import tebd_np  # noqa: E402
 
 HBM_GBS = 6533.8
 try:
@@ -164,6 +165,83 @@ def dynamics_rows():
          max_abs_err_vs_oracle=float(np.abs(out2 - ref2).max()))
 
 
+def tebd_row(n_sites=16):
+    """SURVEY 8a A7 / BASELINE configs[3] shape: PT-TEBD chain of 16 spins, a process tensor
+    on EVERY site.  Inputs: the gates and the process tensor of the reference's test F
+    (tests/golden/pt_tebd_F2.npz; chi_pt up to 51), the bond gates tiled to 16 sites."""
+    from types import SimpleNamespace
+    g = load_golden("pt_tebd_F2")
+    gammas, lambdas, layers, _, mpos, caps = tebd_fixture(g)
+    # eps_tebd = 1e-5 (BASELINE configs[3]); 4 steps: the bond dimension reaches 74 and
+    # chi_pt 51, the splits are tall (3800 x 300) and the CPU oracle needs ~30 s
+    eps, steps = 1.0e-5, 4
+    by_bond = [{} for _ in layers]
+    for li, layer in enumerate(layers):
+        for sites, tensors in layer:
+            by_bond[li][sites[0]] = tensors
+    big_layers = []
+    for li, layer in enumerate(layers):
+        parity = layer[0][0][0] % 2
+        src = sorted(by_bond[li])
+        big_layers.append([((b, b + 1), by_bond[li][src[(b // 2) % len(src)]])
+                           for b in range(parity, n_sites - 1, 2)])
+    gam = [gammas[0]] * n_sites
+    lam = [lambdas[0]] * (n_sites - 1)
+    # --- device
+    ops = ob.default_ops()
+    pt = ob.DeviceProcessTensor(2, dt=float(g["dt"]), ops=ops)
+    for k, t in enumerate(mpos):
+        pt.set_mpo_tensor(k, t)
+    pt.compute_caps()
+    gate_layers = [SimpleNamespace(gates=[SimpleNamespace(sites=list(s), tensors=list(t))
+                                          for s, t in layer]) for layer in big_layers]
+
+    def run_device(steps=steps):
+        be = ob.PtTebdBackend(gam, lam, eps, {}, ops=ops)
+        nsvd0 = ops.launch_count()
+        for step in range(1, steps + 1):
+            for layer in gate_layers:
+                be.apply_nn_gate_layer(layer)
+            be.apply_process_tensors(step, [pt] * n_sites)
+            for layer in gate_layers:
+                be.apply_nn_gate_layer(layer)
+            be.compute_traces(step, [pt] * n_sites)
+        rho = [be.get_density_matrix([s]) for s in range(n_sites)]
+        return be, np.array(rho), ops.launch_count() - nsvd0
+
+    run_device(steps=2)          # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    be, rho, launches = run_device()
+    torch.cuda.synchronize()
+    gpu_s = time.perf_counter() - t0
+    # --- CPU oracle
+    t0 = time.perf_counter()
+    orc = tebd_np.PtTebdOracle(gam, lam, eps)
+    for step in range(1, steps + 1):
+        for layer in big_layers:
+            orc.apply_nn_gate_layer(layer)
+        orc.apply_process_tensors(step, [mpos[step - 1]] * n_sites)
+        for layer in big_layers:
+            orc.apply_nn_gate_layer(layer)
+        orc.compute_traces([caps[step]] * n_sites)
+    cpu_s = time.perf_counter() - t0
+    rho_ref = np.array([orc.get_density_matrix([s]) for s in range(n_sites)])
+    gates_per_step = 2 * sum(len(layer) for layer in big_layers)
+    emit(row="A7 PT-TEBD step (config 4 shape: 16 spins, a PT on every site)",
+         metric="PT-TEBD steps/s", gpu=steps / gpu_s, cpu_oracle=steps / cpu_s,
+         workload=f"{n_sites} sites, {gates_per_step} nn gates = {3 * gates_per_step} truncated "
+                  f"SVDs per step, {steps} steps, eps={eps}, chi_pt<=51",
+         bond_dims_gpu=[int(x) for x in be.get_bond_dimensions()],
+         bond_dims_oracle=[int(x) for x in orc.get_bond_dimensions()],
+         max_abs_err_vs_oracle=float(np.abs(rho - rho_ref).max()), gpu_launches=launches,
+         bound="latency (a chain of small dependent SVDs per gate; gates of a layer are "
+               "independent and could run on separate streams)")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "tebd":
+        tebd_row()
+        sys.exit(0)
     tempo_c1()
     dynamics_rows()
