@@ -25,10 +25,10 @@ def main():
     rec = []
     orig = ops.svd_factor
 
-    def timed(theta, m, n, rs, cs, eps, off=0):
+    def timed(theta, m, n, rs, cs, eps, off=0, **kw):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        h = orig(theta, m, n, rs, cs, eps, off)
+        h = orig(theta, m, n, rs, cs, eps, off, **kw)
         torch.cuda.synchronize()
         ms = (time.perf_counter() - t0) * 1e3
         pc = ops.svd_phase_cycles(h)
