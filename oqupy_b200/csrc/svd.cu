@@ -66,7 +66,17 @@ struct Header {        // lives at the start of the workspace (device)
 struct Layout {
   size_t header, ctrl, ctrl_bytes, blkmax, sig2, sval, perm, gpart, y, total;
   int p, q, T, nb, S, R, Rx, Rw, RSx, RSw, SE, transposed;
+  int U;     // > 0: cost-balanced slices of U units (an X row costs 2, a W row 1)
 };
+
+// Cost-balanced slicing of the stacked rows [X ; W]: an X row pays a Gram pass and an apply
+// pass (2 units), a W row only the apply pass (1 unit).  Row reached after `c` cost units,
+// aligned down to a multiple of 4 (DMMA fragments).
+__host__ __device__ inline int cost_row(long long c, int p, int T) {
+  long long r = (c <= 2LL * p) ? (c >> 1) : (long long)p + (c - 2LL * p);
+  r &= ~3LL;
+  return (int)((r > T) ? T : r);
+}
 
 __host__ __device__ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -117,7 +127,21 @@ __host__ Layout make_layout(int m, int n) {
     if (rx > max_r - 1) rx = max_r - 1;
     L.Rx = rx; L.Rw = max_r - rx;
   }
-  if (L.Rw == 0) {
+  L.U = 0;
+  if (max_r > 1 && want_x + want_w > max_r && !getenv("B200_SVD_OLD_SLICES")) {
+    // few slices per slot (wide operands): balance them by cost; ONE slice may hold the
+    // X/W boundary (its X rows come first)
+    const long long cost = 2LL * L.p + L.q;
+    long long u = (cost + max_r - 1) / max_r;
+    u = (u + 7) & ~7LL;
+    L.U = (int)u;
+    L.R = (int)((cost + u - 1) / u);
+    L.Rx = 0;
+    for (int r = 0; r < L.R; ++r)
+      if (cost_row((long long)r * u, L.p, L.T) < L.p) L.Rx = r + 1;
+    L.Rw = L.R - L.Rx;
+    L.RSx = L.RSw = 0;
+  } else if (L.Rw == 0) {
     L.RSx = L.T; L.RSw = 0;
   } else {
     L.RSx = (((L.p + L.Rx - 1) / L.Rx) + 3) & ~3;
@@ -126,6 +150,7 @@ __host__ Layout make_layout(int m, int n) {
     L.Rw = (L.q + L.RSw - 1) / L.RSw;
   }
   L.R = L.Rx + L.Rw;
+  if (L.R < 1) L.R = 1;
   L.SE = L.S;                       // slots resident at once
   if (L.SE * L.R > sms) L.SE = sms / L.R;
   if (L.SE < 1) L.SE = 1;
@@ -252,7 +277,7 @@ __device__ __forceinline__ double inner_threshold(double a, double b, double flo
 //     __shfl_xor away.  (The sweep is bound by shared-memory traffic; this halves it.)
 // R = [[c, se], [-conj(se), c]] acting on columns (p, q = p XOR k).
 __device__ void inner_sweep(InnerShared& S, unsigned mask, double floor2, double neg2,
-                            cplx* __restrict__ sj) {
+                            cplx* __restrict__ sj, int npass) {
   const int t = threadIdx.x;
   const bool gthread = t < 256;
   const bool jthread = (t >= 256) && (t < 384);
@@ -262,6 +287,7 @@ __device__ void inner_sweep(InnerShared& S, unsigned mask, double floor2, double
   cplx jv[8];
 #pragma unroll
   for (int r = 0; r < 8; ++r) jv[r] = make_double2((jthread && jrow0 + r == lane) ? 1.0 : 0.0, 0.0);
+  for (int pass = 0;; ++pass) {
   while (mask) {
     const int round = __ffs(mask) - 1;
     mask &= mask - 1;
@@ -351,6 +377,31 @@ __device__ void inner_sweep(InnerShared& S, unsigned mask, double floor2, double
       }
     }
     __syncthreads();
+  }
+  if (pass + 1 >= npass) break;
+  // another pass over the rounds that still hold a pair above the rotation threshold
+  // (large operands: a fully diagonalised block pair per stage saves outer sweeps)
+  if (t == 0) S.mask = 0u;
+  __syncthreads();
+  {
+    unsigned mm = 0u;
+#pragma unroll
+    for (int e = t; e < PB * PB; e += JT) {
+      const int i = e >> 5, j = e & 31;
+      if (i < j) {
+        const double ga = S.gr[i][i], gb = S.gr[j][j];
+        const double xr = S.gr[i][j], xi = S.gi[i][j];
+        if (xr * xr + xi * xi > inner_threshold(ga, gb, floor2, neg2) && fmax(ga, gb) > 0.0)
+          mm |= 1u << round_of_pair(i, j);
+      }
+    }
+    mm = __reduce_or_sync(0xffffffffu, mm);
+    if ((t & 31) == 0 && mm) atomicOr(&S.mask, mm);
+  }
+  __syncthreads();
+  mask = S.mask;
+  __syncthreads();
+  if (!mask) break;
   }
   // sort columns by descending norm^2 (the diagonal of the rotated Gram matrix)
   {
@@ -542,7 +593,8 @@ jacobi_kernel(const cplx* __restrict__ theta, long long rs, long long cs,
               Header* __restrict__ hdr, int32_t* __restrict__ info, int p, int q, int nb,
               int Rx, int Rw, int RSx, int RSw, int SE, int transposed, int minmn,
               double tol, double eps, double neg_rel, int rin, long long rsi, int cin,
-              long long csi, double kappa0, double* __restrict__ blkmax, double drop_rel) {
+              long long csi, double kappa0, double* __restrict__ blkmax, double drop_rel,
+              int npass, int U) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ InnerShared S;
   __shared__ double s_red[JT / 32];
@@ -610,13 +662,21 @@ jacobi_kernel(const cplx* __restrict__ theta, long long rs, long long cs,
   const int r_slice = blockIdx.x % R;
   const int s_first = blockIdx.x / R;
   int row0, nrows, xrows;
-  if (Rw == 0) { row0 = 0; nrows = T; xrows = p; }
+  if (U > 0) {
+    row0 = cost_row((long long)r_slice * U, p, T);
+    const int row1 = (r_slice == R - 1) ? T : cost_row((long long)(r_slice + 1) * U, p, T);
+    nrows = row1 - row0;
+    xrows = max(0, min(nrows, p - row0));
+  }
+  else if (Rw == 0) { row0 = 0; nrows = T; xrows = p; }
   else if (r_slice < Rx) { row0 = r_slice * RSx; nrows = min(RSx, p - row0); xrows = nrows; }
   else { row0 = p + (r_slice - Rx) * RSw; nrows = min(RSw, T - row0); xrows = 0; }
   const bool single_chunk = nrows <= CHUNK_ROWS;
   // tall X slices form their partial Gram matrix on the fp64 tensor cores (slices that
   // mix X and W rows -- only the single-slice layout -- keep the FMA path)
-  const bool gram_tc = (Rw > 0) && (xrows >= DMMA_MIN_ROWS);
+  // (a slice that holds the X/W boundary needs its X part in whole 4-row fragments)
+  const bool gram_tc = (R > 1) && (xrows >= DMMA_MIN_ROWS) &&
+                       (xrows == nrows || (xrows & 3) == 0);
   const bool leader = (r_slice == 0);
 
   int sweeps_done = 0, total_rot = 0, status = 1;
@@ -774,7 +834,7 @@ jacobi_kernel(const cplx* __restrict__ theta, long long rs, long long cs,
         const int need = S.viol;
         PHASE(4)
         if (need) {
-          inner_sweep(S, S.mask, floor2, neg2, sj);
+          inner_sweep(S, S.mask, floor2, neg2, sj, npass);
           PHASE(5)
           if (leader) ++my_rot;
           __syncthreads();
@@ -1052,6 +1112,7 @@ extern "C" int b200_svd_factor2(void* stream_, const void* theta, int m, int n, 
   }
   const cplx* th = (const cplx*)theta;
   long long rs_ = rs, cs_ = cs;
+  int U = L.U;
   int p = L.p, q = L.q, nb = L.nb, Rx = L.Rx, Rw = L.Rw, RSx = L.RSx, RSw = L.RSw, SE = L.SE,
       tr = L.transposed;
   int minmn = (m < n) ? m : n;
@@ -1076,11 +1137,18 @@ extern "C" int b200_svd_factor2(void* stream_, const void* theta, int m, int n, 
   double drop_rel = 1e-3 * neg_rel;      // 1e-5 * eps * ||X||_F
   if (const char* e = getenv("B200_SVD_DROP")) drop_rel = atof(e) * neg_rel;
   double* blkmax = (double*)(base + L.blkmax);
+  // inner passes per stage: a second pass (block pair fully diagonalised) pays off where
+  // the stage is bound by the tensor-core Gram / apply passes, i.e. for wide operands
+  int npass = 1, npass_minq = 1 << 30;
+  if (const char* e = getenv("B200_SVD_NPASS")) npass = atoi(e);
+  if (const char* e = getenv("B200_SVD_NPASS_MINQ")) npass_minq = atoi(e);
+  if (L.q < npass_minq && !getenv("B200_SVD_NPASS_ALL")) npass = 1;
   if (const char* e = getenv("B200_SVD_KAPPA")) kappa0 = atof(e);
   if (const char* e = getenv("B200_SVD_NEGREL")) neg_rel = atof(e) * ((eps > 0.0) ? eps : 0.0);
   void* args[] = {&th, &rs_, &cs_, &y, &gpart, &ctrl, &sig2, &sval, &perm, &hdr,
                   &info_host, &p, &q, &nb, &Rx, &Rw, &RSx, &RSw, &SE, &tr, &minmn, &tol, &eps,
-                  &neg_rel, &rin, &rsi_, &cin, &csi_, &kappa0, &blkmax, &drop_rel};
+                  &neg_rel, &rin, &rsi_, &cin, &csi_, &kappa0, &blkmax, &drop_rel,
+                  &npass, &U};
   const int grid = L.SE * L.R;
   b200::profile_begin(stream);
   B200_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)jacobi_kernel, dim3(grid), dim3(JT),

@@ -32,7 +32,7 @@ def main():
         torch.cuda.synchronize()
         ms = (time.perf_counter() - t0) * 1e3
         pc = ops.svd_phase_cycles(h)
-        rec.append((m, n, h.keep, h.sweeps, ms, pc))
+        rec.append((m, n, h.keep, h.sweeps, ms, pc, h.rotations))
         return h
 
     ops.svd_factor = timed
@@ -45,7 +45,9 @@ def main():
     rec_sorted = sorted(rec, key=lambda r: -r[4])
     print("top 15 (m, n, keep, sweeps, ms):")
     for r in rec_sorted[:15]:
-        print("  ", r[0], r[1], r[2], r[3], round(r[4], 2), "phase kcyc", [round(c / 1e3) for c in r[5][:10]], "stages", r[5][15])
+        q = min(r[0], r[1]); nb = (q + 15) // 16; nb += nb & 1
+        print("  ", r[0], r[1], r[2], r[3], round(r[4], 2), "phase kcyc", [round(c / 1e3) for c in r[5][:10]], "stages", r[5][15],
+              "rotated stage-slots", r[6], "of", r[3] * (nb - 1) * (nb // 2))
     print("typical mid-size (every 25th call):")
     for r in rec[5::25]:
         print("  ", r[0], r[1], r[2], r[3], round(r[4], 3), "phase kcyc", [round(c / 1e3) for c in r[5][:10]], "stages", r[5][15])
