@@ -165,6 +165,29 @@ int b200_chain_shape(void* chain, int i, int32_t* out3);
 int b200_chain_read(void* chain, int i, void* dev_dst);
 int b200_chain_svd_sweep(void* chain, int from_index, int to_index, double eps);
 int b200_chain_pt_zip_up_left(void* chain, const b200_pt_site* mpo, int n_mpo, double eps);
+/* One whole TEMPO time step on the chain (oqupy/backends/tempo_backend.py:439-575):
+ * first half propagator on the newest site (:521-529), sum out the oldest leg beyond the
+ * memory cut-off (:531-537), mps.zip_up(mpo, direction="right") (:539-547 -> node_array.py:
+ * 482-552) with the implicit influence MPO (tempo_backend.py:419,426)
+ *     kind START  first aligned site, west leg summed:  mat[s,e] = infl[s,e] * sum_west[e]
+ *     kind MID    B[w,n,s,e] = d_we d_ns mat[s,e]
+ *     kind DENSE  dk = 0 site incl. the unitary transform, mat[(w,n),(s,e)] (rows x cols),
+ *                 nw = size of its west leg (1 when it is the first aligned site), ns = size of s
+ * svd_sweep right-to-left (:549-553), append the second half propagator `p2site`
+ * ((d2,d2,1) = prop_2^T, :555-558) and the read-out of the state (:560-573) into
+ * `state_out` (device, d2).  p1 is prop_1 (d2 x d2, row-major); sum_north complex128. */
+#define B200_TEMPO_START 0
+#define B200_TEMPO_MID 1
+#define B200_TEMPO_DENSE 2
+typedef struct {
+  int kind;
+  int rows, cols;
+  int nw, ns;
+  const void* mat; /* device, complex128, row-major */
+} b200_tempo_site;
+int b200_chain_tempo_step(void* chain, const b200_tempo_site* mpo, int n_mpo, const void* p1,
+                          const void* p2site, const void* sum_north, int d2, double eps,
+                          void* state_out);
 /* counters since the last reset: truncated SVDs, Jacobi sweeps, D2H bytes (keep read-backs) */
 int b200_chain_stats(void* chain, uint64_t* nsvd, uint64_t* sweeps, uint64_t* d2h_bytes,
                      int reset);

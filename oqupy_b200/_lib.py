@@ -22,7 +22,8 @@ EXPORTS = [
     "b200_dyn_step", "b200_caps_step", "b200_dyn_run", "b200_dyn_run_workspace_bytes",
     "b200_chain_create", "b200_chain_destroy", "b200_chain_len", "b200_chain_push",
     "b200_chain_shape", "b200_chain_read", "b200_chain_svd_sweep",
-    "b200_chain_pt_zip_up_left", "b200_chain_stats", "b200_chain_log",
+    "b200_chain_pt_zip_up_left", "b200_chain_tempo_step", "b200_chain_stats",
+    "b200_chain_log",
 ]
 
 
@@ -40,7 +41,13 @@ class _PtSite(Structure):
                 ("north_map", POINTER(c_int32)), ("west_map", POINTER(c_int32))]
 
 
+class _TempoSite(Structure):
+    _fields_ = [("kind", c_int), ("rows", c_int), ("cols", c_int), ("nw", c_int),
+                ("ns", c_int), ("mat", c_void_p)]
+
+
 PT_KINDS = {"first": 0, "mid": 1, "last": 2, "closed": 3}
+TEMPO_KINDS = {"start": 0, "mid": 1, "dense": 2}
 
 _lib = None
 
@@ -119,6 +126,9 @@ def load_library():
     lib.b200_chain_svd_sweep.argtypes = [c_void_p, c_int, c_int, c_double]
     lib.b200_chain_pt_zip_up_left.restype = c_int
     lib.b200_chain_pt_zip_up_left.argtypes = [c_void_p, POINTER(_PtSite), c_int, c_double]
+    lib.b200_chain_tempo_step.restype = c_int
+    lib.b200_chain_tempo_step.argtypes = [c_void_p, POINTER(_TempoSite), c_int, c_void_p,
+                                          c_void_p, c_void_p, c_int, c_double, c_void_p]
     lib.b200_chain_stats.restype = c_int
     lib.b200_chain_stats.argtypes = [c_void_p, POINTER(c_uint64), POINTER(c_uint64),
                                      POINTER(c_uint64), c_int]
@@ -378,6 +388,20 @@ class NativeChain:
         self.ops._check(self.lib.b200_chain_pt_zip_up_left(c_void_p(self.h), arr, len(mpo),
                                                            float(eps)),
                         "b200_chain_pt_zip_up_left")
+
+    def tempo_step(self, mpo, p1, p2site, sum_north, d2, eps, state_out):
+        """One whole TEMPO time step (b200_chain_tempo_step); mpo: list of chain.TempoSite."""
+        arr = (_TempoSite * len(mpo))()
+        for k, site in enumerate(mpo):
+            arr[k].kind = TEMPO_KINDS[site.kind]
+            arr[k].rows, arr[k].cols = int(site.mat.shape[0]), int(site.mat.shape[1])
+            arr[k].nw = 0 if site.nw is None else int(site.nw)
+            arr[k].ns = 0 if site.ns is None else int(site.ns)
+            arr[k].mat = site.mat.data_ptr()
+        self.ops._check(self.lib.b200_chain_tempo_step(
+            c_void_p(self.h), arr, len(mpo), p1.data_ptr(), p2site.data_ptr(),
+            sum_north.data_ptr(), int(d2), float(eps), state_out.data_ptr()),
+            "b200_chain_tempo_step")
 
     def stats(self, reset=False):
         """(truncated SVDs, Jacobi sweeps, D2H bytes) since the last reset."""

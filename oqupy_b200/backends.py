@@ -217,6 +217,12 @@ class BaseTempoBackend:
         self._dim = dim
         self._ops = default_ops() if ops is None else ops
         self._mps = None
+        # device: the whole time step is ONE C-ABI call on the native chain engine
+        # (b200_chain_tempo_step); the Python chain below is the readable specification
+        # (OQUPY_B200_PYCHAIN=1, and the CPU-only host-logic tests)
+        self._native = (getattr(self._ops, "name", "") == "cuda"
+                        and os.environ.get("OQUPY_B200_PYCHAIN", "0") != "1")
+        self._chain = None
         self._infl = None        # influence matrices by dk (host, d2 x d2)
         self._dense0 = None      # (w, n, s, e) dk=0 site incl. unitary transform
 
@@ -263,6 +269,10 @@ class BaseTempoBackend:
         self._sn_dev = ops.from_host(self._sum_north)
         self._d2 = d2
         self._mps = [ops.from_host(self._initial_state.reshape(1, d2, 1))]
+        if self._native:
+            self._chain = NativeChain(ops)
+            self._chain.push(self._mps[0])
+            self._mps = None
 
     def _mid_site(self, dk, start):
         key = (dk, start)
@@ -301,6 +311,13 @@ class BaseTempoBackend:
                 mpo.append(TempoSite("start", ops.from_host(mat)))
             else:
                 mpo.append(self._mid_site(dk, pos == 0))
+        if self._native:
+            state = ops.empty(1, d2)
+            self._chain.tempo_step(
+                mpo, ops.from_host(prop_1),
+                ops.from_host(np.asarray(prop_2, dtype=CDTYPE).T.reshape(d2, d2, 1)),
+                self._sn_dev, d2, self._epsrel, state)
+            return ops.to_host(state).reshape(-1)
         mps = self._mps
         # -- first half propagator on the newest site (:521-529)
         last = mps[-1]
@@ -345,6 +362,8 @@ class BaseTempoBackend:
         return ops.to_host(state).reshape(-1)
 
     def get_bond_dimensions(self):
+        if self._native:
+            return [self._chain.shape(k)[2] for k in range(len(self._chain) - 1)]
         return [int(t.shape[2]) for t in self._mps[:-1]]
 
 

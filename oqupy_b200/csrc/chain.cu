@@ -390,3 +390,153 @@ int b200_chain_pt_zip_up_left(void* h, const b200_pt_site* mpo, int nb, double e
 }
 
 }  // extern "C"
+
+// mps.zip_up(mpo, left_index=0, right_index=-1, direction="right") with the implicit TEMPO
+// influence MPO (oqupy/backends/tempo_backend.py:539-547 -> node_array.py:482-552):
+//   Theta[(k,s),(r,e)] = M[s,e] sum_l carry[k,l,e] A[l,s,r];  new site = U as (k, s, j),
+//   carry' = S Vh as (j, r, e); the last (dk = 0) site is dense and takes the carry.
+static int tempo_zip_up_right(Chain* c, const b200_tempo_site* mpo, int nb, double eps) {
+  if (nb != (int)c->sites.size()) {
+    b200::set_error("tempo_zip_up_right: MPO and MPS lengths differ");
+    return B200_EINVAL;
+  }
+  cplx* carry = nullptr;
+  int ck = 0, cl = 0, ce = 0;            // carry (k, l, e)
+  for (int ib = 0; ib < nb; ++ib) {
+    Site a = c->sites[ib];
+    const int nl = a.dl, nn = a.da, nr = a.dr;
+    const b200_tempo_site& site = mpo[ib];
+    const cplx* mat = (const cplx*)site.mat;
+    if (ib == nb - 1) {                  // dense dk = 0 site, no SVD
+      if (site.kind != B200_TEMPO_DENSE || nr != 1) {
+        b200::set_error("tempo_zip_up_right: last site must be dense");
+        return B200_EINVAL;
+      }
+      const int nw = site.nw, nse = site.cols, ns = site.ns;
+      int nk = 1;
+      b200_operand cv = op(c->one, 0, 0);
+      if (carry) {
+        if (ce != nw || cl != nl) { b200::set_error("tempo_zip_up_right: carry mismatch"); return B200_EINVAL; }
+        nk = ck;
+        cv = op(carry, (int64_t)nl * nw, nw, 1);
+      } else if (nl != 1 || nw != 1) {
+        b200::set_error("tempo_zip_up_right: bad single-site step");
+        return B200_EINVAL;
+      }
+      cplx *tmp = nullptr, *out = nullptr;         // T[k,w,n] = sum_l C[k,l,w] A[l,n]
+      B200_TRY(dev_alloc(c, &tmp, (size_t)nk * nw * nn));
+      B200_TRY(gemm(c, nk, nn, nl, nw, 1, cv, op(a.p, (int64_t)nn * nr, nr), tmp,
+                    (int64_t)nw * nn, 1, nn, 0));
+      B200_TRY(dev_alloc(c, &out, (size_t)nk * nse));
+      B200_TRY(gemm(c, nk, nse, nw * nn, 1, 1, op(tmp, (int64_t)nw * nn, 1), op(mat, nse, 1), out,
+                    nse, 1, 0, 0));
+      B200_TRY(dev_free(c, tmp));
+      B200_TRY(dev_free(c, a.p));
+      if (carry) B200_TRY(dev_free(c, carry));
+      c->sites[ib] = Site{out, nk, ns, nse / ns};
+      return B200_OK;
+    }
+    const int ns = site.rows, ne = site.cols;
+    if (ns != nn) { b200::set_error("tempo_zip_up_right: array leg mismatch"); return B200_EINVAL; }
+    int nk = 0;
+    cplx* theta = nullptr;
+    if (!carry) {                        // Theta[0,s,r,e] = A[0,s,r] M[s,e]
+      if (site.kind != B200_TEMPO_START || nl != 1) {
+        b200::set_error("tempo_zip_up_right: bad first site");
+        return B200_EINVAL;
+      }
+      nk = 1;
+      B200_TRY(dev_alloc(c, &theta, (size_t)ns * nr * ne));
+      B200_TRY(gemm(c, 1, nr, 1, ns, ne, op(c->one, 0, 0), op(a.p, 0, 1, nr), theta, 0, ne,
+                    (int64_t)nr * ne, 1, mat, ne, 1));
+    } else {
+      if (site.kind != B200_TEMPO_MID || cl != nl || ce != ne) {
+        b200::set_error("tempo_zip_up_right: bad middle site");
+        return B200_EINVAL;
+      }
+      nk = ck;
+      B200_TRY(dev_alloc(c, &theta, (size_t)nk * ns * nr * ne));
+      B200_TRY(gemm(c, nk, nr, nl, ns, ne, op(carry, (int64_t)nl * ne, ne, 0, 1),
+                    op(a.p, (int64_t)nn * nr, 1, nr), theta, (int64_t)ns * nr * ne, ne,
+                    (int64_t)nr * ne, 1, mat, ne, 1));
+    }
+    const int m = nk * ns, n = nr * ne;
+    int nj = 0;
+    B200_TRY(split(c, theta, m, n, n, 1, eps, &nj));
+    cplx *new_site = nullptr, *new_carry = nullptr;
+    B200_TRY(dev_alloc(c, &new_site, (size_t)m * nj));
+    B200_TRY(dev_alloc(c, &new_carry, (size_t)nj * n));
+    B200_TRY(emit(c, m, n, nj, new_site, 1, nj, 0, 1, new_carry));
+    B200_TRY(dev_free(c, theta));
+    B200_TRY(dev_free(c, a.p));
+    if (carry) B200_TRY(dev_free(c, carry));
+    c->sites[ib] = Site{new_site, nk, ns, nj};
+    carry = new_carry; ck = nj; cl = nr; ce = ne;
+  }
+  if (carry) B200_TRY(dev_free(c, carry));
+  return B200_OK;
+}
+
+extern "C" int b200_chain_tempo_step(void* h, const b200_tempo_site* mpo, int nb, const void* p1_,
+                                     const void* p2site_, const void* sum_north_, int d2,
+                                     double eps, void* state_out_) {
+  Chain* c = (Chain*)h;
+  const cplx *p1 = (const cplx*)p1_, *p2site = (const cplx*)p2site_,
+             *sn = (const cplx*)sum_north_;
+  cplx* state = (cplx*)state_out_;
+  if (!c || !mpo || !p1 || !p2site || !sn || !state || nb < 1 || d2 < 1 || c->sites.empty()) {
+    b200::set_error("b200_chain_tempo_step: invalid argument");
+    return B200_EINVAL;
+  }
+  // first half propagator on the newest site (tempo_backend.py:521-529)
+  {
+    Site last = c->sites.back();
+    if (last.da != d2 || last.dr != 1) { b200::set_error("tempo_step: bad newest site"); return B200_EINVAL; }
+    cplx* nl_ = nullptr;
+    B200_TRY(dev_alloc(c, &nl_, (size_t)last.dl * d2));
+    B200_TRY(gemm(c, last.dl, d2, d2, 1, 1, op(last.p, d2, 1), op(p1, 1, d2), nl_, d2, 1, 0, 0));
+    B200_TRY(dev_free(c, last.p));
+    c->sites.back().p = nl_;
+  }
+  // sum out the oldest leg beyond the memory cut-off (:531-537)
+  if ((int)c->sites.size() != nb) {
+    if ((int)c->sites.size() != nb + 1 || c->sites[0].dl != 1) {
+      b200::set_error("tempo_step: MPS / MPO length mismatch");
+      return B200_EINVAL;
+    }
+    Site first = c->sites[0], second = c->sites[1];
+    cplx *vec = nullptr, *merged = nullptr;
+    B200_TRY(dev_alloc(c, &vec, (size_t)first.dr));
+    B200_TRY(gemm(c, 1, first.dr, first.da, 1, 1, op(sn, 0, 1), op(first.p, first.dr, 1), vec, 0, 1, 0, 0));
+    const int sn2 = second.da * second.dr;
+    B200_TRY(dev_alloc(c, &merged, (size_t)sn2));
+    B200_TRY(gemm(c, 1, sn2, first.dr, 1, 1, op(vec, 0, 1), op(second.p, sn2, 1), merged, 0, 1, 0, 0));
+    B200_TRY(dev_free(c, vec));
+    B200_TRY(dev_free(c, first.p));
+    B200_TRY(dev_free(c, second.p));
+    c->sites[1] = Site{merged, 1, second.da, second.dr};
+    c->sites.erase(c->sites.begin());
+  }
+  B200_TRY(tempo_zip_up_right(c, mpo, nb, eps));                       // :539-547
+  B200_TRY(b200_chain_svd_sweep(h, (int)c->sites.size() - 1, 0, eps));    // :549-553
+  B200_TRY(b200_chain_push(h, p2site, d2, d2, 1));                     // :555-558
+  // read-out (:560-573): vec <- sum_a sn[a] (vec . A[:, a, :])
+  const cplx* vec = c->one;
+  cplx* owned = nullptr;
+  const int n = (int)c->sites.size();
+  for (int i = 0; i < n - 1; ++i) {
+    const Site& a = c->sites[i];
+    cplx *tmp = nullptr, *nxt = nullptr;
+    B200_TRY(dev_alloc(c, &tmp, (size_t)a.da * a.dr));
+    B200_TRY(gemm(c, 1, a.da * a.dr, a.dl, 1, 1, op(vec, 0, 1), op(a.p, (int64_t)a.da * a.dr, 1), tmp,
+                  0, 1, 0, 0));
+    B200_TRY(dev_alloc(c, &nxt, (size_t)a.dr));
+    B200_TRY(gemm(c, 1, a.dr, a.da, 1, 1, op(sn, 0, 1), op(tmp, a.dr, 1), nxt, 0, 1, 0, 0));
+    B200_TRY(dev_free(c, tmp));
+    if (owned) B200_TRY(dev_free(c, owned));
+    owned = nxt; vec = nxt;
+  }
+  B200_TRY(gemm(c, 1, d2, d2, 1, 1, op(vec, 0, 1), op(c->sites.back().p, d2, 1), state, 0, 1, 0, 0));
+  if (owned) B200_TRY(dev_free(c, owned));
+  return B200_OK;
+}
