@@ -8,11 +8,13 @@ the compute_dynamics loop.  Everything reaches the GPU through the C-ABI library
 from .backends import (BaseTempoBackend, MeanFieldTempoBackend, PtTempoBackend,
                        TempoBackend)
 from .tebd import PtTebdBackend
-from .process_tensor import DeviceProcessTensor, dynamics_device, gradient_device
+from .process_tensor import (DeviceProcessTensor, dynamics_device, gradient_device,
+                             import_process_tensor)
 from ._lib import B200Error, CudaOps, default_ops, load_library
 
 __all__ = ["BaseTempoBackend", "MeanFieldTempoBackend", "PtTempoBackend", "TempoBackend",
            "PtTebdBackend",
-           "DeviceProcessTensor", "dynamics_device", "gradient_device", "B200Error", "CudaOps",
+           "DeviceProcessTensor", "dynamics_device", "gradient_device",
+           "import_process_tensor", "B200Error", "CudaOps",
            "default_ops", "load_library"]
 __version__ = "0.1.0"

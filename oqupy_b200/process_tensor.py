@@ -81,6 +81,36 @@ class DeviceProcessTensor:
         dims.append(int(self._sites[-1].shape[1]))
         return np.array(dims)
 
+    # -- persistence -------------------------------------------
+    def export(self, filename):
+        """Write the PT-MPO to ``filename`` (numpy ``.npz`` container, uncompressed): the
+        side-format of this package for the reference's HDF5 ``FileProcessTensor``
+        (process_tensor.py:501-559, 801-823; h5py is not part of this image).  Same
+        content: dimension, dt, name, description, the rank-3 sites ``(chi_k, chi_k+1, d2)``
+        and the cap vectors.  Sites are copied device -> host one at a time."""
+        data = {"format": "oqupy_b200-pt-1", "hilbert_space_dimension": self._hs_dim,
+                "dt": np.nan if self._dt is None else float(self._dt),
+                "name": "" if self.name is None else str(self.name),
+                "description": "" if self.description is None else str(self.description),
+                "num_sites": len(self._sites), "num_caps": len(self._caps)}
+        for k, t in enumerate(self._sites):
+            data[f"mpo_{k}"] = self._ops.to_host(t)
+        for k, c in enumerate(self._caps):
+            data[f"cap_{k}"] = self._ops.to_host(c)
+        with open(filename, "wb") as f:
+            np.savez(f, **data)
+
+    def export_to(self, process_tensor):
+        """Fill a reference process tensor (``SimpleProcessTensor`` or the HDF5-backed
+        ``FileProcessTensor``) through its own ``set_mpo_tensor`` / ``set_cap_tensor``
+        (process_tensor.py:291-324): the route to the reference's on-disk format where h5py
+        is installed."""
+        for k, t in enumerate(self._sites):
+            process_tensor.set_mpo_tensor(k, self._ops.to_host(t))
+        for k, c in enumerate(self._caps):
+            process_tensor.set_cap_tensor(k, self._ops.to_host(c))
+        return process_tensor
+
     def compute_caps(self):
         """cap_N = [1]; cap_k = sum T_k cap_{k+1} tr^2   (process_tensor.py:380-406)."""
         ops = self._ops
@@ -92,6 +122,24 @@ class DeviceProcessTensor:
             ops.caps_step(chi_l, chi_r, d2, t, caps[0], tr2, cap)
             caps.insert(0, cap)
         self._caps = caps
+
+
+def import_process_tensor(filename, ops=None):
+    """Read a file written by :meth:`DeviceProcessTensor.export` straight onto the device
+    (counterpart of ``oqupy.import_process_tensor``, process_tensor.py:801-823)."""
+    with np.load(filename, allow_pickle=False) as f:
+        if str(f["format"]) != "oqupy_b200-pt-1":
+            raise ValueError(f"{filename}: not an oqupy_b200 process tensor file")
+        dt = float(f["dt"])
+        pt = DeviceProcessTensor(int(f["hilbert_space_dimension"]),
+                                 dt=None if np.isnan(dt) else dt,
+                                 name=str(f["name"]) or None,
+                                 description=str(f["description"]) or None, ops=ops)
+        for k in range(int(f["num_sites"])):
+            pt.set_mpo_tensor(k, f[f"mpo_{k}"])
+        caps = [pt._ops.from_host(f[f"cap_{k}"]) for k in range(int(f["num_caps"]))]
+    pt._caps = caps
+    return pt
 
 
 def dynamics_device(pt, propagators, initial_states, num_steps=None, ops=None):

@@ -199,3 +199,32 @@ def test_multi_environment_dynamics_host_logic():
     np.testing.assert_allclose(states, g["states"], atol=1e-10, rtol=0)
     swapped = ob.dynamics_device(pts[::-1], props, g["initial_state"], ops=ops)
     np.testing.assert_allclose(swapped, g["states_swapped"], atol=1e-10, rtol=0)
+
+
+def test_process_tensor_file_round_trip(tmp_path):
+    """DeviceProcessTensor.export / import_process_tensor (the side-format for the
+    reference's HDF5 FileProcessTensor, process_tensor.py:501-559, 801-823) and export_to a
+    host process tensor through the reference's set_mpo_tensor / set_cap_tensor protocol."""
+    g = load_golden("pt_k8_eps9_n24")
+    ops = HostModelOps()
+    _, pt, propagators = build_pt(g, ops)
+    path = tmp_path / "pt.b200pt"
+    pt.export(str(path))
+    back = ob.import_process_tensor(str(path), ops=ops)
+    assert len(back) == len(pt) and back.dt == pt.dt
+    assert list(back.get_bond_dimensions()) == list(pt.get_bond_dimensions())
+    states = ob.dynamics_device(back, propagators, g["initial_state"], ops=ops)
+    np.testing.assert_allclose(states, g["states"], atol=1e-10, rtol=0)
+
+    class HostPt:                     # the two setters of SimpleProcessTensor
+        def __init__(self):
+            self.mpo, self.cap = {}, {}
+
+        def set_mpo_tensor(self, step, tensor):
+            self.mpo[step] = np.array(tensor)
+
+        def set_cap_tensor(self, step, tensor):
+            self.cap[step] = np.array(tensor)
+    host = pt.export_to(HostPt())
+    assert len(host.mpo) == len(pt) and len(host.cap) == len(pt) + 1
+    np.testing.assert_array_equal(host.mpo[3], pt.get_mpo_tensor(3))
