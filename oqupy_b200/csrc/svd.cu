@@ -112,6 +112,12 @@ __host__ Layout make_layout(int m, int n) {
   L.S = L.nb / 2;
   const int sms = device_sms();
   int max_r = sms / L.S;
+  {   // throughput mode for ensembles of small problems: fewer row slices per SVD leave
+      // SMs to the SVDs of other members running on their own streams
+    static int cap = -1;
+    if (cap < 0) { const char* e = getenv("B200_SVD_MAX_SLICES"); cap = e ? atoi(e) : 0; }
+    if (cap > 0 && max_r > cap) max_r = cap;
+  }
   if (max_r < 1) max_r = 1;
   // Row slices: X rows cost a Gram pass AND an apply pass, W rows only an apply pass,
   // so X slices are made smaller.  Slices never mix X and W rows (except R == 1).
