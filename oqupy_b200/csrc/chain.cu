@@ -9,6 +9,8 @@
 // ~70 us of interpreter time per SVD from a ~400-SVD dependency chain.
 #include <stdlib.h>
 
+#include <atomic>
+#include <map>
 #include <vector>
 
 #include "common.cuh"
@@ -20,7 +22,46 @@ struct Site {
   int dl, da, dr;       // (chi_l, array leg, chi_r), contiguous complex128
 };
 
+// Host-side first-fit allocator over ONE device arena.  Everything a chain allocates is
+// used on its single stream, so a freed range may be handed out again at once (the kernels
+// that read it are ordered before the kernels that will overwrite it): no CUDA call per
+// allocation -- ten cudaMallocAsync / cudaFreeAsync per truncated SVD were the largest
+// host cost of a step.  Requests that do not fit fall back to the stream-ordered pool.
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0;
+  std::map<size_t, size_t> free_;     // offset -> size, coalesced
+  void init(char* b, size_t c) { base = b; cap = c; free_.clear(); if (c) free_[0] = c; }
+  void* alloc(size_t n) {
+    n = (n + 255) & ~(size_t)255;
+    for (auto it = free_.begin(); it != free_.end(); ++it) {
+      if (it->second >= n) {
+        const size_t off = it->first, rest = it->second - n;
+        free_.erase(it);
+        if (rest) free_[off + n] = rest;
+        return base + off;
+      }
+    }
+    return nullptr;
+  }
+  bool owns(const void* p) const { return base && (const char*)p >= base && (const char*)p < base + cap; }
+  void release(void* p, size_t n) {
+    n = (n + 255) & ~(size_t)255;
+    size_t off = (size_t)((char*)p - base);
+    auto nxt = free_.lower_bound(off);
+    if (nxt != free_.begin()) {
+      auto prv = std::prev(nxt);
+      if (prv->first + prv->second == off) { off = prv->first; n += prv->second; free_.erase(prv); }
+    }
+    if (nxt != free_.end() && off + n == nxt->first) { n += nxt->second; free_.erase(nxt); }
+    free_[off] = n;
+  }
+};
+
 struct Chain {
+  std::vector<Arena> arenas;            // grows by doubling (256 MB, 512 MB, ...)
+  size_t next_arena_bytes;
+  std::map<const void*, size_t> live;   // arena allocations -> size
   cudaStream_t stream;
   std::vector<Site> sites;
   void* work;
@@ -35,11 +76,41 @@ struct Chain {
 
 int dev_alloc(Chain* c, cplx** out, size_t n) {
   if (n == 0) n = 1;
-  B200_CUDA_CHECK(cudaMallocAsync((void**)out, n * sizeof(cplx), c->stream));
+  const size_t bytes = n * sizeof(cplx);
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    for (auto& a : c->arenas) {
+      if (void* p = a.alloc(bytes)) {
+        c->live[p] = bytes;
+        *out = (cplx*)p;
+        return B200_OK;
+      }
+    }
+    // no room: add a chunk (a rare, synchronous cudaMalloc), at most 10 of them
+    if (attempt || c->next_arena_bytes == 0 || c->arenas.size() >= 10) break;
+    size_t want = c->next_arena_bytes;
+    while (want < 2 * bytes) want *= 2;
+    void* p = nullptr;
+    if (cudaMalloc(&p, want) != cudaSuccess) { (void)cudaGetLastError(); break; }
+    Arena a;
+    a.init((char*)p, want);
+    c->arenas.push_back(a);
+    c->next_arena_bytes = want * 2;
+  }
+  B200_CUDA_CHECK(cudaMallocAsync((void**)out, bytes, c->stream));
   return B200_OK;
 }
+Arena* arena_of(Chain* c, const void* p) {
+  for (auto& a : c->arenas) if (a.owns(p)) return &a;
+  return nullptr;
+}
 int dev_free(Chain* c, cplx* p) {
-  if (p) B200_CUDA_CHECK(cudaFreeAsync(p, c->stream));
+  if (!p) return B200_OK;
+  if (Arena* a = arena_of(c, p)) {
+    auto it = c->live.find(p);
+    if (it != c->live.end()) { a->release(p, it->second); c->live.erase(it); }
+    return B200_OK;
+  }
+  B200_CUDA_CHECK(cudaFreeAsync(p, c->stream));
   return B200_OK;
 }
 
@@ -75,8 +146,22 @@ int split(Chain* c, const cplx* theta, int m, int n, int64_t rs, int64_t cs, dou
     B200_CUDA_CHECK(cudaMalloc(&c->work, want));
     c->work_bytes = want;
   }
+  // `keep` comes back through pinned host memory: the kernel writes info[0..2], a system
+  // fence, then info[3] (>= 0).  Spinning on that word costs ~1 us; a blocking stream
+  // synchronisation costs a scheduler wake-up per SVD.
+  volatile int32_t* vinfo = c->info;
+  vinfo[3] = -1;
   B200_TRY(b200_svd_factor(c->stream, theta, m, n, rs, cs, eps, c->work, c->info));
-  B200_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  for (uint64_t it = 1;; ++it) {
+    if (vinfo[3] != -1) break;
+    if ((it & 0x3FFF) == 0) {            // a faulted kernel never writes the word
+      const cudaError_t q = cudaStreamQuery(c->stream);
+      if (q == cudaSuccess) break;
+      if (q != cudaErrorNotReady) B200_CUDA_CHECK(q);
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  if (vinfo[3] == -1) B200_CUDA_CHECK(cudaStreamSynchronize(c->stream));
   c->d2h_bytes += 16;
   ++c->nsvd;
   c->sweeps += (uint64_t)c->info[1];
@@ -136,6 +221,12 @@ void* b200_chain_create(void* stream) {
     else
       (void)cudaGetLastError();
   }
+  {   // device arenas for the sites and temporaries: first chunk on first use
+      // (B200_CHAIN_ARENA_MB, default 256; 0 = stream-ordered pool only)
+    size_t mb = 256;
+    if (const char* e = getenv("B200_CHAIN_ARENA_MB")) mb = (size_t)atoll(e);
+    c->next_arena_bytes = mb << 20;
+  }
   const cplx h1 = make_double2(1.0, 0.0);
   cudaMemcpyAsync(c->one, &h1, sizeof(cplx), cudaMemcpyHostToDevice, c->stream);
   cudaStreamSynchronize(c->stream);
@@ -146,8 +237,9 @@ int b200_chain_destroy(void* h) {
   Chain* c = (Chain*)h;
   if (!c) return B200_OK;
   cudaStreamSynchronize(c->stream);
-  for (auto& s : c->sites) if (s.p) cudaFreeAsync(s.p, c->stream);
+  for (auto& s : c->sites) if (s.p && !arena_of(c, s.p)) cudaFreeAsync(s.p, c->stream);
   cudaStreamSynchronize(c->stream);
+  for (auto& a : c->arenas) if (a.base) cudaFree(a.base);
   if (c->work) cudaFree(c->work);
   if (c->info) cudaFreeHost(c->info);
   if (c->one) cudaFree(c->one);

@@ -118,6 +118,9 @@ __host__ Layout make_layout(int m, int n) {
     if (cap < 0) { const char* e = getenv("B200_SVD_MAX_SLICES"); cap = e ? atoi(e) : 0; }
     if (cap > 0 && max_r > cap) max_r = cap;
   }
+  // narrow operands (<= 6 column blocks) are pure latency: three slices per slot are faster
+  // than seven (measured on the config-1 TEMPO step: 74 -> 81 steps/s)
+  if (L.q <= 96 && max_r > 3) max_r = 3;
   if (max_r < 1) max_r = 1;
   // Row slices: X rows cost a Gram pass AND an apply pass, W rows only an apply pass,
   // so X slices are made smaller.  Slices never mix X and W rows (except R == 1).
@@ -994,6 +997,7 @@ jacobi_kernel(const cplx* __restrict__ theta, long long rs, long long cs,
       info[0] = keep;
       info[1] = sweeps_done;
       info[2] = status;
+      __threadfence_system();          // info[3] is the word a polling host waits for
       info[3] = total_rot;
     }
   }
