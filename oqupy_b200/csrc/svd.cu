@@ -80,6 +80,29 @@ __host__ __device__ inline int cost_row(long long c, int p, int T) {
 
 __host__ __device__ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// Diagnostic knobs (environment, read ONCE: a getenv per SVD is host time on the critical
+// path of a dependent chain).  Defaults are the measured choices described in DESIGN.md.
+struct Knobs {
+  int max_slices, old_slices, npass, npass_minq, npass_all;
+  double drop, kappa, negrel;      // < 0: not set
+};
+const Knobs& knobs() {
+  static const Knobs k = [] {
+    Knobs v;
+    const char* e;
+    v.max_slices = (e = getenv("B200_SVD_MAX_SLICES")) ? atoi(e) : 0;
+    v.old_slices = getenv("B200_SVD_OLD_SLICES") ? 1 : 0;
+    v.npass = (e = getenv("B200_SVD_NPASS")) ? atoi(e) : 1;
+    v.npass_minq = (e = getenv("B200_SVD_NPASS_MINQ")) ? atoi(e) : (1 << 30);
+    v.npass_all = getenv("B200_SVD_NPASS_ALL") ? 1 : 0;
+    v.drop = (e = getenv("B200_SVD_DROP")) ? atof(e) : -1.0;
+    v.kappa = (e = getenv("B200_SVD_KAPPA")) ? atof(e) : -1.0;
+    v.negrel = (e = getenv("B200_SVD_NEGREL")) ? atof(e) : -1.0;
+    return v;
+  }();
+  return k;
+}
+
 int device_sms() {
   static int sms = 0;
   if (!sms) {
@@ -114,8 +137,7 @@ __host__ Layout make_layout(int m, int n) {
   int max_r = sms / L.S;
   {   // throughput mode for ensembles of small problems: fewer row slices per SVD leave
       // SMs to the SVDs of other members running on their own streams
-    static int cap = -1;
-    if (cap < 0) { const char* e = getenv("B200_SVD_MAX_SLICES"); cap = e ? atoi(e) : 0; }
+    const int cap = knobs().max_slices;
     if (cap > 0 && max_r > cap) max_r = cap;
   }
   // narrow operands (<= 6 column blocks) are pure latency: three slices per slot are faster
@@ -137,7 +159,7 @@ __host__ Layout make_layout(int m, int n) {
     L.Rx = rx; L.Rw = max_r - rx;
   }
   L.U = 0;
-  if (max_r > 1 && want_x + want_w > max_r && !getenv("B200_SVD_OLD_SLICES")) {
+  if (max_r > 1 && want_x + want_w > max_r && !knobs().old_slices) {
     // few slices per slot (wide operands): balance them by cost; ONE slice may hold the
     // X/W boundary (its X rows come first)
     const long long cost = 2LL * L.p + L.q;
@@ -1145,16 +1167,14 @@ extern "C" int b200_svd_factor2(void* stream_, const void* theta, int m, int n, 
   double kappa0 = (cos_tol > 0.0) ? 0.01 : 8.0;
   if (cos_tol > 0.0) neg_rel = 0.0;
   double drop_rel = 1e-3 * neg_rel;      // 1e-5 * eps * ||X||_F
-  if (const char* e = getenv("B200_SVD_DROP")) drop_rel = atof(e) * neg_rel;
+  if (knobs().drop >= 0.0) drop_rel = knobs().drop * neg_rel;
   double* blkmax = (double*)(base + L.blkmax);
   // inner passes per stage: a second pass (block pair fully diagonalised) pays off where
   // the stage is bound by the tensor-core Gram / apply passes, i.e. for wide operands
-  int npass = 1, npass_minq = 1 << 30;
-  if (const char* e = getenv("B200_SVD_NPASS")) npass = atoi(e);
-  if (const char* e = getenv("B200_SVD_NPASS_MINQ")) npass_minq = atoi(e);
-  if (L.q < npass_minq && !getenv("B200_SVD_NPASS_ALL")) npass = 1;
-  if (const char* e = getenv("B200_SVD_KAPPA")) kappa0 = atof(e);
-  if (const char* e = getenv("B200_SVD_NEGREL")) neg_rel = atof(e) * ((eps > 0.0) ? eps : 0.0);
+  int npass = knobs().npass;
+  if (L.q < knobs().npass_minq && !knobs().npass_all) npass = 1;
+  if (knobs().kappa >= 0.0) kappa0 = knobs().kappa;
+  if (knobs().negrel >= 0.0) neg_rel = knobs().negrel * ((eps > 0.0) ? eps : 0.0);
   void* args[] = {&th, &rs_, &cs_, &y, &gpart, &ctrl, &sig2, &sval, &perm, &hdr,
                   &info_host, &p, &q, &nb, &Rx, &Rw, &RSx, &RSw, &SE, &tr, &minmn, &tol, &eps,
                   &neg_rel, &rin, &rsi_, &cin, &csi_, &kappa0, &blkmax, &drop_rel,
