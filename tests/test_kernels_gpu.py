@@ -215,3 +215,37 @@ def test_svd_split_strides_and_parts(shape, rows):
     np.testing.assert_allclose((hu * hl) @ hvh, mat, atol=1e-11 * s_ref[0])
     np.testing.assert_allclose(hu.conj().T @ hu, np.eye(k), atol=1e-10)
     np.testing.assert_allclose(hvh @ hvh.conj().T, np.eye(k), atol=1e-10)
+
+
+@pytest.mark.parametrize("m,n", [(1, 1), (1, 9), (9, 1), (2, 33), (33, 2)])
+def test_trunc_svd_degenerate_shapes(m, n):
+    """Vectors and 1x1 operands (the first and last sites of a chain)."""
+    ops = default_ops()
+    rng = np.random.default_rng(10 * m + n)
+    a = rnd(rng, m, n)
+    h = ops.svd_factor(ops.from_host(a), m, n, n, 1, 1e-9)
+    s_ref = np.linalg.svd(a, compute_uv=False)
+    assert h.keep == ref_keep(s_ref, 1e-9)
+    k = h.keep
+    u, svh = ops.empty(m, k), ops.empty(k, n)
+    ops.svd_emit(h, u=u, u_na=1, u_so=k, u_sj=1, svh=svh)
+    np.testing.assert_allclose(ops.to_host(u) @ ops.to_host(svh), a, atol=1e-13)
+    np.testing.assert_allclose(ops.svd_values(h)[:k], s_ref[:k], rtol=1e-12)
+
+
+def test_trunc_svd_zero_matrix_and_clusters():
+    """s_0 = 0 keeps nothing (the only way the rule returns 0); exactly degenerate singular
+    values (an isometry times a scalar) keep everything."""
+    ops = default_ops()
+    h = ops.svd_factor(ops.from_host(np.zeros((12, 7))), 12, 7, 7, 1, 1e-9)
+    assert h.keep == 0
+    ops.svd_emit(h, u=ops.empty(12, 1), u_na=1, u_so=1, u_sj=1, svh=ops.empty(1, 7))
+    rng = np.random.default_rng(4)
+    q, _ = np.linalg.qr(rnd(rng, 80, 40))
+    a = 3.0 * q
+    h = ops.svd_factor(ops.from_host(a), 80, 40, 40, 1, 1e-9)
+    assert h.keep == 40
+    np.testing.assert_allclose(ops.svd_values(h), 3.0 * np.ones(40), rtol=1e-13)
+    u, svh = ops.empty(80, 40), ops.empty(40, 40)
+    ops.svd_emit(h, u=u, u_na=1, u_so=40, u_sj=1, svh=svh)
+    np.testing.assert_allclose(ops.to_host(u) @ ops.to_host(svh), a, atol=1e-13)
