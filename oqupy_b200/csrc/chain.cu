@@ -59,7 +59,7 @@ struct Arena {
 };
 
 struct Chain {
-  std::vector<Arena> arenas;            // grows by doubling (256 MB, 512 MB, ...)
+  std::vector<Arena> arenas;            // grows by doubling (64 MB, 128 MB, ...)
   size_t next_arena_bytes;
   std::map<const void*, size_t> live;   // arena allocations -> size
   cudaStream_t stream;
@@ -222,8 +222,8 @@ void* b200_chain_create(void* stream) {
       (void)cudaGetLastError();
   }
   {   // device arenas for the sites and temporaries: first chunk on first use
-      // (B200_CHAIN_ARENA_MB, default 256; 0 = stream-ordered pool only)
-    size_t mb = 256;
+      // (B200_CHAIN_ARENA_MB, default 64; 0 = stream-ordered pool only)
+    size_t mb = 64;
     if (const char* e = getenv("B200_CHAIN_ARENA_MB")) mb = (size_t)atoll(e);
     c->next_arena_bytes = mb << 20;
   }
