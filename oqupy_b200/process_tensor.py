@@ -68,6 +68,18 @@ class DeviceProcessTensor:
     def get_mpo_tensor_device(self, step):
         return self._sites[step]
 
+    def get_mpo_tensor_device_swapped(self, step):
+        """The site with its bond legs swapped, ``(chi_k+1, chi_k, d2)`` (the MPO the
+        back-propagation of the gradient runs through, system_dynamics.py:588-628); a
+        device copy made on first use and kept."""
+        cache = self.__dict__.setdefault("_sites_swapped", {})
+        t = self._sites[step]
+        hit = cache.get(step)
+        if hit is None or hit[0] is not t:
+            hit = (t, t.permute(1, 0, 2).contiguous())
+            cache[step] = hit
+        return hit[1]
+
     def get_cap_tensor(self, step):
         if step >= len(self._caps) or step < 0:
             return None
@@ -311,7 +323,7 @@ def gradient_device(pt, propagators, initial_state, target_derivative, num_steps
     # ---- forward (gradient.py:275-316): the fused dynamics step, states kept
     v = ops.from_host(rho0.reshape(1, 1, d2))
     rho = ops.empty(num_steps + 1, 1, d2)
-    forward, props = [], []
+    forward, props, props_t = [], [], []
     for step in range(num_steps):
         t = pt.get_mpo_tensor_device(step)
         chi_l, chi_r, _ = t.shape
@@ -319,6 +331,8 @@ def gradient_device(pt, propagators, initial_state, target_derivative, num_steps
                   for p in propagators(step))
         dp1, dp2 = ops.from_host(p1.reshape(1, d2, d2)), ops.from_host(p2.reshape(1, d2, d2))
         props.append((dp1, dp2))
+        props_t.append((ops.from_host(p1.T.reshape(1, d2, d2)),
+                        ops.from_host(p2.T.reshape(1, d2, d2))))
         forward.append(v)
         v_out = ops.empty(1, chi_r, d2)
         ops.dyn_step(1, chi_l, chi_r, d2, t, dp1, dp2, v, v_out,
@@ -329,42 +343,44 @@ def gradient_device(pt, propagators, initial_state, target_derivative, num_steps
     ops.gemm(1, d2, chi, View(cap, col=1), View(v, row=d2, col=1),
              View(rho[num_steps], col=1))
     states = ops.to_host(rho).reshape(num_steps + 1, d, d)
-    # ---- backward (gradient.py:336-425)
+    # ---- backward (gradient.py:336-425).  Both passes over T are the fused streaming
+    # kernel of compute_dynamics (b200_dyn_step, T read once and coalesced):
+    #  * adjoint tensor: W[i][r,x] = sum_l T[l,r,x] F[l,i] is a dynamics step of d2
+    #    "members" that all carry F and select column i with P1[i][x,i'] = d_{i',i};
+    #  * back-propagation: B <- ((B P2) o T^swap) P1 is a dynamics step through the
+    #    bond-swapped site with the propagators P2^T, P1^T.
     target = target_derivative(states[-1]) if callable(target_derivative) \
         else target_derivative
-    back = ops.from_host(np.asarray(target, dtype=CDTYPE).reshape(1, d2))   # (chi_N = 1, d2)
+    back = ops.from_host(np.asarray(target, dtype=CDTYPE).reshape(1, 1, d2))  # (1, chi_N=1, d2)
     out = ops.empty(num_steps, d2, d2, d2)        # D3[step][x][i][j]
+    sel = np.zeros((d2, d2, d2), dtype=CDTYPE)
+    for e in range(d2):
+        sel[e, :, e] = 1.0
+    p1_sel = ops.from_host(sel)
+    p2_id = ops.from_host(np.array([np.identity(d2)] * d2, dtype=CDTYPE))
 
     def adjoint(step, b):
         """D3[x][i, j] = sum_{l,r} F[l, i] T[l, r, x] B[r, j] for the MPO of `step`."""
         t = pt.get_mpo_tensor_device(step)
         chi_l, chi_r, _ = t.shape
         f = forward[step]                                     # (1, chi_l, d2)
-        tmp = ops.empty(d2, d2, chi_r)                        # [x][i][r]
-        ops.gemm(d2, chi_r, chi_l, View(f, row=1, col=d2),
-                 View(t, row=chi_r * d2, col=d2, b1=1),
-                 View(tmp, row=chi_r, col=1, b1=d2 * chi_r), nb1=d2)
-        ops.gemm(d2, d2, chi_r, View(tmp, row=chi_r, col=1, b1=d2 * chi_r),
+        frep = ops.empty(d2, chi_l, d2)                       # d2 copies of F
+        ops.gemm(1, chi_l * d2, 1, View(ops.one), View(f, col=1),
+                 View(frep, col=1, b1=chi_l * d2), nb1=d2)
+        w = ops.empty(d2, chi_r, d2)                          # W[i][r][x]
+        ops.dyn_step(d2, chi_l, chi_r, d2, t, p1_sel, p2_id, frep, w)
+        ops.gemm(d2, d2, chi_r, View(w, row=chi_r * d2, col=d2, b1=1),
                  View(b, row=d2, col=1),
                  View(out[step], row=d2, col=1, b1=d2 * d2), nb1=d2)
 
     adjoint(num_steps - 1, back)
     for step in range(num_steps - 1, 0, -1):
-        t = pt.get_mpo_tensor_device(step)
-        chi_l, chi_r, _ = t.shape
-        dp1, dp2 = props[step]
-        # B <- B P2   (_apply_system_superoperator with P2^T)
-        b1 = ops.empty(chi_r, d2)
-        ops.gemm(chi_r, d2, d2, View(back, row=d2, col=1), View(dp2, row=d2, col=1),
-                 View(b1, row=d2, col=1))
-        # B[l, x] <- sum_r T[l, r, x] B[r, x]   (MPO with bond and system legs swapped)
-        b2 = ops.empty(chi_l, d2)
-        ops.gemm(chi_l, 1, chi_r, View(t, row=chi_r * d2, col=d2, b1=1),
-                 View(b1, row=d2, col=0, b1=1), View(b2, row=d2, col=0, b1=1), nb1=d2)
-        # B <- B P1
-        back = ops.empty(chi_l, d2)
-        ops.gemm(chi_l, d2, d2, View(b2, row=d2, col=1), View(dp1, row=d2, col=1),
-                 View(back, row=d2, col=1))
+        ts = pt.get_mpo_tensor_device_swapped(step)           # (chi_r, chi_l, d2)
+        chi_r, chi_l, _ = ts.shape
+        dp1t, dp2t = props_t[step]
+        nxt = ops.empty(1, chi_l, d2)
+        ops.dyn_step(1, chi_r, chi_l, d2, ts, dp2t, dp1t, back, nxt)
+        back = nxt
         adjoint(step - 1, back)
     d3 = ops.to_host(out)                                     # (N, x, i, j)
     derivs = []
