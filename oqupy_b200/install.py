@@ -14,7 +14,8 @@ from . import backends as _b200
 from . import tebd as _tebd
 
 _ORIGINALS = {}
-_FORCE = {"tebd": False}     # PtTebd has no module-level config dictionary to mutate
+# PtTebd and compute_dynamics have no module-level config dictionary to mutate
+_FORCE = {"tebd": False, "dynamics": False}
 
 
 def _dispatch(b200_cls, original_cls, force_key=None):
@@ -35,9 +36,74 @@ def _dispatch(b200_cls, original_cls, force_key=None):
     return factory
 
 
-def install(default=False):
+def _device_process_tensor(pt):
+    """``pt`` on the device, or None when the device path does not cover it: a
+    DeviceProcessTensor as is; a host process tensor with rank-3 sites, no transforms and no
+    initial tensor (what PT-TEMPO produces for a diagonalised coupling) is uploaded once and
+    the copy kept on the object."""
+    from .process_tensor import DeviceProcessTensor  # pylint: disable=import-outside-toplevel
+    if isinstance(pt, DeviceProcessTensor):
+        return pt
+    cached = getattr(pt, "_b200_device", None)
+    sites = getattr(pt, "_mpo_tensors", None)
+    if sites is None or len(sites) == 0 or pt.get_initial_tensor() is not None:
+        return None
+    if getattr(pt, "_transform_in", None) is not None or \
+            getattr(pt, "_transform_out", None) is not None:
+        return None
+    if any(t is None or t.ndim != 3 for t in sites):
+        return None
+    if cached is not None and cached[0] == len(sites):
+        return cached[1]
+    dev = DeviceProcessTensor(pt.hilbert_space_dimension, dt=pt.dt)
+    for k, t in enumerate(sites):
+        dev.set_mpo_tensor(k, t)
+    dev.compute_caps()
+    try:
+        pt._b200_device = (len(sites), dev)   # pylint: disable=protected-access
+    except AttributeError:
+        pass
+    return dev
+
+
+def _compute_dynamics_factory(original, dynamics_cls):
+    """``oqupy.compute_dynamics`` (system_dynamics.py:41-182) with the hot loop on the
+    device when every process tensor is (or can be put) on the device, there are no
+    controls and every step is recorded; anything else runs the reference code."""
+    import numpy as np  # pylint: disable=import-outside-toplevel
+    from .process_tensor import dynamics_device  # pylint: disable=import-outside-toplevel
+
+    def compute_dynamics(system, initial_state=None, dt=None, num_steps=None, start_time=0.0,
+                         process_tensor=None, control=None, record_all=True, **kwargs):
+        if _FORCE["dynamics"] and process_tensor is not None and control is None \
+                and record_all and initial_state is not None:
+            pts = process_tensor if isinstance(process_tensor, (list, tuple)) \
+                else [process_tensor]
+            devs = [_device_process_tensor(p) for p in pts]
+            if devs and all(d is not None for d in devs):
+                step = dt if dt is not None else devs[0].dt
+                n = num_steps if num_steps is not None else min(len(d) for d in devs)
+                if step is not None and all(len(d) >= n for d in devs):
+                    from oqupy.config import INTEGRATE_EPSREL, SUBDIV_LIMIT  # pylint: disable=import-outside-toplevel
+                    props = system.get_propagators(
+                        step, start_time, kwargs.get("subdiv_limit", SUBDIV_LIMIT),
+                        kwargs.get("liouvillian_epsrel", INTEGRATE_EPSREL))
+                    states = dynamics_device(devs if len(devs) > 1 else devs[0], props,
+                                             np.asarray(initial_state), num_steps=n)
+                    times = [start_time + step * k for k in range(n + 1)]
+                    return dynamics_cls(times=times, states=list(states))
+        return original(system, initial_state=initial_state, dt=dt, num_steps=num_steps,
+                        start_time=start_time, process_tensor=process_tensor,
+                        control=control, record_all=record_all, **kwargs)
+    compute_dynamics.__doc__ = original.__doc__
+    return compute_dynamics
+
+
+def install(default=False, dynamics=True):
     """Rebind OQuPy's backend names.  With ``default=True`` the config dictionaries are
-    also mutated in place so that every Tempo / PtTempo uses the B200 backend."""
+    also mutated in place so that every Tempo / PtTempo uses the B200 backend.
+    ``dynamics=True`` also routes ``oqupy.compute_dynamics`` through the device loop
+    whenever its process tensors are (or can be uploaded to) device process tensors."""
     import oqupy  # pylint: disable=import-outside-toplevel
     import oqupy.backends.tempo_backend as tb  # pylint: disable=import-outside-toplevel
     import oqupy.pt_tebd as tebdm  # pylint: disable=import-outside-toplevel
@@ -60,6 +126,15 @@ def install(default=False):
     tebdm.PtTebdBackend = _dispatch(_tebd.PtTebdBackend, _ORIGINALS["PtTebdBackend"],
                                     force_key="tebd")
     _FORCE["tebd"] = bool(default)
+    # oqupy.compute_dynamics (system_dynamics.py:41-182): module attribute of
+    # oqupy.system_dynamics, re-exported by oqupy/__init__.py
+    import oqupy.system_dynamics as sdm  # pylint: disable=import-outside-toplevel
+    if "compute_dynamics" not in _ORIGINALS:
+        _ORIGINALS["compute_dynamics"] = sdm.compute_dynamics
+    shim = _compute_dynamics_factory(_ORIGINALS["compute_dynamics"], oqupy.Dynamics)
+    sdm.compute_dynamics = shim
+    oqupy.compute_dynamics = shim
+    _FORCE["dynamics"] = bool(dynamics)
     if default:
         oqupy.config.TEMPO_BACKEND_CONFIG["backend"] = "b200"
         oqupy.config.PT_TEMPO_BACKEND_CONFIG["backend"] = "b200"
@@ -76,6 +151,10 @@ def uninstall():
     import oqupy.tempo as tm  # pylint: disable=import-outside-toplevel
     tebdm.PtTebdBackend = _ORIGINALS["PtTebdBackend"]
     _FORCE["tebd"] = False
+    _FORCE["dynamics"] = False
+    import oqupy.system_dynamics as sdm  # pylint: disable=import-outside-toplevel
+    sdm.compute_dynamics = _ORIGINALS["compute_dynamics"]
+    oqupy.compute_dynamics = _ORIGINALS["compute_dynamics"]
     tm.TempoBackend = _ORIGINALS["TempoBackend"]
     tb.BaseTempoBackend = _ORIGINALS["BaseTempoBackend"]
     tm.MeanFieldTempoBackend = _ORIGINALS["MeanFieldTempoBackend"]

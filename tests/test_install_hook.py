@@ -17,11 +17,12 @@ pytestmark = pytest.mark.skipif(not reference_available(),
 
 def test_install_dispatch(monkeypatch):
     oqupy = load_reference()
-    from oqupy_b200 import backends, install
+    from oqupy_b200 import backends, install, process_tensor
     from host_model_ops import HostModelOps
     ops = HostModelOps()
     # product default_ops raises without CUDA; inject the test model for this check
     monkeypatch.setattr(backends, "default_ops", lambda: ops)
+    monkeypatch.setattr(process_tensor, "default_ops", lambda: ops)
     install.install()
     try:
         corr = oqupy.PowerLawSD(alpha=0.1, zeta=1, cutoff=4.0,
@@ -97,10 +98,11 @@ def test_install_dispatch_pt_tebd_and_unique(monkeypatch):
     SimpleProcessTensor) on the rebound PtTebdBackend; oqupy.PtTempo / Tempo with
     unique=True on the rebound TEMPO backends."""
     oqupy = load_reference()
-    from oqupy_b200 import backends, install, tebd
+    from oqupy_b200 import backends, install, process_tensor, tebd
     from host_model_ops import HostModelOps
     ops = HostModelOps()
     monkeypatch.setattr(backends, "default_ops", lambda: ops)
+    monkeypatch.setattr(process_tensor, "default_ops", lambda: ops)
     monkeypatch.setattr(tebd, "default_ops", lambda: ops)
     sig = oqupy.operators.sigma
     corr = oqupy.PowerLawSD(alpha=0.3, zeta=3, cutoff=3.0, cutoff_type="exponential",
@@ -162,3 +164,51 @@ def test_install_dispatch_pt_tebd_and_unique(monkeypatch):
     finally:
         install.uninstall()
     assert oqupy.pt_tebd.PtTebdBackend is install._ORIGINALS["PtTebdBackend"]
+
+
+def test_install_compute_dynamics(monkeypatch):
+    """oqupy.compute_dynamics rebound (system_dynamics.py:41-182): host process tensors from
+    the reference's PT-TEMPO are uploaded once, one and two environments; controls fall
+    through to the reference code."""
+    oqupy = load_reference()
+    from oqupy_b200 import backends, install, process_tensor
+    from host_model_ops import HostModelOps
+    ops = HostModelOps()
+    monkeypatch.setattr(backends, "default_ops", lambda: ops)
+    monkeypatch.setattr(process_tensor, "default_ops", lambda: ops)
+    sig = oqupy.operators.sigma
+    corr = oqupy.PowerLawSD(alpha=0.1, zeta=1, cutoff=4.0, cutoff_type="exponential",
+                            temperature=0.5)
+    bath = oqupy.Bath(0.5 * sig("z"), corr)
+    system = oqupy.System(0.5 * sig("x") + 0.2 * sig("z"))
+    params = oqupy.TempoParameters(dt=0.1, dkmax=5, epsrel=1e-6)
+    rho0 = oqupy.operators.spin_dm("z+")
+    pt = oqupy.pt_tempo_compute(bath=bath, start_time=0.0, end_time=1.0, parameters=params,
+                                progress_type="silent")
+    ref1 = oqupy.compute_dynamics(system, process_tensor=pt, initial_state=rho0,
+                                  progress_type="silent")
+    ref2 = oqupy.compute_dynamics(system, process_tensor=[pt, pt], initial_state=rho0,
+                                  progress_type="silent")
+    install.install()
+    try:
+        launches = ops.launches
+        new1 = oqupy.compute_dynamics(system, process_tensor=pt, initial_state=rho0,
+                                      progress_type="silent")
+        assert ops.launches > launches            # ran on the (model) device
+        assert hasattr(pt, "_b200_device")
+        np.testing.assert_allclose(new1.times, ref1.times, atol=1e-12)
+        np.testing.assert_allclose(new1.states, ref1.states, atol=1e-10)
+        new2 = oqupy.compute_dynamics(system, process_tensor=[pt, pt], initial_state=rho0,
+                                      num_steps=6, progress_type="silent")
+        np.testing.assert_allclose(new2.states, ref2.states[:7], atol=1e-10)
+        # a control is outside the device path: the reference code answers
+        control = oqupy.Control(2)
+        control.add_single(3, oqupy.operators.left_super(sig("x")))
+        launches = ops.launches
+        withc = oqupy.compute_dynamics(system, process_tensor=pt, initial_state=rho0,
+                                       control=control, progress_type="silent")
+        assert ops.launches == launches
+        assert len(withc.states) == len(ref1.states)
+    finally:
+        install.uninstall()
+    assert oqupy.compute_dynamics is install._ORIGINALS["compute_dynamics"]
