@@ -92,7 +92,7 @@ int b200_zgemm_strided(void* stream, int m, int n, int k, int nb1, int nb2,
  *   sets the orthogonality target |cos| of the Jacobi iteration (default 1e-11, never below
  *   the rounding level 2 sqrt(max(m,n)) eps_mach): PT-TEBD multiplies the factors by
  *   inverse singular values (pt_tebd_backend.py:533-559), which amplifies a residual
- *   non-orthogonality by 1/lambda, and asks for 1e-15.
+ *   non-orthogonality by 1/lambda, and asks for 1e-12 (which also selects the relative-accuracy mode).
  * b200_svd_emit_parts: as b200_svd_emit; `vh` receives S*Vh (vh_unscaled = 0) or Vh
  *   (vh_unscaled = 1), `lam` / `inv_lam` (complex128[keep], may be NULL) the kept singular
  *   values and their inverses (the lambda matrices of pt_tebd_backend.py:526, 573-578).

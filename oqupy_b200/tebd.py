@@ -27,7 +27,7 @@ CDTYPE = np.complex128
 # cos_tol > 0 selects (tiny absolute floor, Rutishauser updates, no loose columns); the
 # tolerance itself was measured: 1e-12 and 1e-15 give the same 5e-10 agreement with the
 # LAPACK oracle on the config-4 shape, 1e-12 is 19 % faster.
-COS_TOL = float(os.environ.get("B200_TEBD_COS_TOL", "1e-15"))
+COS_TOL = float(os.environ.get("B200_TEBD_COS_TOL", "1e-12"))
 
 
 def _isqrt(x):
