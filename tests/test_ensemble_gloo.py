@@ -40,6 +40,14 @@ def _worker(rank, world, port, n_members, out_dir):
                             1e-6, 8, ops=ops)
 
     res = run_ensemble(n_members, member)
+    # the same ensemble with two members of this rank in flight (thread + ops object each)
+    res_c = run_ensemble(n_members, lambda i, o: tempo_member(
+        np.where(g["influences"] == 0, 0,
+                 np.exp(np.log(np.where(g["influences"] == 0, 1, g["influences"]))
+                        * (1.0 + 0.1 * i)))[:7],
+        lambda s: (p1, p2), g["initial_state"], 6, 1e-6, 8, ops=o),
+        concurrent=2, make_ops=HostModelOps)
+    np.testing.assert_array_equal(res_c, res)
     assert shard_indices(n_members, rank, world) == list(range(rank, n_members, world))
     np.save(os.path.join(out_dir, f"rank{rank}.npy"), res)
     dist.destroy_process_group()
