@@ -315,7 +315,7 @@ def gpu_arm(args):
             "peak_source": ("fp64 cuBLAS DGEMM 4096^3 measured in this run "
                             "(MEASURED_PEAKS.json carries no fp64 figure)"),
             "note": ("a chain of ~400 DEPENDENT small/medium SVDs per step: the kernel "
-                     "is latency-bound (ncu: issue slots 25% active, fp64 pipe 13%, "
+                     "is latency-bound (ncu: issue slots 21% active, fp64 pipe 11%, "
                      "barrier stalls dominate; DRAM traffic ~ the compulsory read, the "
                      "working set lives in L2) -- see DESIGN.md section 5"),
             "kernel_ms": k_ms, "kernel_share_of_step": k_ms / dev_ms,
