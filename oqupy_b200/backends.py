@@ -191,8 +191,21 @@ class PtTempoBackend:
             for step in reversed(range(self._num_steps)):
                 pt.set_mpo_tensor_device(step, self.get_mpo_tensor_device(step))
         else:
+            # a host process tensor (the reference's SimpleProcessTensor) gets host copies
+            # through its own protocol; the device copies stay attached to it, so that the
+            # rebound oqupy.compute_dynamics (install.py) does not upload them again
+            from .process_tensor import DeviceProcessTensor  # pylint: disable=import-outside-toplevel
+            dev = DeviceProcessTensor(self._dimension, dt=getattr(pt, "dt", None),
+                                      ops=self._ops)
             for step in reversed(range(self._num_steps)):
-                pt.set_mpo_tensor(step, self.get_mpo_tensor(step))
+                site = self.get_mpo_tensor_device(step)
+                dev.set_mpo_tensor_device(step, site)
+                pt.set_mpo_tensor(step, self._ops.to_host(site))
+            dev.compute_caps()
+            try:
+                pt._b200_device = (self._num_steps, dev)   # pylint: disable=protected-access
+            except AttributeError:
+                pass
         pt.compute_caps()
 
 

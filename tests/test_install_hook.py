@@ -46,8 +46,11 @@ def test_install_dispatch(monkeypatch):
         assert isinstance(ptn._backend_instance, backends.PtTempoBackend)
         d_ref = oqupy.compute_dynamics(system, process_tensor=ptr.get_process_tensor(
             progress_type="silent"), initial_state=rho0, progress_type="silent")
-        d_new = oqupy.compute_dynamics(system, process_tensor=ptn.get_process_tensor(
-            progress_type="silent"), initial_state=rho0, progress_type="silent")
+        pt_new = ptn.get_process_tensor(progress_type="silent")
+        # the device copies of the sites stay attached to the host process tensor
+        assert pt_new._b200_device[0] == len(pt_new)
+        d_new = oqupy.compute_dynamics(system, process_tensor=pt_new, initial_state=rho0,
+                                       progress_type="silent")
         np.testing.assert_allclose(d_new.states, d_ref.states, atol=1e-9)
     finally:
         install.uninstall()
