@@ -37,33 +37,8 @@ def _dispatch(b200_cls, original_cls, force_key=None):
 
 
 def _device_process_tensor(pt):
-    """``pt`` on the device, or None when the device path does not cover it: a
-    DeviceProcessTensor as is; a host process tensor with rank-3 sites, no transforms and no
-    initial tensor (what PT-TEMPO produces for a diagonalised coupling) is uploaded once and
-    the copy kept on the object."""
-    from .process_tensor import DeviceProcessTensor  # pylint: disable=import-outside-toplevel
-    if isinstance(pt, DeviceProcessTensor):
-        return pt
-    cached = getattr(pt, "_b200_device", None)
-    sites = getattr(pt, "_mpo_tensors", None)
-    if sites is None or len(sites) == 0 or pt.get_initial_tensor() is not None:
-        return None
-    if getattr(pt, "_transform_in", None) is not None or \
-            getattr(pt, "_transform_out", None) is not None:
-        return None
-    if any(t is None or t.ndim != 3 for t in sites):
-        return None
-    if cached is not None and cached[0] == len(sites):
-        return cached[1]
-    dev = DeviceProcessTensor(pt.hilbert_space_dimension, dt=pt.dt)
-    for k, t in enumerate(sites):
-        dev.set_mpo_tensor(k, t)
-    dev.compute_caps()
-    try:
-        pt._b200_device = (len(sites), dev)   # pylint: disable=protected-access
-    except AttributeError:
-        pass
-    return dev
+    from .process_tensor import as_device_process_tensor  # pylint: disable=import-outside-toplevel
+    return as_device_process_tensor(pt)
 
 
 def _compute_dynamics_factory(original, dynamics_cls):

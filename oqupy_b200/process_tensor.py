@@ -136,6 +136,37 @@ class DeviceProcessTensor:
         self._caps = caps
 
 
+def as_device_process_tensor(pt, ops=None):
+    """``pt`` on the device, or None when the device path does not cover it: a
+    DeviceProcessTensor as is; a host process tensor with rank-3 sites, no transforms and no
+    initial tensor (what PT-TEMPO produces for a diagonalised coupling,
+    process_tensor.py:249-430) is uploaded once and the copy kept on the object -- its
+    public ``get_mpo_tensor`` would expand every site to four legs in an interpreted loop
+    (process_tensor.py:346-347, util.py:30-57) on every call."""
+    if isinstance(pt, DeviceProcessTensor):
+        return pt
+    sites = getattr(pt, "_mpo_tensors", None)
+    if sites is None or len(sites) == 0 or pt.get_initial_tensor() is not None:
+        return None
+    if getattr(pt, "_transform_in", None) is not None or \
+            getattr(pt, "_transform_out", None) is not None:
+        return None
+    if any(t is None or getattr(t, "ndim", 0) != 3 for t in sites):
+        return None
+    cached = getattr(pt, "_b200_device", None)
+    if cached is not None and cached[0] == len(sites):
+        return cached[1]
+    dev = DeviceProcessTensor(pt.hilbert_space_dimension, dt=pt.dt, ops=ops)
+    for k, t in enumerate(sites):
+        dev.set_mpo_tensor(k, t)
+    dev.compute_caps()
+    try:
+        pt._b200_device = (len(sites), dev)   # pylint: disable=protected-access
+    except AttributeError:
+        pass
+    return dev
+
+
 def import_process_tensor(filename, ops=None):
     """Read a file written by :meth:`DeviceProcessTensor.export` straight onto the device
     (counterpart of ``oqupy.import_process_tensor``, process_tensor.py:801-823)."""

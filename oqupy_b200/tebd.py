@@ -19,6 +19,7 @@ import os
 import numpy as np
 
 from ._lib import View, default_ops
+from .process_tensor import as_device_process_tensor
 
 CDTYPE = np.complex128
 # Orthogonality target of the truncated SVDs.  The gate update multiplies the factors by
@@ -201,7 +202,8 @@ class PtTebdBackend:
     # -------------------------------------------------------------- process tensors
     def apply_process_tensors(self, step, process_tensors):
         """Contract the step-1 PT-MPO site of every chain site into its gamma (:158-175).
-        A device-resident process tensor (oqupy_b200.DeviceProcessTensor: rank-3 site, delta
+        A device-resident process tensor (oqupy_b200.DeviceProcessTensor, or a host process
+        tensor with rank-3 sites and no transforms, uploaded once: rank-3 site = delta
         between the system legs, process_tensor.py:346-347) is applied without ever
         forming the 4-leg tensor; any other process tensor through its public 4-leg
         ``get_mpo_tensor``."""
@@ -211,8 +213,9 @@ class PtTebdBackend:
             gam = self._gammas[site]
             nl, d2, npt, nr = gam.shape
             t3 = None
-            if hasattr(pt, "get_mpo_tensor_device"):
-                t3 = pt.get_mpo_tensor_device(step - 1)
+            dev = as_device_process_tensor(pt, ops)
+            if dev is not None and step - 1 < len(dev):
+                t3 = dev.get_mpo_tensor_device(step - 1)
             if t3 is not None:
                 assert t3.shape[0] == npt and t3.shape[2] == d2
                 nq = int(t3.shape[1])
