@@ -92,6 +92,18 @@ def test_install_dispatch_mean_field(monkeypatch):
         np.testing.assert_allclose(dn.fields, dr.fields, atol=1e-8)
         np.testing.assert_allclose(dn.system_dynamics[0].states,
                                    dr.system_dynamics[0].states, atol=1e-8)
+        # the same with degeneracy-reduced legs (tests/physics/degeneracy_mean_field_test.py)
+        ref_u = oqupy.MeanFieldTempo(mfs, [bath], params, [rho0], 1.0, start_time=0.0,
+                                     unique=True)
+        new_u = oqupy.MeanFieldTempo(mfs, [bath], params, [rho0], 1.0, start_time=0.0,
+                                     unique=True, backend_config={"backend": "b200"})
+        assert isinstance(new_u._backend_instance, backends.MeanFieldTempoBackend)
+        ref_u.compute(0.4, progress_type="silent")
+        new_u.compute(0.4, progress_type="silent")
+        du, dnu = ref_u.get_dynamics(), new_u.get_dynamics()
+        np.testing.assert_allclose(dnu.fields, du.fields, atol=1e-8)
+        np.testing.assert_allclose(dnu.system_dynamics[0].states,
+                                   du.system_dynamics[0].states, atol=1e-8)
     finally:
         install.uninstall()
 
