@@ -79,13 +79,17 @@ def round_robin(nb):
         ring = [ring[0]] + [ring[-1]] + ring[1:-1]
 
 
-def block_jacobi(x, max_sweeps=60):
+def block_jacobi(x, max_sweeps=60, accumulate=False):
     """One-sided block Jacobi on the columns of x (copy).  Returns (sweeps, singular values,
-    rotated stage-slots, tested stage-slots)."""
+    rotated stage-slots, tested stage-slots); with accumulate=True the identity is stacked
+    under x like the kernel's [X ; W] and (sweeps, rotated columns, accumulated J) come back."""
     x = np.array(x, dtype=complex, order="F")
     n = x.shape[1]
     nb = (n + B - 1) // B
     floor2 = (8 * EPS * np.linalg.norm(x)) ** 2
+    mg = x.shape[0]
+    if accumulate:
+        x = np.asfortranarray(np.vstack([x, np.eye(n, dtype=complex)]))
     rotated = tested = 0
     for sweep in range(1, max_sweeps + 1):
         dirty = False
@@ -93,8 +97,7 @@ def block_jacobi(x, max_sweeps=60):
             for a, b in pairs:
                 idx = np.r_[a * B:min((a + 1) * B, n), b * B:min((b + 1) * B, n)]
                 t = x[:, idx]
-                g = t.conj().T @ t
-                g = np.ascontiguousarray(g)
+                g = np.ascontiguousarray(t[:mg].conj().T @ t[:mg])
                 j = np.eye(len(idx), dtype=complex)
                 tested += 1
                 if LIB.inner_sweeps(len(idx), g.ctypes.data, j.ctypes.data,
@@ -106,8 +109,46 @@ def block_jacobi(x, max_sweeps=60):
                 x[:, idx] = t @ j[:, order]
         if not dirty:
             break
+    if accumulate:
+        return sweep, x[:mg], x[mg:]
     s = np.sort(np.linalg.norm(x, axis=0))[::-1]
     return sweep, s, rotated, tested
+
+
+def pipeline(theta):
+    """The whole proposed factorisation in numpy, next to the
+    oracle's truncated SVD: stopped QRCP -> QR of [R11 R12]^H -> block Jacobi on R2^H ->
+    U = Q1[:, :k] W_hat,  S.Vh = (Q2 J Sigma)^H P^T.  Returns the figures a parity test of the
+    round-2 kernel will assert."""
+    from oracle import tempo_np
+    flip = theta.shape[0] < theta.shape[1]
+    a = theta.conj().T if flip else theta
+    q1, r, piv = sla.qr(a, mode="economic", pivoting=True)
+    tau = 1e-5 * EPSREL * np.linalg.norm(a)
+    k = int(np.count_nonzero(np.abs(np.diag(r)) > tau))
+    tail2 = float(np.linalg.norm(r[k:, k:]) ** 2)
+    q2, r2 = sla.qr(r[:k, :].conj().T, mode="economic")
+    sweeps, w, j = block_jacobi(r2.conj().T, accumulate=True)
+    sig = np.linalg.norm(w, axis=0)
+    order = np.argsort(-sig, kind="stable")
+    sig, w, j = sig[order], w[:, order], j[:, order]
+    keep = keep_rule(sig, tail2)
+    u = q1[:, :k] @ (w[:, :keep] / sig[:keep])
+    svh_p = ((q2 @ j[:, :keep]) * sig[:keep]).conj().T
+    svh = np.empty_like(svh_p)
+    svh[:, piv] = svh_p
+    if flip:                                       # Theta = (U S Vh)^H = V (S U^H)
+        u, svh = svh.conj().T / sig[:keep], (u * sig[:keep]).conj().T
+    u_ref, s_lap, vh_lap = tempo_np.truncated_svd(theta, EPSREL)[:3]
+    svh_ref = s_lap[:, None] * vh_lap
+    s0 = sig[0]
+    return {"columns": k, "sweeps": sweeps, "keep": keep, "keep_lapack": int(u_ref.shape[1]),
+            "recon_vs_theta_over_s0": float(np.linalg.norm(u @ svh - theta, 2) / s0),
+            "lapack_recon_vs_theta_over_s0":
+                float(np.linalg.norm(u_ref @ svh_ref - theta, 2) / s0),
+            "product_vs_lapack_over_s0": float(np.linalg.norm(u @ svh - u_ref @ svh_ref, 2) / s0)
+            if keep == u_ref.shape[1] else None,
+            "u_orthogonality": float(np.linalg.norm(u.conj().T @ u - np.eye(keep), 2))}
 
 
 def variants(theta):
@@ -199,6 +240,11 @@ def main():
         row = {"step": step, "svd_index": i, "shape": list(theta.shape),
                "decades": float(np.log10(s_ref[0] / max(s_ref[-1], 1e-300))), "variants": {}}
         only = os.environ.get("STUDY_VARIANTS")
+        if only == "pipeline":
+            row["pipeline"] = pipeline(theta)
+            print(f"  {theta.shape} pipeline: {row['pipeline']}", file=sys.stderr, flush=True)
+            print(json.dumps(row), flush=True)
+            continue
         for name, x in variants(theta):
             if only and name not in only.split(","):
                 continue
