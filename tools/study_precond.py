@@ -196,6 +196,79 @@ def gram_pivot_order(theta):
     return perm
 
 
+def qrcp_stopped(a, stop):
+    """numpy statement, step by step, of oqupy_b200/csrc/draft/qrcp.cu (physical columns stay
+    in place, perm[] holds the pivot order, LAPACK zlarfg reflectors with real beta, xGEQP3
+    norm down-dating, stop at the first pivot norm <= stop).  Returns (a_out, tau, perm, k,
+    tail2) in the kernel's output layout."""
+    a = np.array(a, dtype=complex, order="F")
+    m, n = a.shape
+    vn = np.linalg.norm(a, axis=0)
+    vn_ref = vn.copy()
+    done = np.zeros(n, dtype=bool)
+    tau = np.zeros(n, dtype=complex)
+    perm = []
+    k = 0
+    while k < min(m, n):
+        cand = np.where(done, -1.0, vn)
+        p = int(np.argmax(cand))                   # first maximum = lowest physical index
+        if not cand[p] > stop:
+            break
+        done[p] = True
+        perm.append(p)
+        alpha = a[k, p]
+        xnorm2 = float(np.sum(np.abs(a[k + 1:, p]) ** 2))
+        v = np.zeros(m - k, dtype=complex)
+        v[0] = 1.0
+        if xnorm2 > 0.0 or alpha.imag != 0.0:
+            an = np.sqrt(abs(alpha) ** 2 + xnorm2)
+            beta = -an if alpha.real >= 0.0 else an
+            tau[k] = complex((beta - alpha.real) / beta, -alpha.imag / beta)
+            v[1:] = a[k + 1:, p] / (alpha - beta)
+            a[k, p] = beta
+        a[k + 1:, p] = v[1:]
+        for c in np.nonzero(~done)[0]:
+            w = np.vdot(v, a[k:, c])
+            a[k:, c] -= np.conj(tau[k]) * w * v
+            if vn[c] > 0.0:
+                r = abs(a[k, c]) / vn[c]
+                t = max(0.0, (1.0 + r) * (1.0 - r))
+                if t * (vn[c] / vn_ref[c]) ** 2 <= np.sqrt(EPS):
+                    vn[c] = vn_ref[c] = np.linalg.norm(a[k + 1:, c])
+                else:
+                    vn[c] *= np.sqrt(t)
+        k += 1
+    rest = np.nonzero(~done)[0]
+    tail2 = float(np.sum(np.abs(a[k:, rest]) ** 2))
+    return a, tau, np.array(perm + list(rest)), k, tail2
+
+
+def check_qrcp_stopped(theta):
+    """qrcp_stopped against scipy's QRCP on one operand: |diag R|, the pivot count at the stop
+    level, ||A P - Q R|| with Q rebuilt from the stored reflectors the way apply_q_kernel does."""
+    a0 = theta.conj().T if theta.shape[0] < theta.shape[1] else theta
+    m, n = a0.shape
+    stop = 1e-5 * EPSREL * np.linalg.norm(a0)
+    a, tau, perm, k, tail2 = qrcp_stopped(a0, stop)
+    r_ref = sla.qr(a0, mode="r", pivoting=True)[0]
+    k_ref = int(np.count_nonzero(np.abs(np.diag(r_ref)) > stop))
+    r = np.zeros((k, n), dtype=complex)
+    for pos in range(n):
+        top = min(pos + 1, k)
+        r[:top, pos] = a[:top, perm[pos]]
+    y = np.vstack([r, np.zeros((m - k, n))])       # Q [R; 0], reflectors k-1 ... 0
+    for i in range(k - 1, -1, -1):
+        v = np.concatenate(([1.0], a[i + 1:, perm[i]]))
+        y[i:] -= tau[i] * np.outer(v, v.conj() @ y[i:])
+    resid = np.linalg.norm(y - a0[:, perm], 2) / np.linalg.norm(a0, 2)
+    return {"k": k, "k_scipy": k_ref, "tail2": tail2,
+            "tail2_scipy": float(np.linalg.norm(r_ref[k_ref:, k_ref:]) ** 2),
+            "diagR_rel_dev": float(np.max(np.abs(np.abs(np.diag(r)[:k])
+                                                 - np.abs(np.diag(r_ref)[:k]))
+                                          / np.abs(np.diag(r_ref)[:k]))),
+            "resid_AP_minus_QR_over_norm": float(resid)}
+
+
 def capture(step, max_ops):
     from oracle import tempo_np
     with np.load("tests/golden/c2_operands.npz") as f:
@@ -243,6 +316,10 @@ def main():
         if only == "pipeline":
             row["pipeline"] = pipeline(theta)
             print(f"  {theta.shape} pipeline: {row['pipeline']}", file=sys.stderr, flush=True)
+            print(json.dumps(row), flush=True)
+            continue
+        if only == "qrcp-check":
+            row["qrcp_stopped_vs_scipy"] = check_qrcp_stopped(theta)
             print(json.dumps(row), flush=True)
             continue
         for name, x in variants(theta):
