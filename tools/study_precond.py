@@ -25,7 +25,8 @@ Variants
   grampiv+qr  column order from a pivoted Cholesky of the fp64 Gram matrix (no pivoting inside
               the QR: a blocked Householder QR, GEMM-rich), Jacobi on L = R^H;  +qr as above
 
-  python tools/study_precond.py [step=25] [max_ops=6] [only_operand=k]   (STUDY_NPASS: inner sweeps)
+  python tools/study_precond.py [step=25] [max_ops=6] [only_operand=k]   (STUDY_NPASS: inner sweeps;
+  STUDY_VARIANTS=a,b | pipeline | qrcp-check | kdist (max_ops=0: every SVD of the step))
 """
 import ctypes
 import json
@@ -289,6 +290,8 @@ def capture(step, max_ops):
     finally:
         tempo_np.truncated_svd = inner
     # the widest operands, one from the middle of the zip-up chain, one sweep operand
+    if max_ops <= 0:
+        return len(mats), list(enumerate(mats))
     by_size = sorted(range(len(mats)), key=lambda i: -min(mats[i].shape))
     pick = by_size[:max(1, max_ops - 2)]
     nz = len(mats) // 2                            # zip-up SVDs come first, then the sweep
@@ -307,6 +310,28 @@ def main():
     nsvd, ops = capture(step, max_ops)
     if len(sys.argv) > 3:
         ops = [ops[int(sys.argv[3])]]
+    if os.environ.get("STUDY_VARIANTS") == "kdist":
+        # every SVD of the step: columns n, pivots k above the stop level, kept rank
+        rows = []
+        for i, theta in ops:
+            a = theta.conj().T if theta.shape[0] < theta.shape[1] else theta
+            r = sla.qr(a, mode="r", pivoting=True)[0]
+            d = np.abs(np.diag(r))
+            k = int(np.count_nonzero(d > 1e-5 * EPSREL * np.linalg.norm(a)))
+            keep = keep_rule(np.linalg.svd(theta, compute_uv=False))
+            rows.append((i, a.shape[0], a.shape[1], k, keep))
+        arr = np.array(rows, dtype=float)
+        nb, kb = np.ceil(arr[:, 2] / B), np.ceil(arr[:, 3] / B)
+        print(json.dumps({
+            "step": step, "svds": len(rows),
+            "sum_columns": int(arr[:, 2].sum()), "sum_pivots": int(arr[:, 3].sum()),
+            "sum_keep": int(arr[:, 4].sum()),
+            "block_pairs_per_sweep_today": int((nb * (nb - 1) / 2).sum()),
+            "block_pairs_per_sweep_stopped": int((kb * (kb - 1) / 2).sum()),
+            "tournament_rounds_per_sweep_today": int(np.maximum(nb - 1, 0).sum()),
+            "tournament_rounds_per_sweep_stopped": int(np.maximum(kb - 1, 0).sum()),
+            "per_svd_m_n_k_keep": [list(map(int, r[1:])) for r in rows]}), flush=True)
+        return
     print(f"step {step}: {nsvd} SVDs, studying {len(ops)}", file=sys.stderr, flush=True)
     for i, theta in ops:
         s_ref = np.linalg.svd(theta, compute_uv=False)
