@@ -39,6 +39,11 @@ uint64_t b200_launch_count(void);
 int b200_profile_enable(int on);
 int b200_profile_read(double* kernel_ms, double* algorithmic_flops,
                       uint64_t* launches, uint64_t* sweeps);
+/* The same, split by kernel family of the truncated SVD: ms4 / launches4 index
+ * 0 = Jacobi stage (jacobi_kernel), 1 = rank-revealing QR (qrcp_kernel), 2 = back-
+ * transformation + emit (apply_q_kernel, emit_l_kernel, emit_kernel), 3 = other. */
+int b200_profile_read_kinds(double* ms4, uint64_t* launches4, double* algorithmic_flops,
+                            uint64_t* sweeps);
 
 /* ---------------------------------------------------------------------------
  * Strided, doubly-batched complex GEMM with per-batch scale:
@@ -66,14 +71,20 @@ int b200_zgemm_strided(void* stream, int m, int n, int k, int nb1, int nb2,
                        int64_t s_b2, int accumulate);
 
 /* ---------------------------------------------------------------------------
- * eps-truncated SVD  (one-sided block Jacobi, row-sliced 2-D grid, one cooperative launch).
+ * eps-truncated SVD: rank-revealing QR stopped at the deflation level (roughly square
+ * operands, eps > 0), then one-sided block Jacobi (row-sliced 2-D grid, cooperative launches)
+ * on the surviving columns, back-transformation by the stored reflectors.
+ *
+ * `info_host` is PINNED host memory of 8 x int32: {keep, sweeps, status, rotations,
+ * pivots of the QR stage (-1 = not used), QR grid, spare, spare}.  The library itself spins
+ * on word 4 inside b200_svd_factor* when the QR stage runs (its pivot count fixes the shape
+ * of the Jacobi stage); the caller waits for word 3 (or the stream) before reading keep.
  *
  * b200_svd_factor: theta is an m x n matrix addressed theta[i*rs + j*cs].
  *   Computes all singular triplets on the device, sorts them, applies the
  *   reference's tail-norm rule
  *       keep = #{ j : sqrt(sum_{i>=j} s_i^2) > eps * s_0 }      (eps < 0: keep all)
- *   and asynchronously copies {keep, sweeps, status, rotations} (4 x int32) to
- *   `info_host` (pinned host memory).  The caller synchronises the stream, reads
+ *   and writes {keep, sweeps, status, rotations} to `info_host` (see above).  The caller synchronises the stream, reads
  *   keep, allocates exact-size outputs and calls b200_svd_emit.
  *   `work` must hold b200_svd_workspace_bytes(m, n) bytes of device memory.
  *
@@ -115,6 +126,17 @@ int b200_svd_emit(void* stream, const void* work, const void* theta, int m, int 
                   int64_t rs, int64_t cs, int keep, void* u, int u_na, int64_t u_so,
                   int64_t u_sa, int64_t u_sj, void* svh);
 int b200_svd_values(void* stream, const void* work, int m, int n, double* s_out);
+/* diagnostics of the factorisation that last ran in `work`: out4 = {QR path used (0/1),
+ * pivots above the stop level, CTAs of the QR grid, columns resident in shared memory} */
+int b200_svd_plan(const void* work, int m, int n, int32_t* out4);
+/* test access to the QR-path workspace (byte offsets of its arrays inside `work`):
+ * out16 = {eligible, p, q, transposed, QR grid, resident columns, perm, tau, work array a,
+ * Jacobi stage, header, tail partials, shared-memory bytes, and for k > 0 pivots the Jacobi
+ * stage's y, singular values, column order} */
+int b200_svd_qr_layout(int m, int n, int k, int64_t* out16);
+/* runtime switches (tests, A/B measurements): "qr" (0/1: rank-revealing QR front end),
+ * "qr_minq" (smallest min(m,n) that takes it), "qr_cols" (columns per CTA of the QR grid) */
+int b200_svd_config(const char* key, double value);
 /* diagnostics: SM-clock cycles CTA 0 (leader of pair slot 0) spent per phase of the
  * Jacobi kernel: {0 wait for input blocks, 1 load + partial Gram, 2 publish, 3 wait
  * for all partials, 4 reduce + convergence test, 5 inner 32x32 sweep, 6 sort + publish

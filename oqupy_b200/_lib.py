@@ -18,7 +18,8 @@ EXPORTS = [
     "b200_last_error", "b200_abi_version", "b200_launch_count",
     "b200_profile_enable", "b200_profile_read",
     "b200_zgemm_strided", "b200_svd_workspace_bytes", "b200_svd_factor",
-    "b200_svd_emit", "b200_svd_factor2", "b200_svd_emit_parts", "b200_svd_values", "b200_svd_phase_cycles", "b200_dyn_workspace_bytes",
+    "b200_svd_emit", "b200_svd_factor2", "b200_svd_emit_parts", "b200_svd_values",
+    "b200_svd_phase_cycles", "b200_svd_plan", "b200_svd_qr_layout", "b200_svd_config", "b200_profile_read_kinds", "b200_dyn_workspace_bytes",
     "b200_dyn_step", "b200_caps_step", "b200_dyn_run", "b200_dyn_run_workspace_bytes",
     "b200_chain_create", "b200_chain_destroy", "b200_chain_len", "b200_chain_push",
     "b200_chain_shape", "b200_chain_read", "b200_chain_svd_sweep",
@@ -96,6 +97,15 @@ def load_library():
     lib.b200_svd_phase_cycles.argtypes = [c_void_p, c_void_p, c_void_p]
     lib.b200_svd_values.restype = c_int
     lib.b200_svd_values.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p]
+    lib.b200_svd_plan.restype = c_int
+    lib.b200_svd_plan.argtypes = [c_void_p, c_int, c_int, POINTER(c_int32)]
+    lib.b200_svd_qr_layout.restype = c_int
+    lib.b200_svd_qr_layout.argtypes = [c_int, c_int, c_int, POINTER(c_int64)]
+    lib.b200_svd_config.restype = c_int
+    lib.b200_svd_config.argtypes = [c_char_p, c_double]
+    lib.b200_profile_read_kinds.restype = c_int
+    lib.b200_profile_read_kinds.argtypes = [POINTER(c_double), POINTER(c_uint64),
+                                            POINTER(c_double), POINTER(c_uint64)]
     lib.b200_dyn_workspace_bytes.restype = c_size_t
     lib.b200_dyn_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
     lib.b200_dyn_step.restype = c_int
@@ -164,7 +174,7 @@ class CudaOps:
         self.lib = load_library()
         self.device = torch.device("cuda", device)
         torch.cuda.set_device(self.device)
-        self._info = torch.zeros(4, dtype=torch.int32).pin_memory()
+        self._info = torch.zeros(8, dtype=torch.int32).pin_memory()
         self._info_np = self._info.numpy()
         self._work = None
         self.one = torch.ones(1, dtype=torch.complex128, device=self.device)
@@ -228,7 +238,7 @@ class CudaOps:
         h = SvdHandle()
         h.work, h.m, h.n = work, m, n
         h.theta, h.theta_ptr, h.rs, h.cs = theta, self._ptr(theta, off), rs, cs
-        h.keep, h.sweeps, h.status, h.rotations = (int(x) for x in self._info_np)
+        h.keep, h.sweeps, h.status, h.rotations = (int(x) for x in self._info_np[:4])
         self.d2h_bytes += 16
         if h.status != 0:
             raise B200Error(f"Jacobi SVD did not converge ({m}x{n}, "
@@ -256,6 +266,37 @@ class CudaOps:
         self._check(self.lib.b200_svd_phase_cycles(self._stream(), h.work.data_ptr(),
                                                    out), "b200_svd_phase_cycles")
         return list(out)
+
+    def svd_plan(self, h):
+        """(qr path used, pivots above the stop level, QRCP CTAs, resident columns)."""
+        out = (c_int32 * 4)()
+        self._check(self.lib.b200_svd_plan(h.work.data_ptr(), h.m, h.n, out), "b200_svd_plan")
+        return tuple(int(x) for x in out)
+
+    def svd_config(self, key, value):
+        """Runtime switch of the truncated SVD ("qr", "qr_minq", "qr_cols")."""
+        self._check(self.lib.b200_svd_config(key.encode(), float(value)), "b200_svd_config")
+
+    def svd_qr_debug(self, h):
+        """Intermediate arrays of the QR path (test access): dict with a (p x q work array),
+        perm, tau, k, tail2, or None when the plain path ran."""
+        qr, k, _, _ = self.svd_plan(h)
+        if not qr:
+            return None
+        out = (c_int64 * 16)()
+        self._check(self.lib.b200_svd_qr_layout(h.m, h.n, k, out), "b200_svd_qr_layout")
+        o = [int(x) for x in out]
+        p, q, grid = o[1], o[2], o[4]
+        raw = h.work.cpu().numpy()
+
+        def arr(off, count, dtype):
+            return np.frombuffer(raw, dtype=dtype, count=count, offset=off).copy()
+        return {"p": p, "q": q, "k": k, "transposed": bool(o[3]), "grid": grid,
+                "resident": o[5],
+                "perm": arr(o[6], q, np.int32), "tau": arr(o[7], k, np.complex128),
+                "a": arr(o[8], p * q, np.complex128).reshape(q, p).T,
+                "tail2": float(arr(o[11], grid, np.float64).sum()),
+                "sval": arr(o[14], k, np.float64)}
 
     def svd_values(self, h):
         k = min(h.m, h.n)
@@ -314,6 +355,17 @@ class CudaOps:
                                                ctypes.byref(n), ctypes.byref(sw)),
                     "b200_profile_read")
         return ms.value, fl.value, n.value, sw.value
+
+    def profile_read_kinds(self):
+        """Per kernel family of the truncated SVD: ({'jacobi','qrcp','emit','other'} ->
+        (ms, launches)), algorithmic flops, Jacobi sweeps."""
+        ms, n = (c_double * 4)(), (c_uint64 * 4)()
+        fl, sw = c_double(0.0), c_uint64(0)
+        self._check(self.lib.b200_profile_read_kinds(ms, n, ctypes.byref(fl),
+                                                     ctypes.byref(sw)),
+                    "b200_profile_read_kinds")
+        names = ("jacobi", "qrcp", "emit", "other")
+        return ({k: (ms[i], int(n[i])) for i, k in enumerate(names)}, fl.value, sw.value)
 
     def synchronize(self):
         torch.cuda.synchronize(self.device)

@@ -66,7 +66,7 @@ struct Chain {
   std::vector<Site> sites;
   void* work;
   size_t work_bytes;
-  int32_t* info;        // pinned: {keep, sweeps, status, rotations}
+  int32_t* info;        // pinned, 8 words: {keep, sweeps, status, rotations, qr pivots, ...}
   cplx* one;            // device scalar 1
   // statistics since the last reset
   uint64_t nsvd, sweeps, d2h_bytes;
@@ -196,7 +196,7 @@ void* b200_chain_create(void* stream) {
   c->one = nullptr;
   c->nsvd = c->sweeps = c->d2h_bytes = 0;
   c->log_on = false;
-  if (cudaMallocHost((void**)&c->info, 4 * sizeof(int32_t)) != cudaSuccess ||
+  if (cudaMallocHost((void**)&c->info, 8 * sizeof(int32_t)) != cudaSuccess ||
       cudaMalloc((void**)&c->one, sizeof(cplx)) != cudaSuccess) {
     b200::set_error("b200_chain_create: allocation failed");
     delete c;

@@ -14,8 +14,9 @@ void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 // roofline profiling of the dominant kernel (see b200_profile_enable)
 bool profile_on();
-void profile_begin(cudaStream_t s);
-void profile_end(cudaStream_t s, double flops, const int* sweeps_dev);
+// kind: 0 Jacobi stage, 1 rank-revealing QR, 2 back-transformation + emit, 3 other
+void profile_begin(cudaStream_t s, int kind);
+void profile_end(cudaStream_t s, int kind, double flops, const int* sweeps_dev);
 
 #define B200_CUDA_CHECK(expr)                                                   \
   do {                                                                          \

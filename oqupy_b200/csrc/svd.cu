@@ -34,7 +34,13 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+
 #include "common.cuh"
+#include "qrcp.cuh"
 
 namespace cg = cooperative_groups;
 using b200::dmma884;
@@ -614,10 +620,23 @@ __device__ __forceinline__ void apply_dmma(const cplx* tile, int rows, const cpl
   }
 }
 
+// Operand of the Jacobi kernel when the rank-revealing QR ran first (qrcp.cuh): X = L =
+// [R11 R12]^H (q rows = pivot positions, k columns), read out of the QRCP work array.
+struct QrSrc {
+  const cplx* a;            // p x q column-major: R above the diagonal of the pivot columns
+  const int* perm;          // position -> physical column
+  const double* tail_part;  // per-CTA Frobenius mass of the discarded block R22
+  long long lda;
+  int ntail;
+  int on;
+};
+
 // ------------------------------------------------------------------ Jacobi kernel
 // Persistent cooperative kernel: load -> sweeps -> column norms -> rank rule.
+// PROF: per-phase clock64 counters of CTA 0 (diagnostics; B200_SVD_PHASES=1).
+template <bool PROF>
 __global__ void __launch_bounds__(JT, 1)
-jacobi_kernel(const cplx* __restrict__ theta, long long rs, long long cs,
+jacobi_kernel(const QrSrc qsrc, const cplx* __restrict__ theta, long long rs, long long cs,
               cplx* __restrict__ y, cplx* __restrict__ gpart,
               int* __restrict__ ctrl, double* __restrict__ sig2,
               double* __restrict__ sval, int* __restrict__ perm,
@@ -644,9 +663,14 @@ jacobi_kernel(const cplx* __restrict__ theta, long long rs, long long cs,
   const int t = threadIdx.x;
   const size_t blk_elems = (size_t)T * BC;
 
-  long long pc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  long long tq = clock64();
-#define PHASE(k) { const long long tn_ = clock64(); pc[k] += tn_ - tq; tq = tn_; }
+  long long pc[PROF ? 16 : 1];
+  long long tq = 0;
+  if (PROF) {
+#pragma unroll
+    for (int k_ = 0; k_ < (PROF ? 16 : 1); ++k_) pc[k_] = 0;
+    tq = clock64();
+  }
+#define PHASE(k) if constexpr (PROF) { const long long tn_ = clock64(); pc[k] += tn_ - tq; tq = tn_; }
 
   // ---- load: Y = [X ; I], ||X||_F^2
   {
@@ -661,7 +685,13 @@ jacobi_kernel(const cplx* __restrict__ theta, long long rs, long long cs,
       const int col = blk * BC + c16;
       cplx v = make_double2(0.0, 0.0);
       if (row < p) {
-        if (col < q) {
+        if (qsrc.on) {
+          // L[i][j] = conj(R[j][position i]): upper trapezoid of the QRCP work array
+          if (col < q && col <= row) {
+            v = qsrc.a[(long long)qsrc.perm[row] * qsrc.lda + col];
+            v.y = -v.y;
+          }
+        } else if (col < q) {
           // theta[i][j] lives at (i / rin) rs + (i % rin) rsi + (j / cin) cs + (j % cin) csi:
           // two-level row and column indices, so that any leg grouping of a rank-4 tensor
           // is factorised in place (rin = cin = 1: plain strides)
@@ -911,7 +941,7 @@ jacobi_kernel(const cplx* __restrict__ theta, long long rs, long long cs,
           st_release(ready + pb * R + r_slice, g + 1);
         }
         PHASE(7)
-        ++pc[15];
+        if constexpr (PROF) ++pc[15];
       }
     }
     // convergence vote: flags[sweep] counts the stages rotated in this sweep
@@ -1002,6 +1032,10 @@ jacobi_kernel(const cplx* __restrict__ theta, long long rs, long long cs,
       if (eps >= 0.0) {
         const double thr = eps * s0;
         double tail = 0.0;
+        // columns the rank-revealing QR left out: their Frobenius mass is the bottom of
+        // the tail (fixed summation order)
+        if (qsrc.on)
+          for (int g = 0; g < qsrc.ntail; ++g) tail += qsrc.tail_part[g];
         keep = 0;
         for (int j = r - 1; j >= 0; --j) {
           const double s = sqrt(fmax(key[j], 0.0));
@@ -1015,7 +1049,8 @@ jacobi_kernel(const cplx* __restrict__ theta, long long rs, long long cs,
       hdr->sweeps = sweeps_done;
       hdr->status = status;
       hdr->rotations = total_rot;
-      for (int k = 0; k < 16; ++k) hdr->phase_cycles[k] = pc[k];
+      if constexpr (PROF)
+        for (int k = 0; k < 16; ++k) hdr->phase_cycles[k] = pc[k];
       info[0] = keep;
       info[1] = sweeps_done;
       info[2] = status;
@@ -1087,37 +1122,128 @@ __global__ void emit_kernel(const cplx* __restrict__ y, const double* __restrict
   }
 }
 
+
 constexpr size_t kDynSmem = (size_t)CHUNK_ROWS * TS * sizeof(cplx) + 2 * PB * PB * sizeof(cplx);
 
-}  // namespace
+// ------------------------------------------------------------------ rank-revealing QR front end
+using b200::qr::QrLayout;
+using b200::qr::QrHeader;
 
-// ============================================================================ C-ABI
-extern "C" size_t b200_svd_workspace_bytes(int m, int n) {
-  if (m <= 0 || n <= 0) return 0;
-  return make_layout(m, n).total;
+struct QrKnobs {
+  int on, minq, cols, phases;
+};
+QrKnobs& qr_knobs() {
+  static QrKnobs k = [] {
+    QrKnobs v;
+    const char* e;
+    v.on = (e = getenv("B200_SVD_QR")) ? atoi(e) : 1;
+    v.minq = (e = getenv("B200_SVD_QR_MINQ")) ? atoi(e) : 48;
+    v.cols = (e = getenv("B200_SVD_QR_COLS")) ? atoi(e) : 4;
+    if (v.cols < 1) v.cols = 1;
+    v.phases = getenv("B200_SVD_PHASES") ? 1 : 0;
+    return v;
+  }();
+  return k;
 }
 
-extern "C" int b200_svd_factor(void* stream_, const void* theta, int m, int n,
-                               int64_t rs, int64_t cs, double eps, void* work,
-                               int32_t* info_host) {
-  return b200_svd_factor2(stream_, theta, m, n, 1, rs, 0, 1, cs, 0, eps, 0.0, work, info_host);
-}
-
-extern "C" int b200_svd_factor2(void* stream_, const void* theta, int m, int n, int rin,
-                                int64_t rso, int64_t rsi, int cin, int64_t cso, int64_t csi,
-                                double eps, double cos_tol, void* work, int32_t* info_host) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  const int64_t rs = rso, cs = cso;
-  if (!theta || !work || !info_host || m <= 0 || n <= 0 || rin < 1 || cin < 1) {
-    b200::set_error("b200_svd_factor: invalid argument");
-    return B200_EINVAL;
+// Workspace of the QR path: [zeroed control words | perm | tau | candidate columns | work
+// copy a (p x q) | workspace of the Jacobi stage on L (q x k, k <= q)].
+QrLayout make_qr_layout(int m, int n) {
+  QrLayout Q;
+  Q.transposed = (m < n) ? 1 : 0;
+  Q.p = Q.transposed ? n : m;
+  Q.q = Q.transposed ? m : n;
+  const int sms = device_sms();
+  int G = (Q.q + qr_knobs().cols - 1) / qr_knobs().cols;
+  if (G > sms) G = sms;
+  if (G < 1) G = 1;
+  Q.G = G;
+  Q.NCmax = (Q.q + G - 1) / G;
+  const size_t col_bytes = (size_t)Q.p * sizeof(cplx);
+  const size_t fixed = col_bytes + (size_t)Q.NCmax * sizeof(double) + (size_t)Q.q + 64;
+  Q.nc_res = 0;
+  if (fixed < (size_t)b200::qr::QR_SMEM_BYTES) {
+    size_t fit = ((size_t)b200::qr::QR_SMEM_BYTES - fixed) / col_bytes;
+    Q.nc_res = (int)((fit > (size_t)Q.NCmax) ? (size_t)Q.NCmax : fit);
   }
-  const Layout L = make_layout(m, n);
+  Q.smem = fixed + (size_t)Q.nc_res * col_bytes;
+  size_t off = 0;
+  Q.header = off; off += 64;
+  Q.cand_val = off; off += sizeof(double) * 2 * (size_t)G;
+  Q.cand_tag = off; off += sizeof(unsigned long long) * 2 * (size_t)G;
+  Q.fro_part = off; off += sizeof(double) * (size_t)G;
+  Q.tail_part = off; off += sizeof(double) * (size_t)G;
+  Q.ctrl_bytes = off;
+  off = align256(off);
+  Q.perm = off; off = align256(off + sizeof(int) * (size_t)Q.q);
+  Q.tau = off; off = align256(off + sizeof(cplx) * (size_t)Q.q);
+  Q.cbuf = off; off = align256(off + sizeof(cplx) * 2 * (size_t)G * Q.p);
+  Q.a = off; off = align256(off + sizeof(cplx) * (size_t)Q.p * Q.q);
+  Q.jac = off;
+  off += make_layout(Q.q, Q.q).total + (size_t)2 * sms * PB * PB * sizeof(cplx);
+  Q.total = off;
+  return Q;
+}
+
+bool qr_eligible(int m, int n, double eps, double cos_tol) {
+  if (!qr_knobs().on || !(eps > 0.0) || cos_tol > 0.0) return false;
+  const int p = (m < n) ? n : m, q = (m < n) ? m : n;
+  if (q < qr_knobs().minq || p > 4096) return false;
+  if ((long long)p > 2LL * q) return false;    // tall sweep operands are full rank at the stop level
+  const size_t fixed = (size_t)p * sizeof(cplx) + 4096 + (size_t)q;
+  return fixed < (size_t)b200::qr::QR_SMEM_BYTES;
+}
+
+// what b200_svd_emit* needs to know about the factorisation that ran in a workspace
+struct Plan {
+  int qr, m, n, k;
+};
+std::mutex g_plan_mu;
+std::unordered_map<const void*, Plan> g_plans;
+
+void plan_set(const void* work, const Plan& pl) {
+  std::lock_guard<std::mutex> g(g_plan_mu);
+  g_plans[work] = pl;
+}
+Plan plan_get(const void* work, int m, int n) {
+  std::lock_guard<std::mutex> g(g_plan_mu);
+  auto it = g_plans.find(work);
+  if (it != g_plans.end() && it->second.m == m && it->second.n == n) return it->second;
+  return Plan{0, m, n, 0};
+}
+
+std::once_flag g_attr_once;
+int g_attr_rc = 0;
+int set_kernel_attributes() {
+  std::call_once(g_attr_once, [] {
+    cudaError_t e = cudaFuncSetAttribute(jacobi_kernel<false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(jacobi_kernel<true>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(b200::qr::qrcp_kernel,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               b200::qr::QR_SMEM_BYTES);
+    if (e != cudaSuccess) {
+      b200::set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      g_attr_rc = B200_ECUDA;
+    }
+  });
+  return g_attr_rc;
+}
+
+// memset + cooperative launch of the Jacobi stage on an (mm x nn) operand whose workspace
+// starts at `base`: either theta (strided) or the L factor of a QRCP (qsrc.on)
+int launch_jacobi(cudaStream_t stream, unsigned char* base, const QrSrc& qsrc, const cplx* th,
+                  int mm, int nn, int rin, long long rs, long long rsi, int cin, long long cs,
+                  long long csi, double eps, double cos_tol, int32_t* info_host,
+                  double flops) {
+  const Layout L = make_layout(mm, nn);
   if (L.nb * BC > 16384) {
     b200::set_error("b200_svd_factor: min(m,n)=%d exceeds 16384", L.q);
     return B200_ESIZE;
   }
-  unsigned char* base = (unsigned char*)work;
   Header* hdr = (Header*)(base + L.header);
   int* ctrl = (int*)(base + L.ctrl);
   double* sig2 = (double*)(base + L.sig2);
@@ -1125,16 +1251,8 @@ extern "C" int b200_svd_factor2(void* stream_, const void* theta, int m, int n, 
   int* perm = (int*)(base + L.perm);
   cplx* gpart = (cplx*)(base + L.gpart);
   cplx* y = (cplx*)(base + L.y);
-
   // header + control words are contiguous: one memset clears both (fro2 = 0, counters = 0)
   B200_CUDA_CHECK(cudaMemsetAsync(base, 0, L.ctrl + L.ctrl_bytes, stream));
-
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200_CUDA_CHECK(cudaFuncSetAttribute(
-        jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmem));
-    attr_set = true;
-  }
   const int ncols = L.nb * BC;
   int npow = 1;
   while (npow < ncols) npow <<= 1;
@@ -1142,12 +1260,10 @@ extern "C" int b200_svd_factor2(void* stream_, const void* theta, int m, int n, 
     b200::set_error("b200_svd_factor: sort buffer exceeds shared memory");
     return B200_ESIZE;
   }
-  const cplx* th = (const cplx*)theta;
-  long long rs_ = rs, cs_ = cs;
   int U = L.U;
   int p = L.p, q = L.q, nb = L.nb, Rx = L.Rx, Rw = L.Rw, RSx = L.RSx, RSw = L.RSw, SE = L.SE,
       tr = L.transposed;
-  int minmn = (m < n) ? m : n;
+  int minmn = (mm < nn) ? mm : nn;
   // relative orthogonality target |cos| <= 1e-11 (singular values are second order in
   // it); never tighter than the rounding level of a length-p dot product
   // (cos_tol > 0 overrides the 1e-11: PT-TEBD multiplies the factors by inverse singular
@@ -1157,7 +1273,6 @@ extern "C" int b200_svd_factor2(void* stream_, const void* theta, int m, int n, 
   if (tol < want) tol = want;
   // columns below 1e-2*eps*||X||_F can never be kept nor change the rank decision
   double neg_rel = (eps > 0.0) ? 1e-2 * eps : 0.0;
-  long long rsi_ = rsi, csi_ = csi;
   // absolute floor of the convergence test, kappa0 * eps_mach * ||X||_F.  TEMPO only needs
   // absolute accuracy (8).  With cos_tol > 0 (PT-TEBD) the factors are later multiplied by
   // inverse singular values, so small kept columns need RELATIVE accuracy: floor 0.01 (pure
@@ -1175,21 +1290,145 @@ extern "C" int b200_svd_factor2(void* stream_, const void* theta, int m, int n, 
   if (L.q < knobs().npass_minq && !knobs().npass_all) npass = 1;
   if (knobs().kappa >= 0.0) kappa0 = knobs().kappa;
   if (knobs().negrel >= 0.0) neg_rel = knobs().negrel * ((eps > 0.0) ? eps : 0.0);
-  void* args[] = {&th, &rs_, &cs_, &y, &gpart, &ctrl, &sig2, &sval, &perm, &hdr,
+  QrSrc qs = qsrc;
+  void* args[] = {&qs, &th, &rs, &cs, &y, &gpart, &ctrl, &sig2, &sval, &perm, &hdr,
                   &info_host, &p, &q, &nb, &Rx, &Rw, &RSx, &RSw, &SE, &tr, &minmn, &tol, &eps,
-                  &neg_rel, &rin, &rsi_, &cin, &csi_, &kappa0, &blkmax, &drop_rel,
+                  &neg_rel, &rin, &rsi, &cin, &csi, &kappa0, &blkmax, &drop_rel,
                   &npass, &U};
   const int grid = L.SE * L.R;
-  b200::profile_begin(stream);
-  B200_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)jacobi_kernel, dim3(grid), dim3(JT),
-                                              args, kDynSmem, stream));
+  void* fn = qr_knobs().phases ? (void*)jacobi_kernel<true> : (void*)jacobi_kernel<false>;
+  b200::profile_begin(stream, 0);
+  B200_CUDA_CHECK(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(JT), args, kDynSmem, stream));
   b200::count_launch();
-  {   // SURVEY 8d convention: 4*(14 m n^2 + 8 n^3) with m >= n
-    const double mm = (double)L.p, nn = (double)L.q;
-    b200::profile_end(stream, 4.0 * (14.0 * mm * nn * nn + 8.0 * nn * nn * nn),
-                      &hdr->sweeps);
-  }
+  b200::profile_end(stream, 0, flops, &hdr->sweeps);
   return B200_OK;
+}
+
+template <int RPT, int C>
+void launch_apply_q(cudaStream_t stream, const b200::qr::ApplyQArgs& A, int threads) {
+  const int blocks = (A.keep + C - 1) / C;
+  b200::qr::apply_q_kernel<RPT, C><<<blocks, threads, 0, stream>>>(A);
+}
+
+int apply_q(cudaStream_t stream, const b200::qr::ApplyQArgs& A) {
+  const int p = A.p;
+  const int rpt = (p <= 256) ? 8 : (p <= 2048 ? 4 : 8);
+  int threads = ((p + rpt - 1) / rpt + 31) & ~31;
+  if (threads < 32) threads = 32;
+  if (threads > 512) {
+    b200::set_error("apply_q: %d rows exceed the supported 4096", p);
+    return B200_ESIZE;
+  }
+  const int sms = device_sms();
+  int c = (A.keep >= 4 * sms) ? 4 : (A.keep >= 2 * sms ? 2 : 1);
+  if (rpt == 4) {
+    if (c == 4) launch_apply_q<4, 4>(stream, A, threads);
+    else if (c == 2) launch_apply_q<4, 2>(stream, A, threads);
+    else launch_apply_q<4, 1>(stream, A, threads);
+  } else {
+    launch_apply_q<8, 1>(stream, A, threads);   // 8 rows per thread: one column fills the registers
+  }
+  B200_LAUNCH_CHECK();
+  return B200_OK;
+}
+
+}  // namespace
+
+// ============================================================================ C-ABI
+extern "C" size_t b200_svd_workspace_bytes(int m, int n) {
+  if (m <= 0 || n <= 0) return 0;
+  size_t need = make_layout(m, n).total;
+  if (qr_eligible(m, n, 1.0, 0.0)) {
+    const size_t nq = make_qr_layout(m, n).total;
+    if (nq > need) need = nq;
+  }
+  return need;
+}
+
+extern "C" int b200_svd_factor(void* stream_, const void* theta, int m, int n,
+                               int64_t rs, int64_t cs, double eps, void* work,
+                               int32_t* info_host) {
+  return b200_svd_factor2(stream_, theta, m, n, 1, rs, 0, 1, cs, 0, eps, 0.0, work, info_host);
+}
+
+extern "C" int b200_svd_factor2(void* stream_, const void* theta, int m, int n, int rin,
+                                int64_t rso, int64_t rsi, int cin, int64_t cso, int64_t csi,
+                                double eps, double cos_tol, void* work, int32_t* info_host) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!theta || !work || !info_host || m <= 0 || n <= 0 || rin < 1 || cin < 1) {
+    b200::set_error("b200_svd_factor: invalid argument");
+    return B200_EINVAL;
+  }
+  {
+    const int rc = set_kernel_attributes();
+    if (rc != B200_OK) return rc;
+  }
+  unsigned char* base = (unsigned char*)work;
+  const cplx* th = (const cplx*)theta;
+  // SURVEY 8d convention: 4*(14 m n^2 + 8 n^3) with m >= n, per truncated SVD whatever the
+  // algorithm; booked on the Jacobi stage
+  const double mm = (double)((m < n) ? n : m), nn = (double)((m < n) ? m : n);
+  const double flops = 4.0 * (14.0 * mm * nn * nn + 8.0 * nn * nn * nn);
+  volatile int32_t* vinfo = info_host;
+  vinfo[4] = -1;
+  if (qr_eligible(m, n, eps, cos_tol)) {
+    const QrLayout Q = make_qr_layout(m, n);
+    B200_CUDA_CHECK(cudaMemsetAsync(base, 0, Q.ctrl_bytes, stream));
+    b200::qr::QrArgs A;
+    A.theta = th; A.rs = rso; A.cs = cso; A.rsi = rsi; A.csi = csi; A.rin = rin; A.cin = cin;
+    A.transposed = Q.transposed; A.p = Q.p; A.q = Q.q;
+    A.a = (cplx*)(base + Q.a);
+    A.cand_val = (double*)(base + Q.cand_val);
+    A.cand_tag = (unsigned long long*)(base + Q.cand_tag);
+    A.fro_part = (double*)(base + Q.fro_part);
+    A.tail_part = (double*)(base + Q.tail_part);
+    A.cbuf = (cplx*)(base + Q.cbuf);
+    A.perm = (int*)(base + Q.perm);
+    A.tauc = (cplx*)(base + Q.tau);
+    A.hdr = (QrHeader*)(base + Q.header);
+    A.info_host = info_host;
+    A.stop_rel = 1e-5 * eps;
+    if (knobs().drop >= 0.0) A.stop_rel = knobs().drop * 1e-2 * eps;
+    A.nc_res = Q.nc_res; A.ncmax = Q.NCmax;
+    void* args[] = {&A};
+    b200::profile_begin(stream, 1);
+    B200_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)b200::qr::qrcp_kernel, dim3(Q.G),
+                                                dim3(b200::qr::QT), args, Q.smem, stream));
+    b200::count_launch();
+    b200::profile_end(stream, 1, 0.0, nullptr);
+    // the pivot count decides the shape of the Jacobi stage: one 4-byte read-back through
+    // pinned memory (spin: ~1 us; a faulted kernel never writes the word)
+    for (uint64_t it = 1;; ++it) {
+      if (vinfo[4] != -1) break;
+      if ((it & 0x3FFF) == 0) {
+        const cudaError_t qe = cudaStreamQuery(stream);
+        if (qe == cudaSuccess) break;
+        if (qe != cudaErrorNotReady) B200_CUDA_CHECK(qe);
+      }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    if (vinfo[4] == -1) B200_CUDA_CHECK(cudaStreamSynchronize(stream));
+    const int k = vinfo[4];
+    if (k < 0 || k > Q.q) {
+      b200::set_error("b200_svd_factor: QRCP returned k = %d", k);
+      return B200_ECUDA;
+    }
+    if (k > 0) {
+      QrSrc qs;
+      qs.a = A.a; qs.perm = A.perm; qs.tail_part = A.tail_part; qs.lda = Q.p;
+      qs.ntail = Q.G; qs.on = 1;
+      plan_set(work, Plan{1, m, n, k});
+      return launch_jacobi(stream, base + Q.jac, qs, nullptr, Q.q, k, 1, 0, 0, 1, 0, 0, eps,
+                           cos_tol, info_host, flops);
+    }
+    // k == 0: a zero operand; the plain path handles it
+  }
+  QrSrc none;
+  none.a = nullptr; none.perm = nullptr; none.tail_part = nullptr; none.lda = 0;
+  none.ntail = 0; none.on = 0;
+  plan_set(work, Plan{0, m, n, 0});
+  return launch_jacobi(stream, base, none, th, m, n, rin, rso, rsi, cin, cso, csi, eps, cos_tol,
+                       info_host, flops);
 }
 
 extern "C" int b200_svd_emit(void* stream_, const void* work, const void* theta, int m,
@@ -1211,23 +1450,74 @@ extern "C" int b200_svd_emit_parts(void* stream_, const void* work, int m, int n
     return B200_EINVAL;
   }
   if (keep == 0) return B200_OK;
-  const Layout L = make_layout(m, n);
+  const Plan pl = plan_get(work, m, n);
   const unsigned char* base = (const unsigned char*)work;
+  if (pl.qr) {
+    const QrLayout Q = make_qr_layout(m, n);
+    const Layout L = make_layout(Q.q, pl.k);
+    const unsigned char* jb = base + Q.jac;
+    if (keep > pl.k) {
+      b200::set_error("b200_svd_emit: keep = %d exceeds the %d computed triplets", keep, pl.k);
+      return B200_EINVAL;
+    }
+    b200::qr::ApplyQArgs A;
+    A.a = (const cplx*)(base + Q.a);
+    A.qperm = (const int*)(base + Q.perm);
+    A.tauc = (const cplx*)(base + Q.tau);
+    A.p = Q.p; A.k = pl.k; A.keep = keep;
+    A.yjac = (const cplx*)(jb + L.y);
+    A.Tj = L.T; A.rowW0 = L.p;
+    A.permJ = (const int*)(jb + L.perm);
+    A.sval = (const double*)(jb + L.sval);
+    A.u_na = u_na; A.u_so = u_so; A.u_sa = u_sa; A.u_sj = u_sj; A.ld = n;
+    A.scale_sigma = vh_unscaled ? 0 : 1;
+    // the Q side: U when X = theta, S*Vh when X = theta^H
+    A.out = (cplx*)(Q.transposed ? svh : u);
+    A.out_mode = Q.transposed ? 1 : 0;
+    b200::profile_begin(stream, 2);
+    if (A.out) {
+      const int rc = apply_q(stream, A);
+      if (rc != B200_OK) return rc;
+    }
+    // the L side (and lambda, 1/lambda)
+    cplx* lout = (cplx*)(Q.transposed ? u : svh);
+    if (lout || lam || inv_lam) {
+      const long long total = (long long)Q.q * keep;
+      int blocks = (int)((total + 255) / 256);
+      if (blocks > 148 * 16) blocks = 148 * 16;
+      if (blocks < 1) blocks = 1;
+      b200::qr::emit_l_kernel<<<blocks, 256, 0, stream>>>(
+          A.yjac, A.Tj, A.permJ, A.sval, A.qperm, Q.q, keep, lout, Q.transposed ? 0 : 1,
+          vh_unscaled, u_na, u_so, u_sa, u_sj, (long long)n, (cplx*)lam, (cplx*)inv_lam);
+      B200_LAUNCH_CHECK();
+    }
+    b200::profile_end(stream, 2, 0.0, nullptr);
+    return B200_OK;
+  }
+  const Layout L = make_layout(m, n);
   const long long total = (long long)(m + n) * keep;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
+  b200::profile_begin(stream, 2);
   emit_kernel<<<blocks, 256, 0, stream>>>(
       (const cplx*)(base + L.y), (const double*)(base + L.sval),
       (const int*)(base + L.perm), m, n, L.p, L.q, L.transposed, keep, (cplx*)u, u_na,
       u_so, u_sa, u_sj, (cplx*)svh, vh_unscaled, (cplx*)lam, (cplx*)inv_lam);
   B200_LAUNCH_CHECK();
+  b200::profile_end(stream, 2, 0.0, nullptr);
   return B200_OK;
 }
 
 extern "C" int b200_svd_phase_cycles(void* stream_, const void* work, long long* out16) {
   if (!work || !out16) { b200::set_error("b200_svd_phase_cycles: invalid argument"); return B200_EINVAL; }
   Header h;
-  B200_CUDA_CHECK(cudaMemcpyAsync(&h, work, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream_));
+  const unsigned char* hb = (const unsigned char*)work;
+  {
+    std::lock_guard<std::mutex> g(g_plan_mu);
+    auto it = g_plans.find(work);
+    if (it != g_plans.end() && it->second.qr) hb += make_qr_layout(it->second.m, it->second.n).jac;
+  }
+  B200_CUDA_CHECK(cudaMemcpyAsync(&h, hb, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream_));
   B200_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream_));
   for (int k = 0; k < 16; ++k) out16[k] = h.phase_cycles[k];
   return B200_OK;
@@ -1239,10 +1529,67 @@ extern "C" int b200_svd_values(void* stream_, const void* work, int m, int n,
     b200::set_error("b200_svd_values: invalid argument");
     return B200_EINVAL;
   }
-  const Layout L = make_layout(m, n);
   const int minmn = (m < n) ? m : n;
+  const Plan pl = plan_get(work, m, n);
+  if (pl.qr) {   // the values below the stop level of the rank-revealing QR are not resolved
+    const QrLayout Q = make_qr_layout(m, n);
+    const Layout L = make_layout(Q.q, pl.k);
+    B200_CUDA_CHECK(cudaMemsetAsync(s_out, 0, sizeof(double) * minmn, (cudaStream_t)stream_));
+    B200_CUDA_CHECK(cudaMemcpyAsync(
+        s_out, (const unsigned char*)work + Q.jac + L.sval, sizeof(double) * pl.k,
+        cudaMemcpyDeviceToDevice, (cudaStream_t)stream_));
+    return B200_OK;
+  }
+  const Layout L = make_layout(m, n);
   B200_CUDA_CHECK(cudaMemcpyAsync(
       s_out, (const unsigned char*)work + L.sval, sizeof(double) * minmn,
       cudaMemcpyDeviceToDevice, (cudaStream_t)stream_));
+  return B200_OK;
+}
+
+/* QR-path diagnostics of the factorisation that last ran in `work`: out4 = {qr used (0/1),
+ * pivots k above the stop level, CTAs of the QRCP grid, columns resident in shared memory} */
+extern "C" int b200_svd_plan(const void* work, int m, int n, int32_t* out4) {
+  if (!work || !out4) { b200::set_error("b200_svd_plan: invalid argument"); return B200_EINVAL; }
+  const Plan pl = plan_get(work, m, n);
+  out4[0] = pl.qr; out4[1] = pl.k; out4[2] = 0; out4[3] = 0;
+  if (pl.qr) {
+    const QrLayout Q = make_qr_layout(m, n);
+    out4[2] = Q.G; out4[3] = Q.nc_res;
+  }
+  return B200_OK;
+}
+
+/* test / diagnostic access to the QR-path workspace: byte offsets of its arrays.
+ * out16 = {eligible, p, q, transposed, G, nc_res, off perm, off tau, off a, off jac,
+ *          off header, off tail_part, smem bytes, 0, 0, 0}; with k (pivots) > 0 also
+ * out16[13..15] = byte offsets (from the start of `work`) of the Jacobi stage's y, sval, perm */
+extern "C" int b200_svd_qr_layout(int m, int n, int k, int64_t* out16) {
+  if (!out16 || m <= 0 || n <= 0) { b200::set_error("b200_svd_qr_layout: invalid argument"); return B200_EINVAL; }
+  for (int i = 0; i < 16; ++i) out16[i] = 0;
+  if (!qr_eligible(m, n, 1.0, 0.0)) return B200_OK;
+  const QrLayout Q = make_qr_layout(m, n);
+  out16[0] = 1; out16[1] = Q.p; out16[2] = Q.q; out16[3] = Q.transposed; out16[4] = Q.G;
+  out16[5] = Q.nc_res; out16[6] = (int64_t)Q.perm; out16[7] = (int64_t)Q.tau;
+  out16[8] = (int64_t)Q.a; out16[9] = (int64_t)Q.jac; out16[10] = (int64_t)Q.header;
+  out16[11] = (int64_t)Q.tail_part; out16[12] = (int64_t)Q.smem;
+  if (k > 0 && k <= Q.q) {
+    const Layout L = make_layout(Q.q, k);
+    out16[13] = (int64_t)(Q.jac + L.y); out16[14] = (int64_t)(Q.jac + L.sval);
+    out16[15] = (int64_t)(Q.jac + L.perm);
+  }
+  return B200_OK;
+}
+
+/* runtime switches of the truncated SVD (tests, tools, A/B measurements): key "qr" (0/1: use
+ * the rank-revealing QR front end), "qr_minq" (smallest min(m,n) that takes it), "qr_cols"
+ * (target columns per CTA of the QR grid).  Not thread-safe against concurrent factorisations. */
+extern "C" int b200_svd_config(const char* key, double value) {
+  if (!key) { b200::set_error("b200_svd_config: invalid argument"); return B200_EINVAL; }
+  const std::string k(key);
+  if (k == "qr") qr_knobs().on = (value != 0.0);
+  else if (k == "qr_minq") qr_knobs().minq = (int)value;
+  else if (k == "qr_cols") qr_knobs().cols = (value < 1.0) ? 1 : (int)value;
+  else { b200::set_error("b200_svd_config: unknown key %s", key); return B200_EINVAL; }
   return B200_OK;
 }

@@ -29,7 +29,7 @@ def test_header_symbols_are_exported():
         assert hasattr(lib, name), name
     assert sorted(_lib.EXPORTS) == names
     _lib.load_library()
-    assert _lib.load_library().b200_abi_version() == 1
+    assert _lib.load_library().b200_abi_version() == 2
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only check")
