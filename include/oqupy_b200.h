@@ -142,6 +142,10 @@ int b200_svd_config(const char* key, double value);
  * for all partials, 4 reduce + convergence test, 5 inner 32x32 sweep, 6 sort + publish
  * J, 7 apply + hand-over, 8 sweep vote, 9 norms/rank, 10..14 spare, 15 #stages} */
 int b200_svd_phase_cycles(void* stream, const void* work, long long* out16);
+/* the same for the rank-revealing QR stage: {0 offer the best column, 1 wait for all offers,
+ * 2 select the panel, 3 fetch it, 4 factorise it, 5 file the pivot columns, 6 apply the
+ * reflectors to the CTA's own columns, 7 #hand-shakes} */
+int b200_svd_qr_phase_cycles(void* stream, const void* work, long long* out8);
 
 /* ---------------------------------------------------------------------------
  * Native matrix-product chain: the device-resident counterpart of NodeArray for the
@@ -248,6 +252,37 @@ int b200_dyn_run(void* stream, int nsteps, int nvec, int d2, const int32_t* chi,
 /* cap_k[l] = sum_{r,x} T[l,r,x] * cap_next[r] * tr2[x]   (oqupy/process_tensor.py:380-406) */
 int b200_caps_step(void* stream, int chi_l, int chi_r, int d2, const void* t,
                    const void* cap_next, const void* tr2, void* cap_out);
+
+/* ---------------------------------------------------------------------------
+ * Lock-step TEMPO ensemble: E independent TEMPO runs (same d2, dkmax, epsrel; different
+ * influence matrices / propagators / initial states) advance one time step per call with
+ * ONE kernel launch -- one CTA per member runs BaseTempoBackend.compute_system_step
+ * (oqupy/backends/tempo_backend.py:439-575) for its member entirely on the device (chain in
+ * capacity-padded device slots, shapes on the device, every truncated SVD in shared memory:
+ * stopped column-pivoted QR + one-sided Jacobi on R + the reference's tail-norm rule).  The
+ * loop it replaces is the ensemble of oqupy.Tempo(...).compute() calls of BASELINE configs[4]
+ * (oqupy/tempo.py:479-484 per member) and MeanFieldTempoBackend's per-system loop
+ * (tempo_backend.py:747-773).  chi_cap bounds the bond dimension (chi_cap * d2 <= 104).
+ *
+ * b200_tempo_batch_set (device pointers, complex128, member-major):
+ *   mid, start (E, dkmax+1, d2, d2): infl[dk][s,e] and infl[dk][s,e]*sum_west[e]
+ *   (tempo_backend.py:419,426,519); dense0 (E, d2*d2, d2*d2): the dk = 0 site incl. the
+ *   unitary transform as [(w,n),(s,e)] (:419-424); dense0w (E, d2, d2*d2): its west leg summed;
+ *   sum_north (d2); state0 (E, d2).
+ * b200_tempo_batch_step: p1 (E, d2, d2) = prop_1, p2t (E, d2, d2) = prop_2^T of this step;
+ *   states_out (E, d2) device or NULL.
+ * b200_tempo_batch_info (host arrays, synchronises): per member status (0 ok, 2 capacity
+ *   exceeded, 3 no convergence, >= 4 internal), truncated SVDs, Jacobi sweeps, largest bond
+ *   dimension; bonds[e*(dkmax+2) + i] = bond dimensions of the chain (-1 padded). */
+void* b200_tempo_batch_create(void* stream, int n_members, int d2, int dkmax, int chi_cap,
+                              double epsrel);
+int b200_tempo_batch_destroy(void* batch);
+int b200_tempo_batch_set(void* batch, const void* mid, const void* start, const void* dense0,
+                         const void* dense0w, const void* sum_north, const void* state0);
+int b200_tempo_batch_step(void* batch, const void* p1, const void* p2t, void* states_out);
+int b200_tempo_batch_info(void* batch, int32_t* status, int32_t* svds, int32_t* sweeps,
+                          int32_t* max_chi, int32_t* bonds);
+size_t b200_tempo_batch_bytes(void* batch);
 
 #ifdef __cplusplus
 }

@@ -11,8 +11,9 @@ from .tebd import PtTebdBackend
 from .process_tensor import (DeviceProcessTensor, dynamics_device, gradient_device,
                              import_process_tensor)
 from ._lib import B200Error, CudaOps, default_ops, load_library
+from .batch import BatchedTempoBackend
 
-__all__ = ["BaseTempoBackend", "MeanFieldTempoBackend", "PtTempoBackend", "TempoBackend",
+__all__ = ["BatchedTempoBackend", "BaseTempoBackend", "MeanFieldTempoBackend", "PtTempoBackend", "TempoBackend",
            "PtTebdBackend",
            "DeviceProcessTensor", "dynamics_device", "gradient_device",
            "import_process_tensor", "B200Error", "CudaOps",

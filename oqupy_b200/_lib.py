@@ -19,12 +19,14 @@ EXPORTS = [
     "b200_profile_enable", "b200_profile_read",
     "b200_zgemm_strided", "b200_svd_workspace_bytes", "b200_svd_factor",
     "b200_svd_emit", "b200_svd_factor2", "b200_svd_emit_parts", "b200_svd_values",
-    "b200_svd_phase_cycles", "b200_svd_plan", "b200_svd_qr_layout", "b200_svd_config", "b200_profile_read_kinds", "b200_dyn_workspace_bytes",
+    "b200_svd_phase_cycles", "b200_svd_qr_phase_cycles", "b200_svd_plan", "b200_svd_qr_layout", "b200_svd_config", "b200_profile_read_kinds", "b200_dyn_workspace_bytes",
     "b200_dyn_step", "b200_caps_step", "b200_dyn_run", "b200_dyn_run_workspace_bytes",
     "b200_chain_create", "b200_chain_destroy", "b200_chain_len", "b200_chain_push",
     "b200_chain_shape", "b200_chain_read", "b200_chain_svd_sweep",
     "b200_chain_pt_zip_up_left", "b200_chain_tempo_step", "b200_chain_stats",
     "b200_chain_log",
+    "b200_tempo_batch_create", "b200_tempo_batch_destroy", "b200_tempo_batch_set",
+    "b200_tempo_batch_step", "b200_tempo_batch_info", "b200_tempo_batch_bytes",
 ]
 
 
@@ -95,6 +97,8 @@ def load_library():
                                         c_void_p, c_void_p]
     lib.b200_svd_phase_cycles.restype = c_int
     lib.b200_svd_phase_cycles.argtypes = [c_void_p, c_void_p, c_void_p]
+    lib.b200_svd_qr_phase_cycles.restype = c_int
+    lib.b200_svd_qr_phase_cycles.argtypes = [c_void_p, c_void_p, c_void_p]
     lib.b200_svd_values.restype = c_int
     lib.b200_svd_values.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p]
     lib.b200_svd_plan.restype = c_int
@@ -144,6 +148,18 @@ def load_library():
                                      POINTER(c_uint64), c_int]
     lib.b200_chain_log.restype = c_int
     lib.b200_chain_log.argtypes = [c_void_p, c_int, POINTER(c_int32), c_int]
+    lib.b200_tempo_batch_create.restype = c_void_p
+    lib.b200_tempo_batch_create.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_double]
+    lib.b200_tempo_batch_destroy.restype = c_int
+    lib.b200_tempo_batch_destroy.argtypes = [c_void_p]
+    lib.b200_tempo_batch_set.restype = c_int
+    lib.b200_tempo_batch_set.argtypes = [c_void_p] * 7
+    lib.b200_tempo_batch_step.restype = c_int
+    lib.b200_tempo_batch_step.argtypes = [c_void_p] * 4
+    lib.b200_tempo_batch_info.restype = c_int
+    lib.b200_tempo_batch_info.argtypes = [c_void_p] + [POINTER(c_int32)] * 5
+    lib.b200_tempo_batch_bytes.restype = c_size_t
+    lib.b200_tempo_batch_bytes.argtypes = [c_void_p]
     _lib = lib
     return lib
 
@@ -297,6 +313,12 @@ class CudaOps:
                 "a": arr(o[8], p * q, np.complex128).reshape(q, p).T,
                 "tail2": float(arr(o[11], grid, np.float64).sum()),
                 "sval": arr(o[14], k, np.float64)}
+
+    def svd_qr_phase_cycles(self, h):
+        out = (ctypes.c_longlong * 8)()
+        self._check(self.lib.b200_svd_qr_phase_cycles(self._stream(), h.work.data_ptr(), out),
+                    "b200_svd_qr_phase_cycles")
+        return list(out)
 
     def svd_values(self, h):
         k = min(h.m, h.n)

@@ -5,6 +5,6 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 $NVCC -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 \
   -Xcompiler -fPIC -shared ${NVCC_EXTRA} \
-  common.cu zgemm.cu svd.cu dyn.cu chain.cu \
+  common.cu zgemm.cu svd.cu dyn.cu chain.cu batch.cu \
   -o ../liboqupy_b200.so
 echo "built $(cd .. && pwd)/liboqupy_b200.so"

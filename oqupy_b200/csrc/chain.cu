@@ -86,7 +86,7 @@ int dev_alloc(Chain* c, cplx** out, size_t n) {
       }
     }
     // no room: add a chunk (a rare, synchronous cudaMalloc), at most 10 of them
-    if (attempt || c->next_arena_bytes == 0 || c->arenas.size() >= 10) break;
+    if (attempt || c->next_arena_bytes == 0 || c->arenas.size() >= 16) break;
     size_t want = c->next_arena_bytes;
     while (want < 2 * bytes) want *= 2;
     void* p = nullptr;
@@ -94,7 +94,8 @@ int dev_alloc(Chain* c, cplx** out, size_t n) {
     Arena a;
     a.init((char*)p, want);
     c->arenas.push_back(a);
-    c->next_arena_bytes = want * 2;
+    // every new chunk is a blocking cudaMalloc: grow fast (x4) up to 16 GB chunks
+    c->next_arena_bytes = (want >= ((size_t)16 << 30)) ? want : want * 4;
   }
   B200_CUDA_CHECK(cudaMallocAsync((void**)out, bytes, c->stream));
   return B200_OK;
@@ -142,7 +143,7 @@ int split(Chain* c, const cplx* theta, int m, int n, int64_t rs, int64_t cs, dou
     if (c->work) B200_CUDA_CHECK(cudaFree(c->work));
     c->work = nullptr;
     c->work_bytes = 0;
-    const size_t want = need + need / 4;
+    const size_t want = 2 * need;       // geometric growth: a reallocation synchronises
     B200_CUDA_CHECK(cudaMalloc(&c->work, want));
     c->work_bytes = want;
   }

@@ -37,12 +37,14 @@ constexpr int QR_MAX_P = 8192;        // rows (apply_q keeps p / threads <= 8 ro
 struct QrHeader {
   int k, status;
   double fro2, stop2;
+  long long phase_cycles[8];  // CTA 0 (PROF): 0 offer, 1 poll wait, 2 select, 3 fetch, 4 panel,
+                              // 5 file pivots, 6 apply, 7 hand-shakes
 };
 
 struct QrLayout {
-  size_t header, cand_val, cand_tag, fro_part, tail_part, ctrl_bytes;   // zeroed region first
+  size_t header, cand_tag, fro_part, tail_part, ctrl_bytes;   // zeroed region first
   size_t perm, tau, cbuf, a, jac, total;
-  int p, q, G, NCmax, nc_res, transposed;
+  int p, q, G, NCmax, nc_res, transposed, panel;
   size_t smem;
 };
 
@@ -71,8 +73,9 @@ struct QrArgs {
   int rin, cin, transposed;
   int p, q;
   cplx* a;                    // p x q column-major work copy / result (lda = p)
-  double* cand_val;           // [2][G]
-  unsigned long long* cand_tag;  // [2][G]: (epoch << 32) | physical column
+  unsigned long long* cand_tag;  // [2][G] x TAG_STRIDE words (one 128-byte line per offer: G
+                                 // CTAs poll G words each, on one line that is an L2 hot spot):
+                                 // norm^2 (top 35 bits) | hand-shake (15) | column (14)
   double* fro_part;           // [G]
   double* tail_part;          // [G]
   cplx* cbuf;                 // [2][G][p] speculatively published candidate columns
@@ -81,9 +84,14 @@ struct QrArgs {
   QrHeader* hdr;
   int32_t* info_host;         // pinned; info_host[4] <- k
   double stop_rel;            // stop = stop_rel * ||X||_F
+  double theta2;              // panel acceptance: remaining norm^2 > theta2 * best offer outside
   int nc_res;                 // local columns resident in shared memory
   int ncmax;
+  int panel;                  // pivots taken per hand-shake, at most (<= PBMAX)
 };
+
+constexpr int PBMAX = 8;
+constexpr int TAG_STRIDE = 16;   // 64-bit words between two offers
 
 // theta element (i, j) of the ORIGINAL m x n operand
 __device__ __forceinline__ cplx theta_at(const QrArgs& A, int i, int j) {
@@ -91,21 +99,43 @@ __device__ __forceinline__ cplx theta_at(const QrArgs& A, int i, int j) {
                  (long long)(j / A.cin) * A.cs + (long long)(j % A.cin) * A.csi];
 }
 
+// One grid-wide hand-shake selects a PANEL of up to `panel` pivots: every CTA offers its best
+// remaining column; the largest offers (different CTAs) are fetched by everybody and
+// factorised redundantly -- greedy pivoting inside the panel on the exact remaining norms, a
+// panel column is only taken while its remaining norm^2 stays above theta2 x the best offer
+// left outside the panel (and above the stop level); the others simply stay ordinary columns
+// of their CTAs.  (CPU study tools/study_panel.py: theta = 0.5 keeps the sweep count of the
+// Jacobi stage at that of strict column pivoting with 3-4 pivots per hand-shake; theta = 0
+// doubles it.)  Then every CTA applies the taken reflectors to its own columns, one warp per
+// column, no CTA barrier inside, and accumulates their exact remaining norms.
+template <bool PROF>
 __global__ void __launch_bounds__(QT, 1) qrcp_kernel(const QrArgs A) {
   extern __shared__ __align__(16) unsigned char qsm[];
+  long long pc[PROF ? 8 : 1];
+  long long tq = 0;
+  if constexpr (PROF) {
+#pragma unroll
+    for (int k_ = 0; k_ < 8; ++k_) pc[k_] = 0;
+    tq = clock64();
+  }
+#define QPHASE(k) if constexpr (PROF) { const long long tn_ = clock64(); pc[k] += tn_ - tq; tq = tn_; }
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = gridDim.x, me = blockIdx.x;
   const int p = A.p, q = A.q;
   const int NC = (q - me + G - 1) / G;          // my local columns: c = me + lc * G
-  cplx* vb = reinterpret_cast<cplx*>(qsm);                       // [p] reflector
-  cplx* scols = vb + p;                                          // [nc_res][p]
+  const int PB = A.panel;
+  cplx* pan = reinterpret_cast<cplx*>(qsm);                      // [PB][p] panel / reflectors
+  cplx* scols = pan + (size_t)PB * p;                            // [nc_res][p]
   double* vn2 = reinterpret_cast<double*>(scols + (size_t)A.nc_res * p);   // [ncmax]
   unsigned char* done = reinterpret_cast<unsigned char*>(vn2 + A.ncmax);   // [q]
   __shared__ cplx s_dot[QW];
-  __shared__ double s_nrm[QW];
-  __shared__ double s_red[QW];
-  __shared__ int s_bl, s_widx, s_wcta;
-  __shared__ double s_best, s_wval, s_stop2;
+  __shared__ double s_pn[QW];
+  __shared__ int s_bl;
+  __shared__ double s_best, s_stop2, s_outside;
+  __shared__ int s_np, s_pidx[PBMAX], s_pcta[PBMAX];
+  __shared__ int s_tslot[PBMAX];          // panel slot taken as pivot t
+  __shared__ cplx s_tau[PBMAX], s_scale[PBMAX];
+  __shared__ double s_beta[PBMAX];
 
   auto colptr = [&](int lc) -> cplx* {
     return (lc < A.nc_res) ? scols + (size_t)lc * p : A.a + (size_t)(me + lc * G) * p;
@@ -113,7 +143,6 @@ __global__ void __launch_bounds__(QT, 1) qrcp_kernel(const QrArgs A) {
 
   for (int c = tid; c < q; c += QT) done[c] = 0;
   // ---- load my columns (X = theta or theta^H), exact norms
-  double my_fro = 0.0;
   for (int lc = warp; lc < NC; lc += QW) {
     const int c = me + lc * G;
     cplx* col = colptr(lc);
@@ -130,21 +159,15 @@ __global__ void __launch_bounds__(QT, 1) qrcp_kernel(const QrArgs A) {
   }
   __syncthreads();
   if (tid == 0) {
+    double my_fro = 0.0;
     for (int lc = 0; lc < NC; ++lc) my_fro += vn2[lc];     // fixed order
     A.fro_part[me] = my_fro;
     s_stop2 = 0.0;
   }
 
-  // warps per column in the apply pass
-  int W = 1;
-  if (NC <= 1) W = 16; else if (NC <= 2) W = 8; else if (NC <= 4) W = 4; else if (NC <= 8) W = 2;
-  const int slots = QW / W;
-  const int my_slot = warp / W, my_part = warp % W;
-
   int j = 0;
-  for (; j < q; ++j) {
-    const int par = j & 1;
-    const unsigned epoch = (unsigned)(j + 1);
+  for (unsigned shake = 1; j < q; ++shake) {
+    const int par = shake & 1;
     // ---- A. my best remaining column
     if (warp == 0) {
       double best = -1.0;
@@ -160,11 +183,10 @@ __global__ void __launch_bounds__(QT, 1) qrcp_kernel(const QrArgs A) {
         const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
         if (ov > best || (ov == best && ol < bl)) { best = ov; bl = ol; }
       }
-      if (lane == 0) { s_bl = (best >= 0.0) ? bl : -1; s_best = best; }
+      if (lane == 0) { s_bl = (best >= 0.0) ? bl : -1; s_best = (best >= 0.0) ? best : 0.0; }
     }
     __syncthreads();
-    // ---- B. publish it (rows j..p-1) and announce: the release-store of the tag is the
-    //         arrival flag of this CTA for pivot j
+    // ---- B. offer it (rows j..p-1); the release-store of the tag is this CTA's arrival
     const int bl = s_bl;
     if (bl >= 0) {
       const cplx* col = colptr(bl);
@@ -173,47 +195,40 @@ __global__ void __launch_bounds__(QT, 1) qrcp_kernel(const QrArgs A) {
     }
     __syncthreads();
     if (tid == 0) {
-      A.cand_val[par * G + me] = s_best;
-      __threadfence();
-      const unsigned idx = (bl >= 0) ? (unsigned)(me + bl * G) : 0x7fffffffu;
-      st_release_u64(A.cand_tag + par * G + me, ((unsigned long long)epoch << 32) | idx);
+      const unsigned long long vb35 =
+          ((unsigned long long)__double_as_longlong(s_best) >> 29) << 29;
+      const unsigned long long idx = (bl >= 0) ? (unsigned long long)(me + bl * G) : 0x3fffull;
+      st_release_u64(A.cand_tag + (size_t)(par * G + me) * TAG_STRIDE,
+                     vb35 | ((unsigned long long)(shake & 0x7fffu) << 14) | idx);
     }
-    // ---- C. poll all G records, pick the pivot (largest norm, lowest column on ties)
+    QPHASE(0)
+    // ---- C. poll the G offers; the PB largest above the stop level form the panel
     if (warp == 0) {
-      double b = -2.0;
-      unsigned bi = 0xffffffffu;
-      int bc = 0;
-      for (int g0 = 0; g0 < G; g0 += 128) {
-        unsigned long long tag[4];
-        bool ok;
-        do {
-          ok = true;
+      unsigned long long key[5];       // norm^2 (35 bits) | 0x3fff - column (14) | CTA (8)
+      unsigned pending = 0u;
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int g = g0 + u * 32 + lane;
-            tag[u] = (g < G) ? ld_acquire_u64(A.cand_tag + par * G + g)
-                             : ((unsigned long long)epoch << 32);
-            ok = ok && ((unsigned)(tag[u] >> 32) == epoch);
-          }
-        } while (!ok);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int g = g0 + u * 32 + lane;
-          if (g < G) {
-            const double v = __ldcg(A.cand_val + par * G + g);
-            const unsigned vi = (unsigned)(tag[u] & 0xffffffffu);
-            if (v > b || (v == b && vi < bi)) { b = v; bi = vi; bc = g; }
-          }
-        }
+      for (int u = 0; u < 5; ++u) {
+        key[u] = 0ull;
+        if (u * 32 + lane < G) pending |= 1u << u;
       }
+      while (pending) {                // re-read only the offers that have not arrived yet
+        unsigned long long tag[5];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const double ov = __shfl_xor_sync(0xffffffffu, b, o);
-        const unsigned oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
-        if (ov > b || (ov == b && oi < bi)) { b = ov; bi = oi; bc = oc; }
+        for (int u = 0; u < 5; ++u)
+          if (pending & (1u << u))
+            tag[u] = ld_acquire_u64(A.cand_tag + (size_t)(par * G + u * 32 + lane) * TAG_STRIDE);
+#pragma unroll
+        for (int u = 0; u < 5; ++u)
+          if ((pending & (1u << u)) &&
+              (((unsigned)(tag[u] >> 14) & 0x7fffu) == (shake & 0x7fffu))) {
+            const unsigned long long idx = tag[u] & 0x3fffull;
+            key[u] = ((tag[u] >> 29) << 22) | ((0x3fffull - idx) << 8) |
+                     (unsigned long long)(u * 32 + lane);
+            pending &= ~(1u << u);
+          }
       }
-      if (j == 0) {             // ||X||_F^2: every CTA sums the G partials in the same order
+      QPHASE(1)
+      if (shake == 1) {         // ||X||_F^2: every CTA sums the G partials in the same order
         double f = 0.0;
         for (int g = lane; g < G; g += 32) f += __ldcg(A.fro_part + g);
         f = warp_sum(f);
@@ -222,66 +237,123 @@ __global__ void __launch_bounds__(QT, 1) qrcp_kernel(const QrArgs A) {
           if (me == 0) { A.hdr->fro2 = f; A.hdr->stop2 = s_stop2; }
         }
       }
-      if (lane == 0) { s_wval = b; s_widx = (int)bi; s_wcta = bc; }
-    }
-    __syncthreads();
-    if (!(s_wval > s_stop2)) break;       // same records everywhere: uniform exit
-    const int widx = s_widx, wcta = s_wcta;
-    // ---- D. the pivot column -> shared memory, its Householder reflector (zlarfg)
-    {
-      const cplx* src = A.cbuf + ((size_t)par * G + wcta) * p;
-      double acc = 0.0;
-      for (int i = j + tid; i < p; i += QT) {
-        const cplx x = ldcg_c(src + i);
-        vb[i] = x;
-        if (i > j) { acc = fma(x.x, x.x, acc); acc = fma(x.y, x.y, acc); }
-      }
-      acc = warp_sum(acc);
-      if (lane == 0) s_red[warp] = acc;
-    }
-    __syncthreads();
-    double xnorm2 = 0.0;
+      __syncwarp();
+      const double stop2 = s_stop2;
+      int np = 0;
+      double outside = 0.0;
+      for (int t = 0; t <= PB; ++t) {
+        unsigned long long m = 0ull;
 #pragma unroll
-    for (int w = 0; w < QW; ++w) xnorm2 += s_red[w];
-    const cplx alpha = vb[j];
-    double beta = alpha.x;
-    cplx tau = make_double2(0.0, 0.0), scale = make_double2(0.0, 0.0);
-    if (xnorm2 > 0.0 || alpha.y != 0.0) {
-      const double an = sqrt(fma(alpha.x, alpha.x, fma(alpha.y, alpha.y, xnorm2)));
-      beta = (alpha.x >= 0.0) ? -an : an;
-      tau = make_double2((beta - alpha.x) / beta, -alpha.y / beta);
-      const double dx = alpha.x - beta, dy = alpha.y;
-      const double dn = 1.0 / fma(dx, dx, dy * dy);
-      scale = make_double2(dx * dn, -dy * dn);
+        for (int u = 0; u < 5; ++u) m = (key[u] > m) ? key[u] : m;
+        {   // warp maximum of a 57-bit key: two 32-bit hardware reductions
+          const unsigned hi = __reduce_max_sync(0xffffffffu, (unsigned)(m >> 32));
+          const unsigned lo = __reduce_max_sync(
+              0xffffffffu, ((unsigned)(m >> 32) == hi) ? (unsigned)(m & 0xffffffffull) : 0u);
+          m = ((unsigned long long)hi << 32) | lo;
+        }
+        const double val = __longlong_as_double((long long)((m >> 22) << 29));
+        if (!(val > stop2)) break;
+        if (t == PB) { outside = val; break; }
+#pragma unroll
+        for (int u = 0; u < 5; ++u)
+          if (key[u] == m) key[u] = 0ull;          // keys are unique (CTA field)
+        if (lane == 0) {
+          s_pidx[t] = (int)(0x3fffull - ((m >> 8) & 0x3fffull));
+          s_pcta[t] = (int)(m & 0xffull);
+        }
+        np = t + 1;
+      }
+      if (lane == 0) { s_np = np; s_outside = outside; }
     }
-    __syncthreads();                      // everybody has read vb[j]
-    for (int i = j + 1 + tid; i < p; i += QT) vb[i] = cmul(vb[i], scale);
-    if (tid == 0) { vb[j] = make_double2(1.0, 0.0); done[widx] = 1; }
     __syncthreads();
-    // ---- E. the owner files the pivot column: R[0..j, j], then the reflector
-    if (me == wcta) {
-      const int lcw = (widx - me) / G;
-      cplx* gcol = A.a + (size_t)widx * p;
-      if (lcw < A.nc_res) {
-        const cplx* col = colptr(lcw);
-        for (int i = tid; i < j; i += QT) gcol[i] = col[i];
-      }
-      for (int i = j + 1 + tid; i < p; i += QT) gcol[i] = vb[i];
-      if (tid == 0) {
-        gcol[j] = make_double2(beta, 0.0);
-        A.perm[j] = widx;
-        A.tauc[j] = tau;
+    const int np = s_np;
+    QPHASE(2)
+    if (np == 0) break;                   // same offers everywhere: uniform exit
+    // ---- D. fetch the panel columns (rows j..p-1): all loads of a batch in flight at once
+    {
+      const int len = p - j, total = np * len;
+      for (int e0 = tid; e0 < total; e0 += 4 * QT) {
+        cplx v[4];
+        int dsto[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = e0 + u * QT;
+          dsto[u] = -1;
+          if (e < total) {
+            const int t = e / len, i = j + (e - t * len);
+            v[u] = ldcg_c(A.cbuf + ((size_t)par * G + s_pcta[t]) * p + i);
+            dsto[u] = t * p + i;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (dsto[u] >= 0) pan[dsto[u]] = v[u];
       }
     }
-    // ---- F. y <- (I - conj(tau) v v^H) y on my remaining columns; exact new norms
-    const cplx ctau = cconj(tau);
-    for (int base = 0; base < NC; base += slots) {
-      const int lc = base + my_slot;
-      const bool act = (lc < NC) && !done[me + lc * G];
-      cplx* col = act ? colptr(lc) : nullptr;
+    __syncthreads();
+    QPHASE(3)
+    // ---- E. factorise the panel (every CTA, bit-identical): greedy pivoting inside it
+    const double thr = fmax(s_stop2, A.theta2 * s_outside);
+    unsigned rem = (1u << np) - 1u;       // panel slots not yet taken
+    int bt = 0;
+    {
+      // remaining norms^2 over rows > j of every panel column: two warps per column
+      const int c = warp >> 1, half = warp & 1;
+      double nn = 0.0;
+      if (c < np) {
+        const cplx* x = pan + (size_t)c * p;
+        for (int i = j + 1 + half * 32 + lane; i < p; i += 64) {
+          const cplx v = x[i];
+          nn = fma(v.x, v.x, nn); nn = fma(v.y, v.y, nn);
+        }
+        nn = warp_sum(nn);
+      }
+      if (lane == 0) s_pn[warp] = nn;
+    }
+    __syncthreads();
+    for (int t = 0; t < np; ++t) {
+      const int row = j + t;
+      // best remaining panel column by its full remaining norm (rows >= row)
+      int bc = -1;
+      double bfull = -1.0;
+      for (int c = 0; c < np; ++c)
+        if (rem & (1u << c)) {
+          const cplx al = pan[(size_t)c * p + row];
+          const double full = s_pn[2 * c] + s_pn[2 * c + 1] + fma(al.x, al.x, al.y * al.y);
+          if (full > bfull) { bfull = full; bc = c; }
+        }
+      if (t > 0 && !(bfull > thr)) break;
+      rem &= ~(1u << bc);
+      // the reflector stays UNSCALED in shared memory: v = [1 ; scale * x], H = I - tau v v^H
+      const cplx* x0 = pan + (size_t)bc * p;
+      const cplx alpha = x0[row];
+      const double xnorm2 = s_pn[2 * bc] + s_pn[2 * bc + 1];
+      double beta = alpha.x;
+      cplx tau = make_double2(0.0, 0.0), scale = make_double2(0.0, 0.0);
+      if (xnorm2 > 0.0 || alpha.y != 0.0) {
+        const double an = sqrt(fma(alpha.x, alpha.x, fma(alpha.y, alpha.y, xnorm2)));
+        beta = (alpha.x >= 0.0) ? -an : an;
+        const double ib = 1.0 / beta;
+        tau = make_double2((beta - alpha.x) * ib, -alpha.y * ib);
+        const double dx = alpha.x - beta, dy = alpha.y;
+        const double dn = 1.0 / fma(dx, dx, dy * dy);
+        scale = make_double2(dx * dn, -dy * dn);
+      }
+      if (tid == 0) {
+        s_tslot[t] = bc; s_tau[t] = tau; s_beta[t] = beta; s_scale[t] = scale;
+      }
+      bt = t + 1;
+      if (rem == 0u || t + 1 >= np) break;
+      // apply H^H to the remaining panel columns (two warps per column), new norms over
+      // rows > row + 1:  w = v^H y = y_row + conj(scale) sum_{i>row} conj(x_i) y_i
+      const int c = warp >> 1, half = warp & 1;
+      const bool act = (c < np) && (rem & (1u << c));
+      cplx* y = pan + (size_t)c * p;
       cplx w = make_double2(0.0, 0.0);
+      cplx yr = make_double2(0.0, 0.0);
       if (act) {
-        for (int i = j + my_part * 32 + lane; i < p; i += W * 32) w = cfma(cconj(vb[i]), col[i], w);
+        yr = y[row];                    // read by both warps BEFORE the barrier, rewritten after
+        for (int i = row + 1 + half * 32 + lane; i < p; i += 64) w = cfma(cconj(x0[i]), y[i], w);
         w.x = warp_sum(w.x);
         w.y = warp_sum(w.y);
       }
@@ -289,31 +361,94 @@ __global__ void __launch_bounds__(QT, 1) qrcp_kernel(const QrArgs A) {
       __syncthreads();
       double nn = 0.0;
       if (act) {
-        cplx tot = make_double2(0.0, 0.0);
-        for (int u = 0; u < W; ++u) {           // fixed order
-          const cplx d = s_dot[my_slot * W + u];
-          tot.x += d.x; tot.y += d.y;
+        const cplx d0 = s_dot[2 * c], d1 = s_dot[2 * c + 1];
+        cplx tot = cmul(cconj(scale), make_double2(d0.x + d1.x, d0.y + d1.y));
+        tot.x += yr.x; tot.y += yr.y;
+        const cplx f = cmul(cconj(tau), tot);          // y -= f v
+        const cplx fs = cmul(f, scale);
+        for (int i = row + 1 + half * 32 + lane; i < p; i += 64) {
+          const cplx xi = x0[i];
+          cplx yy = y[i];
+          yy.x -= fs.x * xi.x - fs.y * xi.y;
+          yy.y -= fs.x * xi.y + fs.y * xi.x;
+          y[i] = yy;
+          if (i > row + 1) { nn = fma(yy.x, yy.x, nn); nn = fma(yy.y, yy.y, nn); }
         }
-        const cplx f = cmul(ctau, tot);
-        for (int i = j + my_part * 32 + lane; i < p; i += W * 32) {
-          const cplx v = vb[i];
-          cplx x = col[i];
-          x.x -= f.x * v.x - f.y * v.y;
-          x.y -= f.x * v.y + f.y * v.x;
-          col[i] = x;
-          if (i > j) { nn = fma(x.x, x.x, nn); nn = fma(x.y, x.y, nn); }
-        }
+        if (half == 0 && lane == 0) y[row] = make_double2(yr.x - f.x, yr.y - f.y);
         nn = warp_sum(nn);
       }
-      if (lane == 0) s_nrm[warp] = nn;
+      if (lane == 0) s_pn[warp] = nn;
       __syncthreads();
-      if (act && my_part == 0 && lane == 0) {
-        double tot = 0.0;
-        for (int u = 0; u < W; ++u) tot += s_nrm[my_slot * W + u];
-        vn2[lc] = tot;
-      }
     }
+    // (the break conditions above are thread-uniform: they only read shared memory)
     __syncthreads();
+    if (tid < bt) done[s_pidx[s_tslot[tid]]] = 1;
+    __syncthreads();
+    QPHASE(4)
+    // ---- G. the owners file the pivot columns: R above the diagonal, then the reflector
+    for (int t = 0; t < bt; ++t) {
+      const int slot = s_tslot[t];
+      if (s_pcta[slot] != me) continue;
+      const int widx = s_pidx[slot];
+      const int lcw = (widx - me) / G;
+      const int row = j + t;
+      cplx* gcol = A.a + (size_t)widx * p;
+      const cplx* x = pan + (size_t)slot * p;
+      const cplx sc = s_scale[t];
+      if (lcw < A.nc_res) {
+        const cplx* col = colptr(lcw);
+        for (int i = tid; i < j; i += QT) gcol[i] = col[i];
+      }
+      for (int i = j + tid; i < p; i += QT) {
+        if (i < row) gcol[i] = x[i];                       // R entries of this panel's rows
+        else if (i > row) gcol[i] = cmul(x[i], sc);        // the reflector
+      }
+      if (tid == 0) gcol[row] = make_double2(s_beta[t], 0.0);
+    }
+    if (me == 0 && tid < bt) {
+      A.perm[j + tid] = s_pidx[s_tslot[tid]];
+      A.tauc[j + tid] = s_tau[tid];
+    }
+    QPHASE(5)
+    // ---- F. y <- H_bt^H ... H_1^H y on my remaining columns, one warp per column; exact
+    //         remaining norms (rows >= j + bt) in the last pass
+    for (int lc = warp; lc < NC; lc += QW) {
+      if (done[me + lc * G]) continue;
+      cplx* col = colptr(lc);
+      double nn = 0.0;
+      for (int t = 0; t < bt; ++t) {
+        const int row = j + t;
+        const cplx* x = pan + (size_t)s_tslot[t] * p;
+        const cplx sc = s_scale[t];
+        cplx w = make_double2(0.0, 0.0);
+        const cplx yr = col[row];
+        for (int i = row + 1 + lane; i < p; i += 32) w = cfma(cconj(x[i]), col[i], w);
+        w.x = warp_sum(w.x);
+        w.y = warp_sum(w.y);
+        cplx tot = cmul(cconj(sc), w);
+        tot.x += yr.x; tot.y += yr.y;
+        const cplx f = cmul(cconj(s_tau[t]), tot);
+        const cplx fs = cmul(f, sc);
+        const bool last = (t == bt - 1);
+        for (int i = row + 1 + lane; i < p; i += 32) {
+          const cplx xi = x[i];
+          cplx yy = col[i];
+          yy.x -= fs.x * xi.x - fs.y * xi.y;
+          yy.y -= fs.x * xi.y + fs.y * xi.x;
+          col[i] = yy;
+          if (last) { nn = fma(yy.x, yy.x, nn); nn = fma(yy.y, yy.y, nn); }
+        }
+        __syncwarp();
+        if (lane == 0) col[row] = make_double2(yr.x - f.x, yr.y - f.y);
+        __syncwarp();
+      }
+      nn = warp_sum(nn);
+      if (lane == 0) vn2[lc] = nn;
+    }
+    j += bt;
+    __syncthreads();
+    QPHASE(6)
+    if constexpr (PROF) ++pc[7];
   }
   const int k = j;
 
@@ -354,11 +489,14 @@ __global__ void __launch_bounds__(QT, 1) qrcp_kernel(const QrArgs A) {
       if (!done[c]) A.perm[pos++] = c;
     if (tid == 0) {
       A.hdr->k = k;
+      if constexpr (PROF)
+        for (int k_ = 0; k_ < 8; ++k_) A.hdr->phase_cycles[k_] = pc[k_];
       A.info_host[5] = G;
       __threadfence_system();             // info_host[4] is the word the host polls
       A.info_host[4] = k;
     }
   }
+#undef QPHASE
 }
 
 // ------------------------------------------------------------------ back-transformation

@@ -1130,17 +1130,22 @@ using b200::qr::QrLayout;
 using b200::qr::QrHeader;
 
 struct QrKnobs {
-  int on, minq, cols, phases;
+  int on, minq, cols, phases, panel;
+  double theta;
 };
 QrKnobs& qr_knobs() {
   static QrKnobs k = [] {
     QrKnobs v;
     const char* e;
     v.on = (e = getenv("B200_SVD_QR")) ? atoi(e) : 1;
-    v.minq = (e = getenv("B200_SVD_QR_MINQ")) ? atoi(e) : 48;
+    // measured on the config-2 operands (profiles/r02_qr_check.jsonl): the QR path wins from
+    // ~250 columns up (332x284: 3.2 vs 4.0 ms; 208x200: 1.40 vs 1.25 ms)
+    v.minq = (e = getenv("B200_SVD_QR_MINQ")) ? atoi(e) : 240;
     v.cols = (e = getenv("B200_SVD_QR_COLS")) ? atoi(e) : 4;
     if (v.cols < 1) v.cols = 1;
     v.phases = getenv("B200_SVD_PHASES") ? 1 : 0;
+    v.panel = (e = getenv("B200_SVD_QR_PANEL")) ? atoi(e) : 0;      // 0: by operand height
+    v.theta = (e = getenv("B200_SVD_QR_THETA")) ? atof(e) : 0.5;
     return v;
   }();
   return k;
@@ -1160,7 +1165,14 @@ QrLayout make_qr_layout(int m, int n) {
   Q.G = G;
   Q.NCmax = (Q.q + G - 1) / G;
   const size_t col_bytes = (size_t)Q.p * sizeof(cplx);
-  const size_t fixed = col_bytes + (size_t)Q.NCmax * sizeof(double) + (size_t)Q.q + 64;
+  // pivots per hand-shake: the panel lives in shared memory next to the resident columns
+  int panel = qr_knobs().panel;
+  if (panel <= 0) panel = (Q.p <= 1024) ? 8 : (Q.p <= 2048 ? 4 : 2);
+  if (panel > b200::qr::PBMAX) panel = b200::qr::PBMAX;
+  if (panel > G) panel = G;
+  Q.panel = panel;
+  const size_t fixed = (size_t)panel * col_bytes + (size_t)Q.NCmax * sizeof(double) +
+                       (size_t)Q.q + 64;
   Q.nc_res = 0;
   if (fixed < (size_t)b200::qr::QR_SMEM_BYTES) {
     size_t fit = ((size_t)b200::qr::QR_SMEM_BYTES - fixed) / col_bytes;
@@ -1168,9 +1180,9 @@ QrLayout make_qr_layout(int m, int n) {
   }
   Q.smem = fixed + (size_t)Q.nc_res * col_bytes;
   size_t off = 0;
-  Q.header = off; off += 64;
-  Q.cand_val = off; off += sizeof(double) * 2 * (size_t)G;
-  Q.cand_tag = off; off += sizeof(unsigned long long) * 2 * (size_t)G;
+  Q.header = off; off += 128;
+  Q.cand_tag = off;
+  off += sizeof(unsigned long long) * 2 * (size_t)G * b200::qr::TAG_STRIDE;
   Q.fro_part = off; off += sizeof(double) * (size_t)G;
   Q.tail_part = off; off += sizeof(double) * (size_t)G;
   Q.ctrl_bytes = off;
@@ -1190,7 +1202,7 @@ bool qr_eligible(int m, int n, double eps, double cos_tol) {
   const int p = (m < n) ? n : m, q = (m < n) ? m : n;
   if (q < qr_knobs().minq || p > 4096) return false;
   if ((long long)p > 2LL * q) return false;    // tall sweep operands are full rank at the stop level
-  const size_t fixed = (size_t)p * sizeof(cplx) + 4096 + (size_t)q;
+  const size_t fixed = 2 * (size_t)p * sizeof(cplx) + 4096 + (size_t)q;
   return fixed < (size_t)b200::qr::QR_SMEM_BYTES;
 }
 
@@ -1222,7 +1234,11 @@ int set_kernel_attributes() {
       e = cudaFuncSetAttribute(jacobi_kernel<true>,
                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDynSmem);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(b200::qr::qrcp_kernel,
+      e = cudaFuncSetAttribute(b200::qr::qrcp_kernel<false>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               b200::qr::QR_SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(b200::qr::qrcp_kernel<true>,
                                cudaFuncAttributeMaxDynamicSharedMemorySize,
                                b200::qr::QR_SMEM_BYTES);
     if (e != cudaSuccess) {
@@ -1378,7 +1394,6 @@ extern "C" int b200_svd_factor2(void* stream_, const void* theta, int m, int n, 
     A.theta = th; A.rs = rso; A.cs = cso; A.rsi = rsi; A.csi = csi; A.rin = rin; A.cin = cin;
     A.transposed = Q.transposed; A.p = Q.p; A.q = Q.q;
     A.a = (cplx*)(base + Q.a);
-    A.cand_val = (double*)(base + Q.cand_val);
     A.cand_tag = (unsigned long long*)(base + Q.cand_tag);
     A.fro_part = (double*)(base + Q.fro_part);
     A.tail_part = (double*)(base + Q.tail_part);
@@ -1390,9 +1405,13 @@ extern "C" int b200_svd_factor2(void* stream_, const void* theta, int m, int n, 
     A.stop_rel = 1e-5 * eps;
     if (knobs().drop >= 0.0) A.stop_rel = knobs().drop * 1e-2 * eps;
     A.nc_res = Q.nc_res; A.ncmax = Q.NCmax;
+    A.panel = Q.panel;
+    A.theta2 = qr_knobs().theta * qr_knobs().theta;
     void* args[] = {&A};
     b200::profile_begin(stream, 1);
-    B200_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)b200::qr::qrcp_kernel, dim3(Q.G),
+    void* qfn = qr_knobs().phases ? (void*)b200::qr::qrcp_kernel<true>
+                                  : (void*)b200::qr::qrcp_kernel<false>;
+    B200_CUDA_CHECK(cudaLaunchCooperativeKernel(qfn, dim3(Q.G),
                                                 dim3(b200::qr::QT), args, Q.smem, stream));
     b200::count_launch();
     b200::profile_end(stream, 1, 0.0, nullptr);
@@ -1523,6 +1542,17 @@ extern "C" int b200_svd_phase_cycles(void* stream_, const void* work, long long*
   return B200_OK;
 }
 
+/* the same for the rank-revealing QR stage (CTA 0): {0 offer, 1 poll wait, 2 select, 3 fetch
+ * the panel, 4 factorise the panel, 5 file the pivots, 6 apply to own columns, 7 hand-shakes} */
+extern "C" int b200_svd_qr_phase_cycles(void* stream_, const void* work, long long* out8) {
+  if (!work || !out8) { b200::set_error("b200_svd_qr_phase_cycles: invalid argument"); return B200_EINVAL; }
+  QrHeader h;
+  B200_CUDA_CHECK(cudaMemcpyAsync(&h, work, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream_));
+  B200_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream_));
+  for (int k = 0; k < 8; ++k) out8[k] = h.phase_cycles[k];
+  return B200_OK;
+}
+
 extern "C" int b200_svd_values(void* stream_, const void* work, int m, int n,
                                double* s_out) {
   if (!work || !s_out || m <= 0 || n <= 0) {
@@ -1590,6 +1620,8 @@ extern "C" int b200_svd_config(const char* key, double value) {
   if (k == "qr") qr_knobs().on = (value != 0.0);
   else if (k == "qr_minq") qr_knobs().minq = (int)value;
   else if (k == "qr_cols") qr_knobs().cols = (value < 1.0) ? 1 : (int)value;
+  else if (k == "qr_panel") qr_knobs().panel = (int)value;
+  else if (k == "qr_theta") qr_knobs().theta = value;
   else { b200::set_error("b200_svd_config: unknown key %s", key); return B200_EINVAL; }
   return B200_OK;
 }

@@ -130,3 +130,50 @@ def tempo_member(influences, propagators, initial_state, dkmax, epsrel, num_step
     for _ in range(num_steps):
         states.append(be.compute_step()[1])
     return np.array(states).reshape(-1, d, d)
+
+
+def broadcast_process_tensor(pt, src=0, device=None, group=None, ops=None):
+    """Share ONE built process tensor with every rank ("build on GPU 0 and
+    ncclBroadcast"): rank ``src`` passes its :class:`DeviceProcessTensor`, the other ranks
+    pass ``None`` and get a device-resident copy.  Sites and caps travel as device tensors
+    (NCCL over NVLink on GPUs -- no host staging; gloo in the CPU tests); only the shapes go
+    through ``broadcast_object_list``.  Ensembles that reuse one bath over many system
+    Hamiltonians (BASELINE configs[2]) then run ``dynamics_device`` on every GPU."""
+    from .process_tensor import DeviceProcessTensor  # pylint: disable=import-outside-toplevel
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return pt
+    rank = dist.get_rank(group)
+    meta = [None]
+    if rank == src:
+        meta = [{"d": pt.hilbert_space_dimension, "dt": pt.dt,
+                 "tin": pt.transform_in, "tout": pt.transform_out,
+                 "sites": [tuple(int(x) for x in pt.get_mpo_tensor_device(k).shape)
+                           for k in range(len(pt))],
+                 "caps": [int(pt.get_cap_tensor_device(k).numel())
+                          for k in range(len(pt) + 1)]}]
+    dist.broadcast_object_list(meta, src=src, group=group)
+    m = meta[0]
+    if rank != src:
+        pt = DeviceProcessTensor(m["d"], dt=m["dt"], transform_in=m["tin"],
+                                 transform_out=m["tout"], ops=ops)
+    dev = device if device is not None else getattr(pt._ops, "device", None)  # pylint: disable=protected-access
+    caps = []
+    for k, shape in enumerate(m["sites"]):
+        if rank == src:
+            t = pt.get_mpo_tensor_device(k).contiguous()
+        else:
+            t = torch.empty(shape, dtype=torch.complex128, device=dev)
+        # complex tensors travel as their real view (NCCL has no complex dtype)
+        dist.broadcast(torch.view_as_real(t), src=src, group=group)
+        if rank != src:
+            pt.set_mpo_tensor_device(k, t)
+    for k, n in enumerate(m["caps"]):
+        if rank == src:
+            c = pt.get_cap_tensor_device(k).contiguous()
+        else:
+            c = torch.empty(n, dtype=torch.complex128, device=dev)
+        dist.broadcast(torch.view_as_real(c), src=src, group=group)
+        caps.append(c)
+    if rank != src:
+        pt._caps = caps  # pylint: disable=protected-access
+    return pt

@@ -14,6 +14,7 @@ from . import backends as _b200
 from . import tebd as _tebd
 
 _ORIGINALS = {}
+_MISSING = object()
 # PtTebd and compute_dynamics have no module-level config dictionary to mutate
 _FORCE = {"tebd": False, "dynamics": False}
 
@@ -42,34 +43,56 @@ def _device_process_tensor(pt):
 
 
 def _compute_dynamics_factory(original, dynamics_cls):
-    """``oqupy.compute_dynamics`` (system_dynamics.py:41-182) with the hot loop on the
-    device when every process tensor is (or can be put) on the device, there are no
-    controls and every step is recorded; anything else runs the reference code."""
+    """``oqupy.compute_dynamics`` (system_dynamics.py:41-182) with the hot loop on the device
+    whenever every process tensor is (or can be put) on the device.  The reference's own
+    argument checks run first (``_compute_dynamics_input_parse``, system_dynamics.py:478-559:
+    system type, state shape, Hilbert-space dimensions, equal time steps, num_steps), so bad
+    input raises exactly what the reference raises.  Controls (system_dynamics.py:131-155) are
+    folded into the per-step propagators:  P1'_k = P1_k C^post_k,  P2'_k = C^pre_{k+1} P2_k,
+    rho_0' = C^pre_0 rho_0;  ``record_all=False`` returns the last state under the reference's
+    time stamp (system_dynamics.py:176-180)."""
     import numpy as np  # pylint: disable=import-outside-toplevel
     from .process_tensor import dynamics_device  # pylint: disable=import-outside-toplevel
 
     def compute_dynamics(system, initial_state=None, dt=None, num_steps=None, start_time=0.0,
                          process_tensor=None, control=None, record_all=True, **kwargs):
-        if _FORCE["dynamics"] and process_tensor is not None and control is None \
-                and record_all and initial_state is not None:
-            pts = process_tensor if isinstance(process_tensor, (list, tuple)) \
-                else [process_tensor]
-            devs = [_device_process_tensor(p) for p in pts]
-            if devs and all(d is not None for d in devs):
-                step = dt if dt is not None else devs[0].dt
-                n = num_steps if num_steps is not None else min(len(d) for d in devs)
-                if step is not None and all(len(d) >= n for d in devs):
-                    from oqupy.config import INTEGRATE_EPSREL, SUBDIV_LIMIT  # pylint: disable=import-outside-toplevel
-                    props = system.get_propagators(
-                        step, start_time, kwargs.get("subdiv_limit", SUBDIV_LIMIT),
-                        kwargs.get("liouvillian_epsrel", INTEGRATE_EPSREL))
-                    states = dynamics_device(devs if len(devs) > 1 else devs[0], props,
-                                             np.asarray(initial_state), num_steps=n)
-                    times = [start_time + step * k for k in range(n + 1)]
-                    return dynamics_cls(times=times, states=list(states))
-        return original(system, initial_state=initial_state, dt=dt, num_steps=num_steps,
-                        start_time=start_time, process_tensor=process_tensor,
-                        control=control, record_all=record_all, **kwargs)
+        def reference():
+            return original(system, initial_state=initial_state, dt=dt, num_steps=num_steps,
+                            start_time=start_time, process_tensor=process_tensor,
+                            control=control, record_all=record_all, **kwargs)
+        if not _FORCE["dynamics"] or process_tensor is None:
+            return reference()
+        from oqupy.system_dynamics import _compute_dynamics_input_parse  # pylint: disable=import-outside-toplevel
+        parsed = _compute_dynamics_input_parse(   # raises like the reference on bad input
+            False, system, initial_state, dt, num_steps, start_time, process_tensor, control,
+            record_all)
+        sys_, rho0, step, n, t0, pts, ctrl, rec_all, hs_dim = parsed
+        devs = [_device_process_tensor(p) for p in pts]
+        if not devs or any(d is None for d in devs) or n < 1:
+            return reference()
+        from oqupy.config import INTEGRATE_EPSREL, SUBDIV_LIMIT  # pylint: disable=import-outside-toplevel
+        props = sys_.get_propagators(step, t0, kwargs.get("subdiv_limit", SUBDIV_LIMIT),
+                                     kwargs.get("liouvillian_epsrel", INTEGRATE_EPSREL))
+        controls = [ctrl.get_controls(k, dt=step, start_time=t0) for k in range(n + 1)]
+        rho0 = np.asarray(rho0, dtype=complex)
+        if any(c[0] is not None or c[1] is not None for c in controls):
+            d2 = hs_dim * hs_dim
+            if controls[0][0] is not None:
+                rho0 = (np.asarray(controls[0][0]) @ rho0.reshape(d2)).reshape(hs_dim, hs_dim)
+            base = props
+
+            def props(k):          # pylint: disable=function-redefined
+                p1, p2 = base(k)
+                if controls[k][1] is not None:
+                    p1 = np.asarray(p1) @ np.asarray(controls[k][1])
+                if controls[k + 1][0] is not None:
+                    p2 = np.asarray(controls[k + 1][0]) @ np.asarray(p2)
+                return p1, p2
+        states = dynamics_device(devs if len(devs) > 1 else devs[0], props, rho0, num_steps=n)
+        if not rec_all:
+            return dynamics_cls(times=[t0 + 1 * step], states=[states[-1]])
+        times = [t0 + step * k for k in range(n + 1)]
+        return dynamics_cls(times=times, states=list(states))
     compute_dynamics.__doc__ = original.__doc__
     return compute_dynamics
 
@@ -111,8 +134,10 @@ def install(default=False, dynamics=True):
     oqupy.compute_dynamics = shim
     _FORCE["dynamics"] = bool(dynamics)
     if default:
-        oqupy.config.TEMPO_BACKEND_CONFIG["backend"] = "b200"
-        oqupy.config.PT_TEMPO_BACKEND_CONFIG["backend"] = "b200"
+        for name, cfg in (("TEMPO", oqupy.config.TEMPO_BACKEND_CONFIG),
+                          ("PT_TEMPO", oqupy.config.PT_TEMPO_BACKEND_CONFIG)):
+            _ORIGINALS.setdefault("cfg_" + name, cfg.get("backend", _MISSING))
+            cfg["backend"] = "b200"
 
 
 def uninstall():
@@ -134,5 +159,12 @@ def uninstall():
     tb.BaseTempoBackend = _ORIGINALS["BaseTempoBackend"]
     tm.MeanFieldTempoBackend = _ORIGINALS["MeanFieldTempoBackend"]
     ptm.PtTempoBackend = _ORIGINALS["PtTempoBackend"]
-    oqupy.config.TEMPO_BACKEND_CONFIG.pop("backend", None)
-    oqupy.config.PT_TEMPO_BACKEND_CONFIG.pop("backend", None)
+    for name, cfg in (("TEMPO", oqupy.config.TEMPO_BACKEND_CONFIG),
+                      ("PT_TEMPO", oqupy.config.PT_TEMPO_BACKEND_CONFIG)):
+        saved = _ORIGINALS.pop("cfg_" + name, None)
+        if saved is None:
+            continue                       # install(default=True) never touched it
+        if saved is _MISSING:
+            cfg.pop("backend", None)
+        else:
+            cfg["backend"] = saved         # the value the user had set before install()

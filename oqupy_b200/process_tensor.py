@@ -13,14 +13,22 @@ CDTYPE = np.complex128
 
 
 class DeviceProcessTensor:
-    """PT-MPO on the device.  Rank-3 sites only (diagonalised coupling)."""
+    """PT-MPO on the device: rank-3 sites (past bond, future bond, array leg).  A
+    non-diagonal system-bath coupling keeps the rank-3 sites of the diagonalised problem
+    plus the pair ``transform_in`` / ``transform_out`` (d2 x d2, oqupy/pt_tempo.py:159-167);
+    the device loop folds them into the system propagators (see :func:`fold_transforms`)
+    instead of expanding every site to four dense legs (process_tensor.py:346-355)."""
 
     def __init__(self, hilbert_space_dimension, dt=None, transform_in=None,
                  transform_out=None, name=None, description=None, ops=None):
-        if transform_in is not None or transform_out is not None:
-            raise NotImplementedError(
-                "oqupy_b200: non-diagonal coupling transforms on the device "
-                "process tensor are not supported yet")
+        d2 = hilbert_space_dimension ** 2
+        self._transform_in = self._transform_out = None
+        if transform_in is not None:
+            self._transform_in = np.array(transform_in, dtype=CDTYPE)
+            assert self._transform_in.shape == (d2, d2)
+        if transform_out is not None:
+            self._transform_out = np.array(transform_out, dtype=CDTYPE)
+            assert self._transform_out.shape == (d2, d2)
         self._hs_dim = hilbert_space_dimension
         self._dt = dt
         self.name = name
@@ -59,11 +67,28 @@ class DeviceProcessTensor:
     def set_mpo_tensor(self, step, tensor):
         self.set_mpo_tensor_device(step, self._ops.from_host(tensor))
 
+    @property
+    def transform_in(self):
+        return self._transform_in
+
+    @property
+    def transform_out(self):
+        return self._transform_out
+
     def get_mpo_tensor(self, step, transformed=True):
-        """Host copy, rank-3 (past, future, array) -- process_tensor.py:326-355."""
+        """Host copy (process_tensor.py:326-355): rank-3 (past, future, array); with
+        transforms and ``transformed`` the dense 4-leg tensor
+        ``T4[l,r,a,b] = sum_x tin[a,x] T3[l,r,x] tout[x,b]`` exactly as the reference forms it
+        (diagnostics / protocol fidelity: the device loop never calls this)."""
         if step >= len(self._sites) or step < 0:
             raise IndexError("Process tensor index out of bound. ")
-        return self._ops.to_host(self._sites[step])
+        t3 = self._ops.to_host(self._sites[step])
+        if not transformed or (self._transform_in is None and self._transform_out is None):
+            return t3
+        d2 = t3.shape[2]
+        tin = np.identity(d2) if self._transform_in is None else self._transform_in
+        tout = np.identity(d2) if self._transform_out is None else self._transform_out
+        return np.einsum("ax,lrx,xb->lrab", tin, t3, tout)
 
     def get_mpo_tensor_device(self, step):
         return self._sites[step]
@@ -148,23 +173,58 @@ def as_device_process_tensor(pt, ops=None):
     sites = getattr(pt, "_mpo_tensors", None)
     if sites is None or len(sites) == 0 or pt.get_initial_tensor() is not None:
         return None
-    if getattr(pt, "_transform_in", None) is not None or \
-            getattr(pt, "_transform_out", None) is not None:
-        return None
     if any(t is None or getattr(t, "ndim", 0) != 3 for t in sites):
         return None
+    caps = getattr(pt, "_cap_tensors", None)
+    if not caps or len(caps) != len(sites) + 1 or any(c is None for c in caps):
+        return None          # no caps: the reference raises (system_dynamics.py:562-575)
+    # the cached device copy is valid for exactly these site / cap arrays (a later
+    # set_mpo_tensor / set_cap_tensor replaces the array object)
+    key = tuple(id(t) for t in sites) + tuple(id(c) for c in caps)
     cached = getattr(pt, "_b200_device", None)
-    if cached is not None and cached[0] == len(sites):
+    if cached is not None and cached[0] == key:
         return cached[1]
-    dev = DeviceProcessTensor(pt.hilbert_space_dimension, dt=pt.dt, ops=ops)
+    dev = DeviceProcessTensor(pt.hilbert_space_dimension, dt=pt.dt,
+                              transform_in=getattr(pt, "_transform_in", None),
+                              transform_out=getattr(pt, "_transform_out", None), ops=ops)
     for k, t in enumerate(sites):
         dev.set_mpo_tensor(k, t)
-    dev.compute_caps()
+    dev._caps = [dev._ops.from_host(np.asarray(c).reshape(-1)) for c in caps]  # pylint: disable=protected-access
     try:
-        pt._b200_device = (len(sites), dev)   # pylint: disable=protected-access
+        pt._b200_device = (key, dev)   # pylint: disable=protected-access
     except AttributeError:
         pass
     return dev
+
+
+def fold_transforms(pts, propagators):
+    """Propagators that carry the coupling transforms of ONE-environment process tensors.
+
+    With T4[l,r,a,b] = sum_x tin[a,x] T3[l,r,x] tout[x,b] (process_tensor.py:349-354) and the
+    conventions v'[j] = sum_i P[j,i] v[i], v'[r,b] = sum_{l,a} v[l,a] T4[l,r,a,b]
+    (system_dynamics.py:631-640, 689-700), a step  P2 . T4 . P1  equals
+    (P2 tout^T) . T3 . (tin^T P1): the rank-3 device kernel with two d2 x d2 products on the
+    host per distinct propagator pair."""
+    pt = pts[0]
+    tin, tout = pt.transform_in, pt.transform_out
+    if tin is None and tout is None:
+        return propagators
+    cache = {}
+
+    def folded(step):
+        p1, p2 = propagators(step)
+        key = (id(p1), id(p2))
+        if key not in cache:
+            cache.clear()
+            q1 = np.asarray(p1, dtype=CDTYPE)
+            q2 = np.asarray(p2, dtype=CDTYPE)
+            if tin is not None:
+                q1 = tin.T @ q1
+            if tout is not None:
+                q2 = q2 @ tout.T
+            cache[key] = (q1, q2, p1, p2)
+        return cache[key][0], cache[key][1]
+    return folded
 
 
 def import_process_tensor(filename, ops=None):
@@ -202,6 +262,7 @@ def dynamics_device(pt, propagators, initial_states, num_steps=None, ops=None):
             return _dynamics_multi_env(list(pt), propagators, initial_states, num_steps,
                                        ops)
         pt = pt[0]
+    propagators = fold_transforms([pt], propagators)
     rho0 = np.asarray(initial_states, dtype=CDTYPE)
     single = rho0.ndim == 2
     if single:
@@ -210,6 +271,10 @@ def dynamics_device(pt, propagators, initial_states, num_steps=None, ops=None):
     d2 = d * d
     if num_steps is None:
         num_steps = len(pt)
+    for k in range(num_steps):       # an out-of-bounds device read otherwise
+        if int(pt.get_mpo_tensor_device(k).shape[2]) != d2:
+            raise ValueError(f"process tensor site {k} has array leg "
+                             f"{int(pt.get_mpo_tensor_device(k).shape[2])}, the state needs {d2}")
     v = ops.from_host(rho0.reshape(nvec, 1, d2))
     rho = ops.empty(num_steps + 1, nvec, d2)
     if hasattr(ops, "dyn_run"):
@@ -290,6 +355,19 @@ def _dynamics_multi_env(pts, propagators, initial_state, num_steps, ops):
                      View(out, col=1))
             cur = out
 
+    tcache = {}
+
+    def system_leg_product(state, mat):
+        """state[..., j] <- sum_i mat[j, i] state[..., i]"""
+        key = id(mat)
+        if key not in tcache:
+            tcache[key] = (ops.from_host(np.ascontiguousarray(mat)), mat)
+        rows_ = state.numel() // d2
+        out = ops.empty(rows_, d2)
+        ops.gemm(rows_, d2, d2, View(state, row=d2, col=1), View(tcache[key][0], row=1, col=d2),
+                 View(out, row=d2, col=1))
+        return out
+
     cache = {}
     for step in range(num_steps):
         readout(v, chis, step, rho[step])
@@ -308,7 +386,9 @@ def _dynamics_multi_env(pts, propagators, initial_state, num_steps, ops):
         for i in range(m):
             t = pts[i].get_mpo_tensor_device(step)
             chi_l, chi_r, _ = t.shape
-            assert chi_l == chis[i]
+            assert chi_l == chis[i] and int(t.shape[2]) == d2
+            if pts[i].transform_in is not None:                     # v <- v tin
+                v = system_leg_product(v, pts[i].transform_in.T)
             na = int(np.prod(chis[:i]))                # legs before the contracted one
             nb = int(np.prod(chis[i + 1:]))            # legs after it
             nxt = ops.empty(na * chi_r * nb, d2)
@@ -320,6 +400,8 @@ def _dynamics_multi_env(pts, propagators, initial_state, num_steps, ops):
                      nb1=d2, nb2=na)
             v = nxt
             chis[i] = chi_r
+            if pts[i].transform_out is not None:                    # v <- v tout
+                v = system_leg_product(v, pts[i].transform_out.T)
         rows = int(np.prod(chis))
         nxt = ops.empty(rows, d2)
         ops.gemm(rows, d2, d2, View(v, row=d2, col=1), View(dp2, row=1, col=d2),

@@ -11,6 +11,14 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+def TEMPO_STATE_ATOL(eps):  # pylint: disable=invalid-name
+    """Tolerance of TEMPO states against the reference: the reproducibility floor of the
+    reference ALGORITHM, measured by tests/test_oracle_vs_reference.py (inputs perturbed by
+    1e-15 move the states by up to ~0.5 eps; oracle and reference, both LAPACK, differ by up
+    to ~20 eps once the memory cut-off sets in)."""
+    return 50.0 * eps
+
+
 def pytest_configure(config):
     config.addinivalue_line(
         "markers", "gpu: needs a CUDA device (run on the B200 box)")
@@ -74,7 +82,8 @@ def check_mean_field_run(backend, g, seen):
         assert complex(field) == complex(g["fields"][k + 1])
         out.append(np.asarray(states[0]).reshape(d, d))
     out = np.array(out)
-    np.testing.assert_allclose(out, g["states"], atol=50 * float(g["epsrel"]), rtol=0)
+    np.testing.assert_allclose(out, g["states"], atol=TEMPO_STATE_ATOL(float(g["epsrel"])),
+                               rtol=0)
     np.testing.assert_allclose(out[:5], g["states"][:5], atol=1e-9, rtol=0)
     np.testing.assert_almost_equal(out[-1], g["rho_golden"], decimal=4)
     # plumbing: every step's propagators saw the field of that step and its derivative

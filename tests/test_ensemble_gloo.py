@@ -74,3 +74,49 @@ def test_ensemble_two_ranks(tmp_path):
     # different couplings give different dynamics, traces stay 1
     assert np.abs(r0[4] - r0[0]).max() > 1e-4
     np.testing.assert_allclose(np.trace(r0, axis1=2, axis2=3), 1.0, atol=1e-4)
+
+
+def _bcast_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from conftest import golden_callables, load_golden
+    from host_model_ops import HostModelOps
+    import oqupy_b200 as ob
+    from oqupy_b200.ensemble import broadcast_process_tensor, run_ensemble
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = load_golden("pt_k8_eps9_n24")
+    influence, propagators = golden_callables(g)
+    ops = HostModelOps()
+    pt = None
+    if rank == 0:       # only rank 0 builds the process tensor
+        pt = ob.DeviceProcessTensor(2, dt=float(g["dt"]), ops=ops)
+        be = ob.PtTempoBackend(2, influence, pt, np.ones(4), np.ones(4), 10, 5, 1e-8, ops=ops)
+        be.initialize()
+        while be.compute_step():
+            pass
+        be.update_process_tensor()
+    pt = broadcast_process_tensor(pt, src=0, ops=ops)
+    assert len(pt) == 10
+    p1, p2 = propagators(0)
+
+    def member(i):      # a panel of system Hamiltonians sharing the one process tensor
+        ph = np.exp(0.05j * i)
+        return ob.dynamics_device(pt, lambda s: (p1 * ph, p2), g["initial_state"], ops=ops)
+
+    res = run_ensemble(5, member)
+    np.save(os.path.join(out_dir, f"bc{rank}.npy"), res)
+    dist.destroy_process_group()
+
+
+def test_broadcast_process_tensor_two_ranks(tmp_path):
+    """one process tensor built on rank 0, broadcast (device tensors; gloo here,
+    NCCL on the GPUs), reused by every rank for its share of a Hamiltonian panel."""
+    port = _free_port()
+    mp.spawn(_bcast_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = np.load(tmp_path / "bc0.npy"), np.load(tmp_path / "bc1.npy")
+    assert r0.shape == (5, 11, 2, 2)
+    np.testing.assert_array_equal(r0, r1)
+    assert np.abs(r0[1] - r0[0]).max() > 1e-6

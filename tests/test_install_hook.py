@@ -183,8 +183,8 @@ def test_install_dispatch_pt_tebd_and_unique(monkeypatch):
 
 def test_install_compute_dynamics(monkeypatch):
     """oqupy.compute_dynamics rebound (system_dynamics.py:41-182): host process tensors from
-    the reference's PT-TEMPO are uploaded once, one and two environments; controls fall
-    through to the reference code."""
+    the reference's PT-TEMPO are uploaded once, one and two environments, controls,
+    record_all=False, non-diagonal coupling transforms, the reference's own input checks."""
     oqupy = load_reference()
     from oqupy_b200 import backends, install, process_tensor
     from host_model_ops import HostModelOps
@@ -216,14 +216,57 @@ def test_install_compute_dynamics(monkeypatch):
         new2 = oqupy.compute_dynamics(system, process_tensor=[pt, pt], initial_state=rho0,
                                       num_steps=6, progress_type="silent")
         np.testing.assert_allclose(new2.states, ref2.states[:7], atol=1e-10)
-        # a control is outside the device path: the reference code answers
+        # controls (system_dynamics.py:131-155) are folded into the per-step propagators
         control = oqupy.Control(2)
         control.add_single(3, oqupy.operators.left_super(sig("x")))
+        control.add_single(5, oqupy.operators.right_super(sig("y")), post=True)
+        control.add_single(0, oqupy.operators.left_right_super(sig("x"), sig("x")))
+        refc = install._ORIGINALS["compute_dynamics"](
+            system, process_tensor=pt, initial_state=rho0, control=control,
+            progress_type="silent")
         launches = ops.launches
         withc = oqupy.compute_dynamics(system, process_tensor=pt, initial_state=rho0,
                                        control=control, progress_type="silent")
-        assert ops.launches == launches
-        assert len(withc.states) == len(ref1.states)
+        assert ops.launches > launches
+        np.testing.assert_allclose(withc.states, refc.states, atol=1e-10)
+        # record_all=False: the last state under the reference's time stamp (:176-180)
+        ref_last = install._ORIGINALS["compute_dynamics"](
+            system, process_tensor=pt, initial_state=rho0, record_all=False,
+            progress_type="silent")
+        new_last = oqupy.compute_dynamics(system, process_tensor=pt, initial_state=rho0,
+                                          record_all=False, progress_type="silent")
+        np.testing.assert_allclose(new_last.times, ref_last.times, atol=1e-12)
+        np.testing.assert_allclose(new_last.states, ref_last.states, atol=1e-10)
+        # bad input raises what the reference raises (system_dynamics.py:478-559)
+        with pytest.raises(ValueError):
+            oqupy.compute_dynamics(system, process_tensor=pt, initial_state=rho0, dt=0.07,
+                                   progress_type="silent")
+        with pytest.raises(ValueError):
+            oqupy.compute_dynamics(system, process_tensor=pt, initial_state=np.eye(3),
+                                   progress_type="silent")
+        with pytest.raises(ValueError):
+            oqupy.compute_dynamics(system, process_tensor=pt, initial_state=rho0,
+                                   num_steps=99, progress_type="silent")
+        # a later set_mpo_tensor invalidates the cached device copy
+        dev_before = pt._b200_device[1]
+        pt.set_mpo_tensor(2, pt._mpo_tensors[2] * 1.0)
+        oqupy.compute_dynamics(system, process_tensor=pt, initial_state=rho0,
+                               progress_type="silent")
+        assert pt._b200_device[1] is not dev_before
+        # non-diagonal coupling (pt_tempo.py:159-167, process_tensor.py:349-354): the
+        # transforms are folded into the propagators, one and two environments
+        bath_x = oqupy.Bath(0.5 * sig("x"), corr)
+        pt_x = oqupy.pt_tempo_compute(bath=bath_x, start_time=0.0, end_time=1.0,
+                                      parameters=params, progress_type="silent")
+        assert pt_x._transform_in is not None
+        for pts in (pt_x, [pt_x, pt]):
+            refx = install._ORIGINALS["compute_dynamics"](
+                system, process_tensor=pts, initial_state=rho0, progress_type="silent")
+            launches = ops.launches
+            newx = oqupy.compute_dynamics(system, process_tensor=pts, initial_state=rho0,
+                                          progress_type="silent")
+            assert ops.launches > launches
+            np.testing.assert_allclose(newx.states, refx.states, atol=1e-10)
     finally:
         install.uninstall()
     assert oqupy.compute_dynamics is install._ORIGINALS["compute_dynamics"]

@@ -31,6 +31,27 @@ def test_model_matches_oracle(m, n, eps):
     np.testing.assert_allclose(u.conj().T @ u, np.eye(keep), atol=1e-4)
 
 
+@pytest.mark.parametrize("m,n,grid,panel", [(96, 90, 23, 8), (70, 130, 18, 4), (130, 120, 30, 8)])
+def test_panel_pivoting_matches_oracle(m, n, grid, panel):
+    """The kernel's relaxed (panel) pivoting gives the same truncated factorisation."""
+    rng = np.random.default_rng(m + 7 * n)
+    theta = graded(rng, m, n)
+    eps = 1e-9
+    u, svh, keep, k, s = qr_model.truncated_svd_model(theta, eps, grid=grid, panel=panel)
+    u_ref, s_ref, vh_ref = tempo_np.truncated_svd(theta, eps)[:3]
+    assert keep == u_ref.shape[1]
+    np.testing.assert_allclose(u @ svh, (u_ref * s_ref) @ vh_ref, atol=5e-14)
+    x = theta.conj().T if m < n else theta
+    a, perm, tau, kk, tail2, shakes = qr_model.qrcp_panel(x, 1e-14, grid, panel)
+    assert kk == k and shakes < k      # several pivots per hand-shake
+    # a valid QR of the permuted operand whatever the pivot order
+    r = np.zeros((k, x.shape[1]), dtype=complex)
+    for pos in range(x.shape[1]):
+        top = min(pos + 1, k)
+        r[:top, pos] = a[:top, perm[pos]]
+    np.testing.assert_allclose(qr_model.apply_q(a, perm, tau, k, r), x[:, perm], atol=1e-12)
+
+
 def test_model_qr_identities():
     rng = np.random.default_rng(3)
     x = graded(rng, 80, 64, lo=-6.0)

@@ -11,8 +11,17 @@ for job in "$@"; do
     tiny_san)  timeout 600 compute-sanitizer --tool memcheck python tools/qr_check.py tiny > gpurun_out/${TAG}_memcheck.log 2>&1 ;;
     kernels)   timeout 1200 python -m pytest tests/test_kernels_gpu.py -x -q > gpurun_out/${TAG}_kernels.log 2>&1 ;;
     gputests)  timeout 2400 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_gputests.log 2>&1 ;;
-    bench)     timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err ;;
-    bench_noqr) B200_SVD_QR=0 timeout 900 python bench.py --steps 20 --warmup 5 --no-cpu > gpurun_out/${TAG}_bench_noqr.json 2> gpurun_out/${TAG}_bench_noqr.err ;;
+    bench)     timeout 1500 python bench.py --steps 20 --warmup 5 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err ;;
+    bench_noqr) B200_SVD_QR=0 timeout 1500 python bench.py --steps 20 --warmup 5 --no-cpu > gpurun_out/${TAG}_bench_noqr.json 2> gpurun_out/${TAG}_bench_noqr.err ;;
+    stepprof)  timeout 600 python tools/step_profile.py 50 300 > gpurun_out/${TAG}_stepprof.jsonl 2> gpurun_out/${TAG}_stepprof.err ;;
+    stepprof_noqr) B200_SVD_QR=0 timeout 600 python tools/step_profile.py 50 300 > gpurun_out/${TAG}_stepprof_noqr.jsonl 2> gpurun_out/${TAG}_stepprof_noqr.err ;;
+    phases)    B200_SVD_PHASES=1 timeout 900 python tools/qr_check.py oracle25 > gpurun_out/${TAG}_phases.log 2>&1 ;;
+    bench_ref) timeout 1500 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_ref.json 2> gpurun_out/${TAG}_bench_ref.err ;;
+    bench_old) timeout 900 python bench.py --steps 20 --warmup 5 --preroll 0 > gpurun_out/${TAG}_bench_old.json 2> gpurun_out/${TAG}_bench_old.err ;;
+    teacher)   timeout 1500 python tools/teacher_forced.py 7 26 > gpurun_out/${TAG}_teacher_7_26.json 2> gpurun_out/${TAG}_teacher.err ;;
+    teacher2)  timeout 1500 python tools/teacher_forced.py 32 34 > gpurun_out/${TAG}_teacher_32_34.json 2> gpurun_out/${TAG}_teacher2.err ;;
+    batch)     timeout 900 python -m pytest tests/test_batch_gpu.py -x -q > gpurun_out/${TAG}_batch.log 2>&1 ;;
+    batchbench) timeout 900 python tools/batch_bench.py 592 60 25 > gpurun_out/${TAG}_batchbench.json 2> gpurun_out/${TAG}_batchbench.err ;;
     *) echo "unknown job $job" ;;
   esac
   echo "== $job rc=$?"

@@ -21,6 +21,7 @@ import qr_model  # noqa: E402
 from oqupy_b200._lib import default_ops  # noqa: E402
 
 EPS = 1e-9
+PANEL = int(os.environ.get("B200_SVD_QR_PANEL", "0"))
 
 
 def graded(rng, m, n, lo=-25.0):
@@ -88,10 +89,15 @@ def check(ops, name, theta, eps=EPS, model=True):
     if h.keep > 0:
         row["recon_qr"] = float(np.abs(u @ svh - best).max() / sr[0])
         row["orth_qr"] = float(np.abs(u.conj().T @ u - np.eye(h.keep)).max())
+    if plan[0] and os.environ.get("B200_SVD_PHASES"):
+        row["qr_phase_kcyc"] = [round(c / 1e3, 1) for c in ops.svd_qr_phase_cycles(h)]
+        row["jac_phase_kcyc"] = [round(c / 1e3, 1) for c in ops.svd_phase_cycles(h)]
     if plan[0] and model:
         dbg = ops.svd_qr_debug(h)
         x = theta.conj().T if m < n else theta
-        a_m, perm_m, tau_m, k_m, tail2_m = qr_model.qrcp_stopped(x, 1e-5 * eps)
+        a_m, perm_m, tau_m, k_m, tail2_m, shakes = qr_model.qrcp_panel(
+            x, 1e-5 * eps, dbg["grid"], PANEL if PANEL else (8 if x.shape[0] <= 1024 else 4))
+        row["handshakes_model"] = shakes
         row["k_model"] = k_m
         row["tail2"] = [dbg["tail2"], tail2_m]
         kk = min(k_m, dbg["k"])
