@@ -262,7 +262,7 @@ int b200_caps_step(void* stream, int chi_l, int chi_r, int d2, const void* t,
  * stopped column-pivoted QR + one-sided Jacobi on R + the reference's tail-norm rule).  The
  * loop it replaces is the ensemble of oqupy.Tempo(...).compute() calls of BASELINE configs[4]
  * (oqupy/tempo.py:479-484 per member) and MeanFieldTempoBackend's per-system loop
- * (tempo_backend.py:747-773).  chi_cap bounds the bond dimension (chi_cap * d2 <= 104).
+ * (tempo_backend.py:747-773).  chi_cap bounds the bond dimension (chi_cap * d2 <= 128; an operand p x q must fit shared memory, (p|1)*q <= 14272).
  *
  * b200_tempo_batch_set (device pointers, complex128, member-major):
  *   mid, start (E, dkmax+1, d2, d2): infl[dk][s,e] and infl[dk][s,e]*sum_west[e]

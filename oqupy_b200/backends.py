@@ -405,10 +405,16 @@ class TempoBackend(BaseTempoBackend):
 
 
 class MeanFieldTempoBackend:
-    """One or more TEMPO networks with a coherent mean field
-    (tempo_backend.py:629-773): one device-resident :class:`BaseTempoBackend` per
-    system, propagated with the same (field-dependent) half-step propagators the
-    reference would use; the field equation of motion stays a host callback."""
+    """One or more TEMPO networks with a coherent mean field (tempo_backend.py:629-773).
+
+    The systems of a mean-field model advance in LOCK-STEP: when they share the Hilbert-space
+    dimension and a finite ``dkmax`` (and use full legs, no correlation-time tail) all of
+    them are members of ONE :class:`oqupy_b200.batch.BatchedTempoBackend` and a time step of
+    the whole model is one kernel launch (one CTA per system) instead of the reference's
+    host loop over per-system backends (:761-764).  Otherwise (``unique=True`` maps,
+    ``dkmax=None``, mixed dimensions) every system keeps its own device-resident
+    :class:`BaseTempoBackend`.  The field equation of motion stays a host callback, as the
+    propagators do (they depend on the field of the step, :755-759)."""
 
     def __init__(self, initial_state_list, initial_field, influence_list,
                  unitary_transform_list, propagators_list, compute_field,
@@ -428,6 +434,30 @@ class MeanFieldTempoBackend:
         self._state_list = initial_state_list
         self._step = None
         self._propagators_list = propagators_list
+        self._batched = None
+        self._backend_list = None
+        ops_ = default_ops() if ops is None else ops
+        sizes = {np.asarray(s).size for s in initial_state_list}
+        lockstep = (getattr(ops_, "name", "") == "cuda" and dkmax is not None and dkmax >= 1
+                    and len(sizes) == 1
+                    and all(m is None for m in degeneracy_maps_list)
+                    and os.environ.get("OQUPY_B200_PYCHAIN", "0") != "1")
+        if lockstep:
+            d2 = sizes.pop()
+            lockstep = (all(len(sn) == d2 and len(sw) == d2 and np.all(np.asarray(sn) == 1)
+                            and np.all(np.asarray(sw) == 1)
+                            for sn, sw in zip(sum_north_list, sum_west_list))
+                        and all(infl(-1) is None for infl in influence_list))
+        if lockstep:
+            from .batch import MAX_OPERAND, BatchedTempoBackend  # pylint: disable=import-outside-toplevel
+            infl = np.array([[np.asarray(f(dk), dtype=CDTYPE) for dk in range(dkmax + 1)]
+                             for f in influence_list])
+            self._batched = BatchedTempoBackend(
+                np.array([np.asarray(s, dtype=CDTYPE).reshape(-1) for s in initial_state_list]),
+                infl, np.array([np.asarray(u, dtype=CDTYPE) for u in unitary_transform_list]),
+                None, np.ones(d2), np.ones(d2), dkmax, epsrel,
+                chi_cap=MAX_OPERAND // d2, ops=ops_)
+            return
         self._backend_list = [
             BaseTempoBackend(state, influence, unitary, sum_north, sum_west, dkmax,
                              epsrel, config, maps, dim, ops=ops)
@@ -443,6 +473,10 @@ class MeanFieldTempoBackend:
     def initialize(self):
         """:740-745"""
         self._step = 0
+        if self._batched is not None:
+            self._batched.initialize()
+            self._state_list = [copy(s).reshape(-1) for s in self._initial_state_list]
+            return self._step, deepcopy(self._state_list), self._field
         for backend in self._backend_list:
             backend.initialize_mps_mpo()
         return self._step, deepcopy(self._state_list), self._field
@@ -459,9 +493,15 @@ class MeanFieldTempoBackend:
         prop_tuple_list = [propagators(current_step, current_field,
                                        current_field_derivative)
                            for propagators in self._propagators_list]
-        next_state_list = [backend.compute_system_step(next_step, *prop_tuple)
-                           for backend, prop_tuple in zip(self._backend_list,
-                                                          prop_tuple_list)]
+        if self._batched is not None:      # every system in ONE launch
+            _, states = self._batched.compute_step_with(
+                np.array([np.asarray(p[0], dtype=CDTYPE) for p in prop_tuple_list]),
+                np.array([np.asarray(p[1], dtype=CDTYPE) for p in prop_tuple_list]))
+            next_state_list = [states[i].copy() for i in range(states.shape[0])]
+        else:
+            next_state_list = [backend.compute_system_step(next_step, *prop_tuple)
+                               for backend, prop_tuple in zip(self._backend_list,
+                                                              prop_tuple_list)]
         next_field = self._compute_field(current_step, current_state_list,
                                          current_field, next_state_list)
         self._state_list = next_state_list
@@ -470,4 +510,6 @@ class MeanFieldTempoBackend:
         return self._step, deepcopy(self._state_list), self._field
 
     def get_bond_dimensions(self):
+        if self._batched is not None:
+            return self._batched.get_bond_dimensions()
         return [backend.get_bond_dimensions() for backend in self._backend_list]

@@ -18,7 +18,7 @@ import numpy as np
 from ._lib import B200Error, default_ops
 
 CDTYPE = np.complex128
-MAX_OPERAND = 104           # chi * d2 must fit the shared-memory resident SVD (csrc/batch.cu)
+MAX_OPERAND = 128           # chi * d2 must fit the shared-memory resident SVD (csrc/batch.cu)
 
 
 def _dense0(infl0, unitary, d2):
@@ -138,6 +138,19 @@ class BatchedTempoBackend:
             c_void_p(self._h), c_void_p(p1.data_ptr()), c_void_p(p2t.data_ptr()),
             c_void_p(out.data_ptr())), "b200_tempo_batch_step")
 
+    def compute_step_with(self, prop_1, prop_2):
+        """One time step with explicitly given propagators, each (E, d2, d2) or (d2, d2)
+        (mean-field systems: the propagators of a step depend on the field of that step,
+        tempo_backend.py:755-764).  Returns (step, states (E, d2)) on the host."""
+        saved = self._propagators
+        self._propagators = lambda step: (prop_1, prop_2)
+        self._prop_cache = None
+        try:
+            return self.compute_step()
+        finally:
+            self._propagators = saved
+            self._prop_cache = None
+
     def compute_step(self):
         """One time step of every member; returns (step, states (E, d2)) on the host."""
         self._launch(self._states_dev)
@@ -145,14 +158,17 @@ class BatchedTempoBackend:
         self.check()
         return self._step, states
 
-    def compute_steps(self, num_steps):
+    def compute_steps(self, num_steps, strict=True):
         """``num_steps`` time steps back to back (one launch each, no host round trip in
-        between); returns the states (num_steps, E, d2) with ONE device-to-host copy."""
+        between); returns the states (num_steps, E, d2) with ONE device-to-host copy.
+        ``strict=False``: members that left the device path (see :meth:`info`) do not raise;
+        their states are undefined from the step at which they stopped."""
         buf = self._ops.empty(num_steps, self.E, self.d2)
         for k in range(num_steps):
             self._launch(buf[k])
         out = self._ops.to_host(buf)
-        self.check()
+        if strict:
+            self.check()
         return out
 
     def info(self):

@@ -24,6 +24,7 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -32,8 +33,9 @@ namespace {
 
 constexpr int BT = 512;
 constexpr int BW = BT / 32;
-constexpr int BATCH_SMEM = 220 * 1024;
-constexpr int MAXD = 104;          // largest operand dimension (chi * d2)
+constexpr int BATCH_SMEM = 223 * 1024;   // + ~3.7 KB static = the 227 KB a CTA can have
+constexpr int MAXD = 128;          // largest operand dimension (chi * d2); an operand must also
+                                   // fit shared memory: (p | 1) * q <= 14272 complex numbers
 
 struct BatchDev {
   int E, d2, n_mpo, ns_slots, cap_chi, slot_elems;
@@ -215,6 +217,33 @@ __device__ int cta_svd(SvdShared& S, cplx* X, int ld, cplx* Jsm, int jsm_elems, 
     return 0;
   }
 
+  // ---- only the k rows of R are live from here on: re-pack X to the leading dimension
+  //      k | 1 (batches of 16 columns through registers; a batch never lands on the source of
+  //      a later one), which frees shared memory for the rotation accumulator J
+  {
+    const int ld2 = k | 1;
+    if (ld2 < ld) {
+      for (int c0 = 0; c0 < q; c0 += 16) {
+        const int nc = min(16, q - c0), tot = nc * k;
+        cplx v[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int e = tid + t * BT;
+          if (e < tot) { const int c = e / k, i = e - c * k; v[t] = X[i + (size_t)(c0 + c) * ld]; }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int e = tid + t * BT;
+          if (e < tot) { const int c = e / k, i = e - c * k; X[i + (size_t)(c0 + c) * ld2] = v[t]; }
+        }
+        __syncthreads();
+      }
+      Jsm = X + (size_t)ld2 * q;
+      jsm_elems += (ld - ld2) * q;
+      ld = ld2;
+    }
+  }
   // ---- cyclic one-sided Jacobi on the rows 0..k-1 of R (k x q), rotations accumulated in J
   cplx* J = ((size_t)k * k <= (size_t)jsm_elems) ? Jsm : jglob;
   for (int e = tid; e < k * k; e += BT) J[e] = make_double2((e / k == e % k) ? 1.0 : 0.0, 0.0);
@@ -406,7 +435,6 @@ __device__ int cta_svd(SvdShared& S, cplx* X, int ld, cplx* Jsm, int jsm_elems, 
 __global__ void __launch_bounds__(BT, 1) tempo_batch_step_kernel(const BatchDev P) {
   extern __shared__ __align__(16) unsigned char bsm[];
   __shared__ SvdShared S;
-  __shared__ int s_keep;
   const int tid = threadIdx.x;
   const int e = P.first_member + blockIdx.x;
   if (e >= P.E) return;
@@ -427,7 +455,6 @@ __global__ void __launch_bounds__(BT, 1) tempo_batch_step_kernel(const BatchDev 
   int n_sites = hdr[0], head = hdr[1];
   const int n_mpo = P.n_mpo;
   auto slot_of = [&](int i) { return (head + i) % NS; };
-  auto site_ptr = [&](int i) { return slots + (size_t)slot_of(i) * P.slot_elems; };
   auto fail = [&](int code) { if (tid == 0) hdr[2] = code; };
 
   // ---- first half propagator on the newest site: last[l, j] <- sum_i last[l, i] P1[j, i]
@@ -531,6 +558,7 @@ __global__ void __launch_bounds__(BT, 1) tempo_batch_step_kernel(const BatchDev 
     const int p = tr ? n : m, q = tr ? m : n;
     const int ld = p | 1;
     const int jsm = smem_elems - ld * q;
+    if (jsm < 0) { fail(2); return; }
     // build Theta straight into shared memory, in the orientation the SVD wants
     for (int idx = tid; idx < m * n; idx += BT) {
       const int i = idx / n, jx = idx - i * n;           // i = (k, s), jx = (r, e)
@@ -571,6 +599,7 @@ __global__ void __launch_bounds__(BT, 1) tempo_batch_step_kernel(const BatchDev 
     const int p = tr ? n : m, q = tr ? m : n;
     const int ld = p | 1;
     const int jsm = smem_elems - ld * q;
+    if (jsm < 0) { fail(2); return; }
     for (int idx = tid; idx < m * n; idx += BT) {
       const int l = idx / m, ii = idx - l * m;            // a[l][ii]: theta[ii][l]
       const cplx v = a[idx];
@@ -644,7 +673,6 @@ __global__ void __launch_bounds__(BT, 1) tempo_batch_step_kernel(const BatchDev 
     }
   }
   if (tid == 0) { hdr[0] = n_sites; hdr[1] = head; }
-  (void)s_keep;
 }
 
 struct Batch {
@@ -663,7 +691,7 @@ extern "C" {
 
 /* Lock-step TEMPO ensemble (oqupy/backends/tempo_backend.py:439-575 for E members at once).
  * All members share d2, dkmax (>= 1, finite) and epsrel; chi_cap bounds the bond dimension
- * (chi_cap * d2 <= 104: every truncated SVD operand lives in shared memory). */
+ * (chi_cap * d2 <= 128; every truncated SVD operand must fit shared memory). */
 void* b200_tempo_batch_create(void* stream, int n_members, int d2, int dkmax, int chi_cap,
                               double epsrel) {
   if (n_members < 1 || d2 < 1 || dkmax < 1 || chi_cap < 1 || chi_cap * d2 > MAXD ||
@@ -715,17 +743,18 @@ void* b200_tempo_batch_create(void* stream, int n_members, int d2, int dkmax, in
   D.p1 = (cplx*)(base + o_p1); D.p2t = (cplx*)(base + o_p2); D.carry = (cplx*)(base + o_carry);
   D.vg = (cplx*)(base + o_vg); D.jg = (cplx*)(base + o_jg); D.tmp = (cplx*)(base + o_tmp);
   D.states = (cplx*)(base + o_states);
-  static bool attr = false;
-  if (!attr) {
-    if (cudaFuncSetAttribute(tempo_batch_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             BATCH_SMEM) != cudaSuccess) {
-      b200::set_error("b200_tempo_batch_create: shared memory attribute failed");
-      (void)cudaGetLastError();
-      cudaFree(b->arena);
-      delete b;
-      return nullptr;
-    }
-    attr = true;
+  static std::once_flag once;       // ensembles drive the library from several host threads
+  static cudaError_t attr_rc = cudaSuccess;
+  std::call_once(once, [] {
+    attr_rc = cudaFuncSetAttribute(tempo_batch_step_kernel,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, BATCH_SMEM);
+  });
+  if (attr_rc != cudaSuccess) {
+    b200::set_error("b200_tempo_batch_create: shared memory attribute failed");
+    (void)cudaGetLastError();
+    cudaFree(b->arena);
+    delete b;
+    return nullptr;
   }
   return b;
 }

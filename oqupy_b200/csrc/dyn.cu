@@ -8,6 +8,8 @@
 //
 // HBM-bound: one step streams T (chi_l*chi_r*d2*16 B) exactly once; `nvec`
 // ensemble members sharing the process tensor reuse each T element from registers.
+#include <mutex>
+
 #include "common.cuh"
 
 namespace {
@@ -44,64 +46,6 @@ __global__ void dyn_pre_kernel(int nvec, int chi_l, int d2, const cplx* __restri
       }
       if (lane == 0) rho[(size_t)e * d2 + i] = acc;
     }
-  }
-}
-
-// partial[s][e][r][x] = sum_{l in slice s} T[l,r,x] * u[e,l,x]
-__global__ void __launch_bounds__(DT)
-dyn_stream_kernel(int nvec, int chi_l, int chi_r, int d2, int lchunk,
-                  const cplx* __restrict__ t, const cplx* __restrict__ u,
-                  cplx* __restrict__ partial) {
-  const int ncol = chi_r * d2;
-  const int c = blockIdx.x * DT + threadIdx.x;
-  const int s = blockIdx.y;
-  const int e0 = blockIdx.z * EV;
-  if (c >= ncol) return;
-  const int x = c % d2;
-  const int l0 = s * lchunk;
-  const int l1 = min(chi_l, l0 + lchunk);
-  cplx acc[EV];
-#pragma unroll
-  for (int k = 0; k < EV; ++k) acc[k] = make_double2(0.0, 0.0);
-  const cplx* tp = t + (size_t)l0 * ncol + c;
-#pragma unroll 4
-  for (int l = l0; l < l1; ++l, tp += ncol) {
-    const cplx tv = __ldg(tp);
-#pragma unroll
-    for (int k = 0; k < EV; ++k) {
-      if (e0 + k < nvec) {
-        const cplx uv = u[((size_t)(e0 + k) * chi_l + l) * d2 + x];
-        acc[k] = b200::cfma(tv, uv, acc[k]);
-      }
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < EV; ++k)
-    if (e0 + k < nvec)
-      partial[((size_t)s * nvec + (e0 + k)) * ncol + c] = acc[k];
-}
-
-// v_out[e,r,j] = sum_x P2[e][j,x] * sum_s partial[s][e][r][x]
-__global__ void dyn_post_kernel(int nvec, int chi_r, int d2, int ns,
-                                const cplx* __restrict__ p2,
-                                const cplx* __restrict__ partial,
-                                cplx* __restrict__ v_out) {
-  const int e = blockIdx.y;
-  const int ncol = chi_r * d2;
-  const cplx* P = p2 + (size_t)e * d2 * d2;
-  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncol;
-       c += gridDim.x * blockDim.x) {
-    const int r = c / d2, j = c % d2;
-    cplx acc = make_double2(0.0, 0.0);
-    for (int x = 0; x < d2; ++x) {
-      cplx w = make_double2(0.0, 0.0);
-      for (int s = 0; s < ns; ++s) {
-        const cplx pv = partial[((size_t)s * nvec + e) * ncol + r * d2 + x];
-        w.x += pv.x; w.y += pv.y;
-      }
-      acc = b200::cfma(P[j * d2 + x], w, acc);
-    }
-    v_out[(size_t)e * ncol + c] = acc;
   }
 }
 
@@ -397,13 +341,17 @@ static int dyn_step_impl(void* stream_, int nvec, int chi_l, int chi_r, int d2,
   }
   unsigned int* tickets = (unsigned int*)work;
   cplx* partial = (cplx*)((unsigned char*)work + kTicketBytes);
-  static bool attr_set = false;
-  if (!attr_set) {
-    B200_CUDA_CHECK(cudaFuncSetAttribute(dyn_fused_kernel<1>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    B200_CUDA_CHECK(cudaFuncSetAttribute(dyn_fused_kernel<EV>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
+  {   // once per process, safe against concurrent first calls (ensemble worker threads)
+    static std::once_flag once;
+    static cudaError_t attr_rc = cudaSuccess;
+    std::call_once(once, [] {
+      attr_rc = cudaFuncSetAttribute(dyn_fused_kernel<1>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (attr_rc == cudaSuccess)
+        attr_rc = cudaFuncSetAttribute(dyn_fused_kernel<EV>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    });
+    B200_CUDA_CHECK(attr_rc);
   }
   // tickets are self-resetting, but `work` may be fresh memory
   if (clear_tickets) B200_CUDA_CHECK(cudaMemsetAsync(tickets, 0, kTicketBytes, stream));

@@ -60,6 +60,10 @@ constexpr int GP = PB + 1;        // padded leading dimension of the 32x32 work 
 constexpr int TS = PB + 4;        // row stride of the staged tile (complex): 576 B = 64 mod 128,
                                   // so the 8x4 / 4x8 DMMA fragments load without bank conflicts
 constexpr int DMMA_MIN_ROWS = 48; // slices at least this tall use the fp64 tensor-core path
+constexpr int SJ = PB + 2;        // row stride of the 32x32 rotation J in shared memory: the B
+                                  // fragments J[k0+t][8c+g] of a quarter warp then fall into
+                                  // eight different 16-byte bank groups (stride 32: 4-way
+                                  // conflicts, 257 M conflict cycles in the r02 ncu capture)
 
 struct Header {        // lives at the start of the workspace (device)
   int m, n, p, q, nb, transposed, keep, sweeps;
@@ -304,7 +308,7 @@ __device__ __forceinline__ double inner_threshold(double a, double b, double flo
 
 // One cyclic sweep of two-sided Jacobi on the 32x32 Hermitian matrix S.gr + i S.gi; only
 // the rounds in `mask` are visited.  The accumulated rotation J (columns sorted by
-// descending norm) is left in sj[32][32].
+// descending norm) is left in sj[32][SJ].
 //   * threads 0..255 own the 2x2 blocks of G in shared memory: thread (a, b) owns (rows
 //     of pair a) x (columns of pair b); G' = R_a^H G R_b touches only its own four
 //     entries, so the update is in place, and the diagonal-block thread (a, a) holds
@@ -455,7 +459,7 @@ __device__ void inner_sweep(InnerShared& S, unsigned mask, double floor2, double
   if (jthread) {
     const int dst = S.rank[lane];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) sj[(jrow0 + r) * PB + dst] = jv[r];
+    for (int r = 0; r < 8; ++r) sj[(jrow0 + r) * SJ + dst] = jv[r];
   }
   __syncthreads();
 }
@@ -501,7 +505,7 @@ __device__ __forceinline__ void apply_tile(const cplx* tile, int rows, const cpl
     }
 #pragma unroll 8
     for (int k = 0; k < PB; ++k) {
-      const cplx j0 = sj[k * PB + tx], j1 = sj[k * PB + tx + BC];
+      const cplx j0 = sj[k * SJ + tx], j1 = sj[k * SJ + tx + BC];
 #pragma unroll
       for (int x = 0; x < NR; ++x) {
         const cplx v = tile[(size_t)rr[x] * TS + k];
@@ -593,14 +597,14 @@ __device__ __forceinline__ void apply_dmma(const cplx* tile, int rows, const cpl
 #pragma unroll
     for (int c = 0; c < 4; ++c) { orr[c][0] = orr[c][1] = oi[c][0] = oi[c][1] = 0.0; }
     const cplx* pa = tile + (size_t)(r0 + g) * TS + t;
-    const cplx* pb = sj + t * PB + g;
+    const cplx* pb = sj + t * SJ + g;
 #pragma unroll 2
     for (int k0 = 0; k0 < PB; k0 += 4) {
       const cplx a = pa[k0];
       const double nai = -a.y;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const cplx bj = pb[k0 * PB + 8 * c];
+        const cplx bj = pb[k0 * SJ + 8 * c];
         dmma884(orr[c][0], orr[c][1], a.x, bj.x);
         dmma884(orr[c][0], orr[c][1], nai, bj.y);
         dmma884(oi[c][0], oi[c][1], a.x, bj.y);
@@ -650,7 +654,7 @@ jacobi_kernel(const QrSrc qsrc, const cplx* __restrict__ theta, long long rs, lo
   __shared__ double s_red[JT / 32];
   cplx* tile = reinterpret_cast<cplx*>(dyn_smem);          // [CHUNK][TS]
   cplx* sj = tile + (size_t)CHUNK_ROWS * TS;               // [32][32] rotation to apply
-  cplx* sg = sj + PB * PB;                                 // [32][32] scratch (Gram halves)
+  cplx* sg = sj + PB * SJ;                                 // [32][32] scratch (Gram halves)
 
   const int T = p + q;
   const int R = Rx + Rw;
@@ -1123,7 +1127,7 @@ __global__ void emit_kernel(const cplx* __restrict__ y, const double* __restrict
 }
 
 
-constexpr size_t kDynSmem = (size_t)CHUNK_ROWS * TS * sizeof(cplx) + 2 * PB * PB * sizeof(cplx);
+constexpr size_t kDynSmem = (size_t)CHUNK_ROWS * TS * sizeof(cplx) + (PB * SJ + PB * PB) * sizeof(cplx);
 
 // ------------------------------------------------------------------ rank-revealing QR front end
 using b200::qr::QrLayout;

@@ -61,9 +61,13 @@ def _run_concurrent(mine, run_member, concurrent, make_ops):
 
 
 def run_ensemble(n_members, run_member, device=None, group=None, concurrent=1,
-                 make_ops=None):
+                 make_ops=None, run_batch=None):
     """Run ``run_member(i)`` (-> real or complex ndarray, same shape for all i) for the
     members of this rank and gather everything on every rank.
+
+    ``run_batch(indices) -> sequence of per-member arrays`` (instead of ``run_member``) hands
+    this rank's whole share to one call: the lock-step engine (:func:`tempo_grid`) steps all of
+    them with one kernel launch per time step.
 
     ``concurrent`` > 1 keeps that many members of this rank in flight at once (one host
     thread + ops object + CUDA stream each); ``run_member`` is then called as
@@ -76,7 +80,10 @@ def run_ensemble(n_members, run_member, device=None, group=None, concurrent=1,
     else:
         world, rank = 1, 0
     mine = shard_indices(n_members, rank, world)
-    if concurrent > 1:
+    if run_batch is not None:
+        results = [np.asarray(r) for r in run_batch(mine)]
+        assert len(results) == len(mine)
+    elif concurrent > 1:
         results = _run_concurrent(mine, run_member, concurrent, make_ops)
     else:
         results = [np.asarray(run_member(i)) for i in mine]
@@ -177,3 +184,72 @@ def broadcast_process_tensor(pt, src=0, device=None, group=None, ops=None):
     if rank != src:
         pt._caps = caps  # pylint: disable=protected-access
     return pt
+
+
+def tempo_grid(influences, initial_state, unitary, propagators, dkmax, epsrel, num_steps,
+               device=None, group=None, ops=None, chunk=4096, chi_cap=None,
+               fallback_concurrency=12):
+    """BASELINE configs[4]: an ensemble of independent TEMPO runs (one per parameter point)
+    sharded over the ranks and, on every rank, advanced in LOCK-STEP by the batched engine
+    (:class:`oqupy_b200.batch.BatchedTempoBackend`: one kernel launch per time step for all
+    members of the rank).  ``influences``: (n_members, dkmax+1, d2, d2) influence matrices by
+    member and dk (what each member's ``influence(dk)`` callback would return,
+    oqupy/tempo.py:969-1020).  A member whose bond dimension outgrows the shared-memory
+    resident SVD (chi * d2 > 128, or an intermediate operand beyond 14272 elements) is re-run alone on the general device backend
+    (:func:`tempo_member`) -- still on the GPU.  Returns the dynamics
+    (n_members, num_steps+1, d, d) on every rank (one gather at the end), and the indices of
+    the members that took the general path."""
+    from .batch import BatchedTempoBackend  # pylint: disable=import-outside-toplevel
+    infl = np.asarray(influences)
+    n_members = infl.shape[0]
+    rho0 = np.asarray(initial_state, dtype=np.complex128)
+    d = rho0.shape[-1]
+    d2 = d * d
+    rerun = []
+
+    def run_batch(indices):
+        out = []
+        for c0 in range(0, len(indices), chunk):
+            idx = list(indices[c0:c0 + chunk])
+            st0 = np.broadcast_to(rho0.reshape(-1, d2), (len(idx), d2)) if rho0.ndim == 2 \
+                else rho0[idx].reshape(len(idx), d2)
+            be = BatchedTempoBackend(st0, infl[idx], unitary, propagators, np.ones(d2),
+                                     np.ones(d2), dkmax, epsrel, chi_cap=chi_cap, ops=ops)
+            _, s0 = be.initialize()
+            states = np.concatenate((s0[None], be.compute_steps(num_steps, strict=False)))
+            status = be.info()["status"]
+            states = np.swapaxes(states, 0, 1).reshape(len(idx), num_steps + 1, d, d).copy()
+            over = []
+            for k in np.nonzero(status)[0]:
+                if int(status[k]) != 2:
+                    raise RuntimeError(f"lock-step TEMPO member {idx[k]}: status {int(status[k])}")
+                over.append(int(k))
+            if over:        # the general device path, several members in flight at once
+                rerun.extend(int(idx[k]) for k in over)
+
+                def member(pos, member_ops=None):
+                    k = over[pos]
+                    st = rho0 if rho0.ndim == 2 else rho0[idx[k]]
+
+                    def member_props(step, pos_=k):
+                        return tuple(np.asarray(x)[pos_] if np.asarray(x).ndim == 3 else x
+                                     for x in propagators(step))
+                    return tempo_member(infl[idx[k]], member_props, st, dkmax, epsrel,
+                                        num_steps, unitary=unitary,
+                                        ops=member_ops if member_ops is not None else ops)
+                cuda = getattr(ops, "name", "cuda") == "cuda"
+                if cuda and len(over) > 1:
+                    from ._lib import CudaOps  # pylint: disable=import-outside-toplevel
+                    dev_index = ops.device.index if ops is not None else 0
+                    redo = _run_concurrent(list(range(len(over))), member,
+                                           min(fallback_concurrency, len(over)),
+                                           lambda: CudaOps(dev_index))
+                else:
+                    redo = [member(pos) for pos in range(len(over))]
+                for pos, k in enumerate(over):
+                    states[k] = redo[pos]
+            out.extend(states)
+        return out
+
+    res = run_ensemble(n_members, None, device=device, group=group, run_batch=run_batch)
+    return res, rerun

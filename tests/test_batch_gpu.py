@@ -81,3 +81,46 @@ def test_batched_tempo_capacity_is_reported():
     be.initialize()
     with pytest.raises(ob.B200Error):
         be.compute_steps(30)
+
+
+def test_mean_field_lock_step_matches_oracle():
+    """MeanFieldTempoBackend (tempo_backend.py:629-773) with a finite memory cut-off: all
+    systems of the model are members of ONE lock-step backend (one launch per time step);
+    live field feedback through the host callbacks, against MeanFieldTempoOracle."""
+    g = load_golden("tempo_c1_k20_eps7_n60")
+    dkmax, eps, steps = 8, 1e-7, 16
+    base = g["influences"][:dkmax + 1]
+    infls = [scaled(base, f) for f in (1.0, 1.6, 0.4)]
+    sz = np.array([1.0, 0.0, 0.0, -1.0])            # <sigma_z> from the vectorised state
+
+    def make_props(k):
+        def props(step, field, dfield):
+            ph = np.exp(-0.05j * (k + 1) * (field.real + 0.5 * dfield.real))
+            return g["prop_1"] * ph, g["prop_2"] * np.conj(ph)
+        return props
+
+    def dfield(step, states, field):
+        return -0.3 * field + 0.1 * sum(complex(sz @ s) for s in states)
+
+    def cfield(step, states, field, next_states):
+        return field + 0.05 * (dfield(step, states, field) + dfield(step, next_states, field)) / 2
+
+    args = ([g["initial_state"]] * 3, 0.2 + 0.1j,
+            [lambda dk, m=m: None if dk < 0 else m[dk] for m in infls],
+            [g["unitary"]] * 3, [make_props(k) for k in range(3)], cfield, dfield,
+            [np.ones(4)] * 3, [np.ones(4)] * 3, dkmax, eps)
+    be = ob.MeanFieldTempoBackend(*args)
+    assert be._batched is not None                      # the lock-step path is taken
+    orc = onp.MeanFieldTempoOracle(*args)
+    be.initialize()
+    orc.initialize()
+    for k in range(steps):
+        s1, st1, f1 = be.compute_step()
+        s2, st2, f2 = orc.compute_step()
+        assert s1 == s2 == k + 1
+        tol = 1e-9 if k < 4 else TEMPO_STATE_ATOL(eps)
+        np.testing.assert_allclose(np.array(st1), np.array(st2), atol=tol, rtol=0)
+        assert abs(f1 - f2) < tol
+    for mine, ref in zip(be.get_bond_dimensions(), [n.bond_dimensions() for n in orc.networks]):
+        diff = [abs(a - b) for a, b in zip(mine, ref)]
+        assert len(mine) == len(ref) and max(diff) <= 1 and sum(diff) <= 3

@@ -22,6 +22,13 @@ for job in "$@"; do
     teacher2)  timeout 1500 python tools/teacher_forced.py 32 34 > gpurun_out/${TAG}_teacher_32_34.json 2> gpurun_out/${TAG}_teacher2.err ;;
     batch)     timeout 900 python -m pytest tests/test_batch_gpu.py -x -q > gpurun_out/${TAG}_batch.log 2>&1 ;;
     batchbench) timeout 900 python tools/batch_bench.py 592 60 25 > gpurun_out/${TAG}_batchbench.json 2> gpurun_out/${TAG}_batchbench.err ;;
+    ncu_svd)   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"qrcp_kernel|jacobi_kernel|apply_q_kernel" -c 6 -f -o gpurun_out/${TAG}_svd python tools/ncu_targets.py svd > gpurun_out/${TAG}_ncu_svd.log 2>&1 ;;
+    ncu_batch) timeout 1200 ncu --set full --clock-control none --import-source on -k regex:tempo_batch_step_kernel -s 22 -c 1 -f -o gpurun_out/${TAG}_batch python tools/ncu_targets.py batch > gpurun_out/${TAG}_ncu_batch.log 2>&1 ;;
+    ncu_list)  timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -s 43000 -c 3300 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/${TAG}_ncu_list.log 2>&1 ;;
+    c5)        timeout 1500 python tools/c5_bench.py 64 200 > gpurun_out/${TAG}_c5_n1.json 2> gpurun_out/${TAG}_c5_n1.err ;;
+    c5small)   timeout 900 python tools/c5_bench.py 24 100 > gpurun_out/${TAG}_c5small.json 2> gpurun_out/${TAG}_c5small.err ;;
+    c5_n2)     timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/c5_bench.py 64 200 > gpurun_out/${TAG}_c5_n2.json 2> gpurun_out/${TAG}_c5_n2.err ;;
+    bench_n2)  timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_n2.json 2> gpurun_out/${TAG}_bench_n2.err ;;
     *) echo "unknown job $job" ;;
   esac
   echo "== $job rc=$?"
