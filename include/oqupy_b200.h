@@ -142,9 +142,9 @@ int b200_svd_config(const char* key, double value);
  * for all partials, 4 reduce + convergence test, 5 inner 32x32 sweep, 6 sort + publish
  * J, 7 apply + hand-over, 8 sweep vote, 9 norms/rank, 10..14 spare, 15 #stages} */
 int b200_svd_phase_cycles(void* stream, const void* work, long long* out16);
-/* the same for the rank-revealing QR stage: {0 offer the best column, 1 wait for all offers,
+/* the same for the rank-revealing QR stage: {0 pick the CTA's best column, 1 wait for all offers,
  * 2 select the panel, 3 fetch it, 4 factorise it, 5 file the pivot columns, 6 apply the
- * reflectors to the CTA's own columns, 7 #hand-shakes} */
+ * reflectors to the CTA's own columns, 7 publish the offer} */
 int b200_svd_qr_phase_cycles(void* stream, const void* work, long long* out8);
 
 /* ---------------------------------------------------------------------------

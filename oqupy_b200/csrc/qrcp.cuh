@@ -37,8 +37,8 @@ constexpr int QR_MAX_P = 8192;        // rows (apply_q keeps p / threads <= 8 ro
 struct QrHeader {
   int k, status;
   double fro2, stop2;
-  long long phase_cycles[8];  // CTA 0 (PROF): 0 offer, 1 poll wait, 2 select, 3 fetch, 4 panel,
-                              // 5 file pivots, 6 apply, 7 hand-shakes
+  long long phase_cycles[8];  // CTA 0 (PROF): 0 pick own best, 1 poll wait, 2 select, 3 fetch,
+                              // 4 panel, 5 file pivots, 6 apply, 7 publish the offer
 };
 
 struct QrLayout {
@@ -186,6 +186,7 @@ __global__ void __launch_bounds__(QT, 1) qrcp_kernel(const QrArgs A) {
       if (lane == 0) { s_bl = (best >= 0.0) ? bl : -1; s_best = (best >= 0.0) ? best : 0.0; }
     }
     __syncthreads();
+    QPHASE(0)
     // ---- B. offer it (rows j..p-1); the release-store of the tag is this CTA's arrival
     const int bl = s_bl;
     if (bl >= 0) {
@@ -201,7 +202,7 @@ __global__ void __launch_bounds__(QT, 1) qrcp_kernel(const QrArgs A) {
       st_release_u64(A.cand_tag + (size_t)(par * G + me) * TAG_STRIDE,
                      vb35 | ((unsigned long long)(shake & 0x7fffu) << 14) | idx);
     }
-    QPHASE(0)
+    QPHASE(7)
     // ---- C. poll the G offers; the PB largest above the stop level form the panel
     if (warp == 0) {
       unsigned long long key[5];       // norm^2 (35 bits) | 0x3fff - column (14) | CTA (8)
@@ -448,7 +449,6 @@ __global__ void __launch_bounds__(QT, 1) qrcp_kernel(const QrArgs A) {
     j += bt;
     __syncthreads();
     QPHASE(6)
-    if constexpr (PROF) ++pc[7];
   }
   const int k = j;
 

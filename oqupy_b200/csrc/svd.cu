@@ -131,6 +131,7 @@ int device_sms() {
 //   [0]            grid barrier counter
 //   [1]            spare
 //   [2 .. 2+NFLAGS)           rotated-stage count per sweep
+//   [2+NFLAGS .. 2+2*NFLAGS)  stages per sweep whose violation was NOT small (prediction)
 //   ready[nb*R]               stages completed per (block, slice)
 //   cnt[2*S]                  slices that published their partial Gram (double-buffered)
 __host__ Layout make_layout(int m, int n) {
@@ -198,7 +199,7 @@ __host__ Layout make_layout(int m, int n) {
   size_t off = 0;
   L.header = off; off = align256(off + sizeof(Header));
   L.ctrl = off;
-  L.ctrl_bytes = sizeof(int) * (size_t)(2 + NFLAGS + (size_t)L.nb * L.R + 2 * (size_t)L.S);
+  L.ctrl_bytes = sizeof(int) * (size_t)(2 + 2 * NFLAGS + (size_t)L.nb * L.R + 2 * (size_t)L.S);
   L.ctrl_bytes = (L.ctrl_bytes + 7) & ~(size_t)7;
   L.blkmax = L.ctrl + L.ctrl_bytes;          // largest column norm^2 per block (zeroed with ctrl)
   L.ctrl_bytes += sizeof(double) * (size_t)L.nb;
@@ -294,6 +295,7 @@ struct InnerShared {
   int rank[PB];                    // position of column c after sorting by norm
   unsigned mask;                   // rounds that hold a violating pair
   int viol;
+  int violb;                       // a violation too large for the convergence prediction
 };
 
 // threshold of the inner rotations: a pair is rotated when |g|^2 exceeds it
@@ -648,7 +650,7 @@ jacobi_kernel(const QrSrc qsrc, const cplx* __restrict__ theta, long long rs, lo
               int Rx, int Rw, int RSx, int RSw, int SE, int transposed, int minmn,
               double tol, double eps, double neg_rel, int rin, long long rsi, int cin,
               long long csi, double kappa0, double* __restrict__ blkmax, double drop_rel,
-              int npass, int U) {
+              int npass, int U, int predict_on) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ InnerShared S;
   __shared__ double s_red[JT / 32];
@@ -661,7 +663,8 @@ jacobi_kernel(const QrSrc qsrc, const cplx* __restrict__ theta, long long rs, lo
   const int S_slots = nb / 2;
   int* bar = ctrl;
   int* flags = ctrl + 2;
-  int* ready = flags + NFLAGS;
+  int* flagsb = flags + NFLAGS;
+  int* ready = flagsb + NFLAGS;
   int* cnt = ready + (size_t)nb * R;
   int epoch = 0;
   const int t = threadIdx.x;
@@ -746,6 +749,8 @@ jacobi_kernel(const QrSrc qsrc, const cplx* __restrict__ theta, long long rs, lo
 
   int sweeps_done = 0, total_rot = 0, status = 1;
   const double tol2 = tol * tol;
+  const double tolp2 = 1e-14;
+  const bool predict = (eps > 0.0) && (neg_rel > 0.0) && (predict_on != 0);
   const double neg2 = (neg_rel * fro) * (neg_rel * fro);
   // DEFLATION: trailing blocks whose columns have all sunk below drop_rel*||X||_F
   // (1e-5 eps ||X||_F, 1e-3 of the negligible level) leave the tournament at the end of a
@@ -762,7 +767,7 @@ jacobi_kernel(const QrSrc qsrc, const cplx* __restrict__ theta, long long rs, lo
   int pa = 0, pb = 0;
   for (int sweep = 0; sweep < MAX_SWEEPS; ++sweep) {
     const int S_act = nb_act / 2;
-    int my_rot = 0;
+    int my_rot = 0, my_rotb = 0;
     // absolute floor: 8 eps ||X||_F, doubled every sweep after FLOOR_GROW_AFTER so that
     // the iteration always terminates
     double kappa = kappa0;
@@ -784,6 +789,7 @@ jacobi_kernel(const QrSrc qsrc, const cplx* __restrict__ theta, long long rs, lo
           while (ld_acquire(ready + pb * R + r_slice) < g) {}
           S.mask = 0u;
           S.viol = 0;
+          S.violb = 0;
         }
         __syncthreads();
         PHASE(0)
@@ -875,7 +881,7 @@ jacobi_kernel(const QrSrc qsrc, const cplx* __restrict__ theta, long long rs, lo
         // whether the stage rotates at all, `mask` which inner rounds are visited
         {
           unsigned my_mask = 0u;
-          int viol = 0;
+          int viol = 0, violb = 0;
 #pragma unroll
           for (int e = t; e < PB * PB; e += JT) {
             const int i = e >> 5, j = e & 31;
@@ -883,16 +889,26 @@ jacobi_kernel(const QrSrc qsrc, const cplx* __restrict__ theta, long long rs, lo
               const double a = S.gr[i][i], b = S.gr[j][j];
               const double xr = S.gr[i][j], xi = S.gi[i][j];
               const double g2 = xr * xr + xi * xi;
-              if (!pair_converged(a, b, g2, tol2, floor2, neg2)) viol = 1;
+              if (!pair_converged(a, b, g2, tol2, floor2, neg2)) {
+                viol = 1;
+                // "not small": |cos| > 1e-7 (or 4x the absolute floor) between columns that
+                // matter; negligible pairs never block the prediction (only their joint
+                // Frobenius mass is used)
+                const double big = fmax(a, b);
+                if (big >= neg2 && g2 > big * (tolp2 * fmax(fmin(a, b), 0.0) + 16.0 * floor2))
+                  violb = 1;
+              }
               if (g2 > inner_threshold(a, b, floor2, neg2) && fmax(a, b) > 0.0)
                 my_mask |= 1u << round_of_pair(i, j);
             }
           }
           my_mask = __reduce_or_sync(0xffffffffu, my_mask);
           viol = __any_sync(0xffffffffu, viol);
+          violb = __any_sync(0xffffffffu, violb);
           if ((t & 31) == 0) {
             if (my_mask) atomicOr(&S.mask, my_mask);
             if (viol) S.viol = 1;
+            if (violb) S.violb = 1;
           }
         }
         __syncthreads();
@@ -901,7 +917,7 @@ jacobi_kernel(const QrSrc qsrc, const cplx* __restrict__ theta, long long rs, lo
         if (need) {
           inner_sweep(S, S.mask, floor2, neg2, sj, npass);
           PHASE(5)
-          if (leader) ++my_rot;
+          if (leader) { ++my_rot; if (S.violb) ++my_rotb; }
           __syncthreads();
         }
         // largest column norm^2 of the two blocks as they leave this stage (columns are
@@ -950,12 +966,20 @@ jacobi_kernel(const QrSrc qsrc, const cplx* __restrict__ theta, long long rs, lo
     }
     // convergence vote: flags[sweep] counts the stages rotated in this sweep
     if (t == 0 && my_rot) atomicAdd(&flags[sweep], my_rot);
+    if (t == 0 && my_rotb) atomicAdd(&flagsb[sweep], my_rotb);
     grid_barrier(bar, epoch);
     const int rot = __ldcg(&flags[sweep]);
+    const int rotb = __ldcg(&flagsb[sweep]);
     PHASE(8)
     total_rot += rot;
     sweeps_done = sweep + 1;
     if (rot == 0) { status = 0; break; }
+    // PREDICTED convergence (truncating mode only): every violation of this sweep was small
+    // (|cos| <= 1e-7 or within 4x of the absolute floor) and has just been rotated away; what
+    // the rotations leave behind is second order, n * 1e-14 in |cos| -- below the 1e-11 target.
+    // The rotation-free verification sweep (a full pass of Gram matrices and hand-shakes) is
+    // skipped.
+    if (predict && rotb == 0) { status = 0; break; }
     g_base += nb_act - 1;
     if (drop2 > 0.0 && nb_act > 2) {      // every CTA derives the same nb_act from blkmax
       if (t == 0) s_last = 0;
@@ -1134,7 +1158,7 @@ using b200::qr::QrLayout;
 using b200::qr::QrHeader;
 
 struct QrKnobs {
-  int on, minq, cols, phases, panel;
+  int on, minq, cols, phases, panel, predict;
   double theta;
 };
 QrKnobs& qr_knobs() {
@@ -1150,6 +1174,7 @@ QrKnobs& qr_knobs() {
     v.phases = getenv("B200_SVD_PHASES") ? 1 : 0;
     v.panel = (e = getenv("B200_SVD_QR_PANEL")) ? atoi(e) : 0;      // 0: by operand height
     v.theta = (e = getenv("B200_SVD_QR_THETA")) ? atof(e) : 0.5;
+    v.predict = (e = getenv("B200_SVD_PREDICT")) ? atoi(e) : 1;
     return v;
   }();
   return k;
@@ -1311,10 +1336,11 @@ int launch_jacobi(cudaStream_t stream, unsigned char* base, const QrSrc& qsrc, c
   if (knobs().kappa >= 0.0) kappa0 = knobs().kappa;
   if (knobs().negrel >= 0.0) neg_rel = knobs().negrel * ((eps > 0.0) ? eps : 0.0);
   QrSrc qs = qsrc;
+  int predict_on = qr_knobs().predict;
   void* args[] = {&qs, &th, &rs, &cs, &y, &gpart, &ctrl, &sig2, &sval, &perm, &hdr,
                   &info_host, &p, &q, &nb, &Rx, &Rw, &RSx, &RSw, &SE, &tr, &minmn, &tol, &eps,
                   &neg_rel, &rin, &rsi, &cin, &csi, &kappa0, &blkmax, &drop_rel,
-                  &npass, &U};
+                  &npass, &U, &predict_on};
   const int grid = L.SE * L.R;
   void* fn = qr_knobs().phases ? (void*)jacobi_kernel<true> : (void*)jacobi_kernel<false>;
   b200::profile_begin(stream, 0);
@@ -1546,8 +1572,8 @@ extern "C" int b200_svd_phase_cycles(void* stream_, const void* work, long long*
   return B200_OK;
 }
 
-/* the same for the rank-revealing QR stage (CTA 0): {0 offer, 1 poll wait, 2 select, 3 fetch
- * the panel, 4 factorise the panel, 5 file the pivots, 6 apply to own columns, 7 hand-shakes} */
+/* the same for the rank-revealing QR stage (CTA 0): {0 pick own best, 1 poll wait, 2 select, 3 fetch
+ * the panel, 4 factorise the panel, 5 file the pivots, 6 apply to own columns, 7 publish} */
 extern "C" int b200_svd_qr_phase_cycles(void* stream_, const void* work, long long* out8) {
   if (!work || !out8) { b200::set_error("b200_svd_qr_phase_cycles: invalid argument"); return B200_EINVAL; }
   QrHeader h;
@@ -1626,6 +1652,7 @@ extern "C" int b200_svd_config(const char* key, double value) {
   else if (k == "qr_cols") qr_knobs().cols = (value < 1.0) ? 1 : (int)value;
   else if (k == "qr_panel") qr_knobs().panel = (int)value;
   else if (k == "qr_theta") qr_knobs().theta = value;
+  else if (k == "predict") qr_knobs().predict = (value != 0.0);
   else { b200::set_error("b200_svd_config: unknown key %s", key); return B200_EINVAL; }
   return B200_OK;
 }

@@ -13,6 +13,8 @@ for job in "$@"; do
     gputests)  timeout 2400 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_gputests.log 2>&1 ;;
     bench)     timeout 1500 python bench.py --steps 20 --warmup 5 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err ;;
     bench_noqr) B200_SVD_QR=0 timeout 1500 python bench.py --steps 20 --warmup 5 --no-cpu > gpurun_out/${TAG}_bench_noqr.json 2> gpurun_out/${TAG}_bench_noqr.err ;;
+    bench_nopred) B200_SVD_PREDICT=0 timeout 1500 python bench.py --steps 20 --warmup 5 --no-cpu > gpurun_out/${TAG}_bench_nopred.json 2> gpurun_out/${TAG}_bench_nopred.err ;;
+    svdstep)   timeout 900 python tools/svd_profile_step.py 40 > gpurun_out/${TAG}_svdstep.log 2>&1 ;;
     stepprof)  timeout 600 python tools/step_profile.py 50 300 > gpurun_out/${TAG}_stepprof.jsonl 2> gpurun_out/${TAG}_stepprof.err ;;
     stepprof_noqr) B200_SVD_QR=0 timeout 600 python tools/step_profile.py 50 300 > gpurun_out/${TAG}_stepprof_noqr.jsonl 2> gpurun_out/${TAG}_stepprof_noqr.err ;;
     phases)    B200_SVD_PHASES=1 timeout 900 python tools/qr_check.py oracle25 > gpurun_out/${TAG}_phases.log 2>&1 ;;
