@@ -31,7 +31,8 @@ namespace qr {
 
 constexpr int QT = 512;               // threads of the QRCP kernel
 constexpr int QW = QT / 32;
-constexpr int QR_SMEM_BYTES = 226 * 1024;  // dynamic shared memory requested for the kernel
+constexpr int QR_SMEM_BYTES = 218 * 1024;  // dynamic shared memory requested for the kernel
+                                           // (+ ~8 KB static = the 227 KB a CTA can have)
 constexpr int QR_MAX_P = 8192;        // rows (apply_q keeps p / threads <= 8 rows per thread)
 
 struct QrHeader {
@@ -88,6 +89,8 @@ struct QrArgs {
   int nc_res;                 // local columns resident in shared memory
   int ncmax;
   int panel;                  // pivots taken per hand-shake, at most (<= PBMAX)
+  int fast_panel;             // 1: one warp per panel column, one CTA barrier per pivot (short
+                              // columns); 0: two warps per column
 };
 
 constexpr int PBMAX = 8;
@@ -136,6 +139,13 @@ __global__ void __launch_bounds__(QT, 1) qrcp_kernel(const QrArgs A) {
   __shared__ int s_tslot[PBMAX];          // panel slot taken as pivot t
   __shared__ cplx s_tau[PBMAX], s_scale[PBMAX];
   __shared__ double s_beta[PBMAX];
+  __shared__ cplx s_vv[PBMAX][PBMAX];     // v_t^H v_s (s < t) of the reflectors of a panel
+  __shared__ cplx s_fd[QW][PBMAX];        // partial v_t^H y per warp (columns split over warps)
+  __shared__ cplx s_ff[QW][PBMAX];        // the coefficients f_t of a column (per column slot)
+  __shared__ cplx s_fs[QW][PBMAX];        // f_t * scale_t
+  __shared__ double s_fn[QW];
+  __shared__ double s_full[PBMAX];        // remaining norm^2 of a panel column incl. its diagonal
+  __shared__ int s_eready;                // reflectors whose scalars are published (fast panel)
 
   auto colptr = [&](int lc) -> cplx* {
     return (lc < A.nc_res) ? scols + (size_t)lc * p : A.a + (size_t)(me + lc * G) * p;
@@ -297,6 +307,130 @@ __global__ void __launch_bounds__(QT, 1) qrcp_kernel(const QrArgs A) {
     const double thr = fmax(s_stop2, A.theta2 * s_outside);
     unsigned rem = (1u << np) - 1u;       // panel slots not yet taken
     int bt = 0;
+    if (A.fast_panel) {
+      // SHORT columns.  The fp64 pipe issues one warp instruction per 4 cycles and SM
+      // sub-partition whatever the number of active lanes, so work repeated in every WARP is
+      // what costs here:
+      //  * warp c < np owns panel column c: dot product and update of a step without any
+      //    cross-warp reduction, ONE CTA barrier per pivot;
+      //  * the reflector's scalars (sqrt, two divisions) are formed by the pivot's own warp
+      //    only -- it has nothing else to do -- while the others already run their dot
+      //    products (which do not need them) and pick the scalars up through a flag;
+      //  * the pivot choice is an integer arg-max over the bit patterns of the remaining
+      //    norms (no fp64 instruction);
+      //  * the spare warps form the inner products x_t^H x_s of the reflectors (phase F).
+      // The new diagonal entry y[row] is written one step late: row `row` of every column is
+      // still being read for the pivot choice.
+      const int c = warp;
+      const bool owner = c < np;
+      cplx* y = pan + (size_t)(owner ? c : 0) * p;
+      if (owner) {
+        double nn = 0.0, al2 = 0.0;
+        for (int i = j + lane; i < p; i += 32) {
+          const cplx v = y[i];
+          const double a2 = fma(v.x, v.x, v.y * v.y);
+          if (i == j) al2 = a2; else nn += a2;
+        }
+        nn = warp_sum(nn);
+        if (lane == 0) { s_pn[c] = nn; s_full[c] = nn + al2; }
+      }
+      if (tid == 0) s_eready = 0;
+      __syncthreads();
+      cplx pend = make_double2(0.0, 0.0);
+      int pend_row = -1;
+      for (int t = 0; t < np; ++t) {
+        const int row = j + t;
+        if (pend_row >= 0 && lane == 0) y[pend_row] = pend;
+        pend_row = -1;
+        // arg-max of the remaining full norms (non-negative doubles order like integers);
+        // ties go to the lowest slot
+        int bc;
+        double bfull;
+        {
+          const bool cand = (lane < np) && ((rem >> lane) & 1u);
+          const unsigned long long key =
+              cand ? (unsigned long long)__double_as_longlong(s_full[lane]) + 1ull : 0ull;
+          const unsigned hi = __reduce_max_sync(0xffffffffu, (unsigned)(key >> 32));
+          const unsigned lo = __reduce_max_sync(
+              0xffffffffu, ((unsigned)(key >> 32) == hi) ? (unsigned)(key & 0xffffffffull) : 0u);
+          const unsigned long long m = ((unsigned long long)hi << 32) | lo;
+          const unsigned who = __ballot_sync(0xffffffffu, cand && key == m);
+          bc = __ffs(who) - 1;
+          bfull = __longlong_as_double((long long)(m - 1ull));
+        }
+        if (t > 0 && !(bfull > thr)) break;
+        rem &= ~(1u << bc);
+        const cplx* x0 = pan + (size_t)bc * p;
+        const bool more = !(rem == 0u || t + 1 >= np);
+        const bool act = more && owner && ((rem >> c) & 1u);
+        if (c == bc) {
+          // the pivot's warp: scalars of the reflector (unscaled: v = [1 ; scale * x])
+          const cplx alpha = x0[row];
+          const double xnorm2 = s_pn[bc];
+          double beta = alpha.x;
+          cplx tau = make_double2(0.0, 0.0), scale = make_double2(0.0, 0.0);
+          if (xnorm2 > 0.0 || alpha.y != 0.0) {
+            const double an = sqrt(fma(alpha.x, alpha.x, fma(alpha.y, alpha.y, xnorm2)));
+            beta = (alpha.x >= 0.0) ? -an : an;
+            const double ib = 1.0 / beta;
+            tau = make_double2((beta - alpha.x) * ib, -alpha.y * ib);
+            const double dx = alpha.x - beta, dy = alpha.y;
+            const double dn = 1.0 / fma(dx, dx, dy * dy);
+            scale = make_double2(dx * dn, -dy * dn);
+          }
+          if (lane == 0) {
+            s_tslot[t] = bc; s_tau[t] = tau; s_beta[t] = beta; s_scale[t] = scale;
+            __threadfence_block();
+            *(volatile int*)&s_eready = t + 1;
+          }
+        } else if (!owner) {
+          // spare warps: x_t^H x_s over rows > row for the earlier reflectors s < t
+          for (int s_ = c - np; s_ < t; s_ += QW - np) {
+            const cplx* xs = pan + (size_t)s_tslot[s_] * p;
+            cplx acc = make_double2(0.0, 0.0);
+            for (int i = row + 1 + lane; i < p; i += 32) acc = cfma(cconj(x0[i]), xs[i], acc);
+            acc.x = warp_sum(acc.x);
+            acc.y = warp_sum(acc.y);
+            if (lane == 0) s_vv[t][s_] = acc;
+          }
+        }
+        bt = t + 1;
+        if (!more) break;
+        if (act) {
+          const cplx yr = y[row];
+          cplx w = make_double2(0.0, 0.0);
+          for (int i = row + 1 + lane; i < p; i += 32) w = cfma(cconj(x0[i]), y[i], w);
+          w.x = warp_sum(w.x);
+          w.y = warp_sum(w.y);
+          while (*(volatile int*)&s_eready < t + 1) {}
+          __threadfence_block();
+          const volatile double* vt_ = reinterpret_cast<const volatile double*>(&s_tau[t]);
+          const volatile double* vs_ = reinterpret_cast<const volatile double*>(&s_scale[t]);
+          const cplx tau = make_double2(vt_[0], vt_[1]);
+          const cplx scale = make_double2(vs_[0], vs_[1]);
+          cplx tot = cmul(cconj(scale), w);
+          tot.x += yr.x; tot.y += yr.y;
+          const cplx f = cmul(cconj(tau), tot);          // y -= f v
+          const cplx fs = cmul(f, scale);
+          double nn = 0.0, al2 = 0.0;
+          for (int i = row + 1 + lane; i < p; i += 32) {
+            const cplx xi = x0[i];
+            cplx yy = y[i];
+            yy.x -= fs.x * xi.x - fs.y * xi.y;
+            yy.y -= fs.x * xi.y + fs.y * xi.x;
+            y[i] = yy;
+            const double a2 = fma(yy.x, yy.x, yy.y * yy.y);
+            if (i == row + 1) al2 = a2; else nn += a2;
+          }
+          nn = warp_sum(nn);
+          if (lane == 0) { s_pn[c] = nn; s_full[c] = nn + al2; }
+          pend = make_double2(yr.x - f.x, yr.y - f.y);
+          pend_row = row;
+        }
+        __syncthreads();
+      }
+      if (pend_row >= 0 && lane == 0) y[pend_row] = pend;
+    } else {
     {
       // remaining norms^2 over rows > j of every panel column: two warps per column
       const int c = warp >> 1, half = warp & 1;
@@ -381,6 +515,7 @@ __global__ void __launch_bounds__(QT, 1) qrcp_kernel(const QrArgs A) {
       if (lane == 0) s_pn[warp] = nn;
       __syncthreads();
     }
+    }
     // (the break conditions above are thread-uniform: they only read shared memory)
     __syncthreads();
     if (tid < bt) done[s_pidx[s_tslot[tid]]] = 1;
@@ -411,6 +546,7 @@ __global__ void __launch_bounds__(QT, 1) qrcp_kernel(const QrArgs A) {
       A.tauc[j + tid] = s_tau[tid];
     }
     QPHASE(5)
+    if (!A.fast_panel) {
     // ---- F. y <- H_bt^H ... H_1^H y on my remaining columns, one warp per column; exact
     //         remaining norms (rows >= j + bt) in the last pass
     for (int lc = warp; lc < NC; lc += QW) {
@@ -445,6 +581,146 @@ __global__ void __launch_bounds__(QT, 1) qrcp_kernel(const QrArgs A) {
       }
       nn = warp_sum(nn);
       if (lane == 0) vn2[lc] = nn;
+    }
+    } else {
+    // ---- F (short columns). y <- H_bt^H ... H_1^H y on my remaining columns in TWO passes
+    //         over the rows instead of bt dependent dot/update pairs:  with d_t = v_t^H y on
+    //         the column as it stands and C[t][s] = v_t^H v_s, the coefficients follow from
+    //         f_t = conj(tau_t) (d_t - sum_{s<t} f_s C[t][s]), then y -= sum_t f_t v_t.
+    //         Rows of a column are split over `wpc` warps; the bt partial dot products of a warp
+    //         are reduced in one transposing butterfly (16 adds instead of 80); ONE warp per
+    //         column solves the recurrence, one reflector per lane.  Exact remaining norms
+    //         (rows >= j + bt) come out of the second pass.
+    {
+      const cplx* xp[PBMAX];
+#pragma unroll
+      for (int t = 0; t < PBMAX; ++t) xp[t] = pan + (size_t)s_tslot[(t < bt) ? t : 0] * p;
+      if (tid < bt * (bt - 1) / 2) {      // C[t][s] from the raw inner products x_t^H x_s
+        int t = 1, s_ = tid;
+        while (s_ >= t) { s_ -= t; ++t; }
+        const cplx ss = s_scale[s_];
+        cplx v = cmul(cconj(s_scale[t]), s_vv[t][s_]);
+        const cplx h = pan[(size_t)s_tslot[s_] * p + j + t];
+        v.x += h.x; v.y += h.y;
+        s_vv[t][s_] = cmul(v, ss);
+      }
+      const int wpc_ = (NC <= 4) ? 4 : ((NC <= 8) ? 2 : 1);
+      if (wpc_ == 1) __syncthreads();     // (otherwise the barrier after the first pass does it)
+      const int wpc = (NC <= 4) ? 4 : ((NC <= 8) ? 2 : 1);     // warps per column
+      const int cpb = QW / wpc;                                 // columns per batch
+      const int part = warp % wpc, cs = warp / wpc;
+      for (int lc0 = 0; lc0 < NC; lc0 += cpb) {
+        const int lc = lc0 + cs;
+        const bool live = (lc < NC) && !done[me + lc * G];
+        cplx* col = live ? colptr(lc) : nullptr;
+        if (live) {
+          double v[2 * PBMAX];
+#pragma unroll
+          for (int t = 0; t < 2 * PBMAX; ++t) v[t] = 0.0;
+          for (int i = j + part * 32 + lane; i < p; i += 32 * wpc) {
+            const cplx yi = col[i];
+#pragma unroll
+            for (int t = 0; t < PBMAX; ++t)
+              if (t < bt && i > j + t) {
+                const cplx xi = xp[t][i];
+                v[2 * t] = fma(xi.x, yi.x, v[2 * t]); v[2 * t] = fma(xi.y, yi.y, v[2 * t]);
+                v[2 * t + 1] = fma(xi.x, yi.y, v[2 * t + 1]);
+                v[2 * t + 1] = fma(-xi.y, yi.x, v[2 * t + 1]);
+              }
+          }
+          // transposing butterfly: lane l ends up with entry (l >> 1) & 15 summed over the warp
+#pragma unroll
+          for (int h = PBMAX, off = 16; h >= 1; h >>= 1, off >>= 1) {
+            const bool upper = (lane & off) != 0;
+#pragma unroll
+            for (int k_ = 0; k_ < h; ++k_) {
+              const double keep = upper ? v[k_ + h] : v[k_];
+              const double send = upper ? v[k_] : v[k_ + h];
+              v[k_] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+          }
+          v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+          if ((lane & 1) == 0) reinterpret_cast<double*>(&s_fd[warp][0])[lane >> 1] = v[0];
+        }
+        if (wpc > 1) __syncthreads(); else __syncwarp();
+        // the column's solver warp (spread over the SM sub-partitions): lane t owns reflector t
+        if (live && part == cs % wpc) {
+          cplx tot = make_double2(0.0, 0.0), sct = make_double2(0.0, 0.0);
+          cplx tau = make_double2(0.0, 0.0);
+          if (lane < bt) {
+            cplx d = s_fd[cs * wpc][lane];
+            for (int u = 1; u < wpc; ++u) { const cplx o = s_fd[cs * wpc + u][lane]; d.x += o.x; d.y += o.y; }
+            sct = s_scale[lane];
+            tau = s_tau[lane];
+            const cplx yr = col[j + lane];
+            tot = cmul(cconj(sct), d);
+            tot.x += yr.x; tot.y += yr.y;
+          }
+          cplx f = make_double2(0.0, 0.0);
+          for (int s_ = 0; s_ < bt; ++s_) {
+            const cplx fc = cmul(cconj(tau), tot);
+            const double fx = __shfl_sync(0xffffffffu, fc.x, s_);
+            const double fy = __shfl_sync(0xffffffffu, fc.y, s_);
+            if (lane == s_) f = make_double2(fx, fy);
+            if (lane > s_ && lane < bt) {
+              const cplx cv = s_vv[lane][s_];
+              tot.x -= fx * cv.x - fy * cv.y;
+              tot.y -= fx * cv.y + fy * cv.x;
+            }
+          }
+          if (lane < PBMAX) {
+            s_ff[cs][lane] = f;
+            s_fs[cs][lane] = cmul(f, sct);
+          }
+        }
+        if (wpc > 1) __syncthreads(); else __syncwarp();
+        double nn = 0.0;
+        if (live) {
+          cplx fs[PBMAX];
+#pragma unroll
+          for (int t = 0; t < PBMAX; ++t) fs[t] = s_fs[cs][t];
+          for (int i = j + part * 32 + lane; i < p; i += 32 * wpc) {
+            cplx yy = col[i];
+            if (i >= j + bt) {
+#pragma unroll
+              for (int t = 0; t < PBMAX; ++t)
+                if (t < bt) {
+                  const cplx xi = xp[t][i];
+                  yy.x -= fs[t].x * xi.x - fs[t].y * xi.y;
+                  yy.y -= fs[t].x * xi.y + fs[t].y * xi.x;
+                }
+              nn = fma(yy.x, yy.x, nn); nn = fma(yy.y, yy.y, nn);
+            } else {
+#pragma unroll
+              for (int t = 0; t < PBMAX; ++t)
+                if (t < bt) {
+                  if (i > j + t) {
+                    const cplx xi = xp[t][i];
+                    yy.x -= fs[t].x * xi.x - fs[t].y * xi.y;
+                    yy.y -= fs[t].x * xi.y + fs[t].y * xi.x;
+                  } else if (i == j + t) {
+                    const cplx ft = s_ff[cs][t];
+                    yy.x -= ft.x; yy.y -= ft.y;
+                  }
+                }
+            }
+            col[i] = yy;
+          }
+          nn = warp_sum(nn);
+        }
+        if (wpc > 1) { if (lane == 0) s_fn[warp] = nn; }
+        else if (live && lane == 0) vn2[lc] = nn;
+        if (wpc == 1) __syncwarp();
+      }
+      if (wpc > 1) {      // (a single batch) the partial norms meet after the CTA barrier
+        __syncthreads();
+        if (tid < NC && !done[me + tid * G]) {
+          double tot = 0.0;
+          for (int u = 0; u < wpc; ++u) tot += s_fn[tid * wpc + u];
+          vn2[tid] = tot;
+        }
+      }
+    }
     }
     j += bt;
     __syncthreads();

@@ -1158,7 +1158,7 @@ using b200::qr::QrLayout;
 using b200::qr::QrHeader;
 
 struct QrKnobs {
-  int on, minq, cols, phases, panel, predict;
+  int on, minq, cols, phases, panel, predict, fastp, fused;
   double theta;
 };
 QrKnobs& qr_knobs() {
@@ -1175,6 +1175,9 @@ QrKnobs& qr_knobs() {
     v.panel = (e = getenv("B200_SVD_QR_PANEL")) ? atoi(e) : 0;      // 0: by operand height
     v.theta = (e = getenv("B200_SVD_QR_THETA")) ? atof(e) : 0.5;
     v.predict = (e = getenv("B200_SVD_PREDICT")) ? atoi(e) : 1;
+    // panel factorisation with one warp per column up to this many rows (0: never)
+    v.fastp = (e = getenv("B200_SVD_QR_FASTP")) ? atoi(e) : 768;
+    v.fused = (e = getenv("B200_SVD_QR_FUSED")) ? atoi(e) : 1;
     return v;
   }();
   return k;
@@ -1436,6 +1439,7 @@ extern "C" int b200_svd_factor2(void* stream_, const void* theta, int m, int n, 
     if (knobs().drop >= 0.0) A.stop_rel = knobs().drop * 1e-2 * eps;
     A.nc_res = Q.nc_res; A.ncmax = Q.NCmax;
     A.panel = Q.panel;
+    A.fast_panel = (Q.p <= qr_knobs().fastp) ? 1 : 0;
     A.theta2 = qr_knobs().theta * qr_knobs().theta;
     void* args[] = {&A};
     b200::profile_begin(stream, 1);
@@ -1653,6 +1657,7 @@ extern "C" int b200_svd_config(const char* key, double value) {
   else if (k == "qr_panel") qr_knobs().panel = (int)value;
   else if (k == "qr_theta") qr_knobs().theta = value;
   else if (k == "predict") qr_knobs().predict = (value != 0.0);
+  else if (k == "qr_fastp") qr_knobs().fastp = (int)value;
   else { b200::set_error("b200_svd_config: unknown key %s", key); return B200_EINVAL; }
   return B200_OK;
 }

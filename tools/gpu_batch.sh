@@ -18,6 +18,9 @@ for job in "$@"; do
     stepprof)  timeout 600 python tools/step_profile.py 50 300 > gpurun_out/${TAG}_stepprof.jsonl 2> gpurun_out/${TAG}_stepprof.err ;;
     stepprof_noqr) B200_SVD_QR=0 timeout 600 python tools/step_profile.py 50 300 > gpurun_out/${TAG}_stepprof_noqr.jsonl 2> gpurun_out/${TAG}_stepprof_noqr.err ;;
     phases)    B200_SVD_PHASES=1 timeout 900 python tools/qr_check.py oracle25 > gpurun_out/${TAG}_phases.log 2>&1 ;;
+    ph00)      B200_SVD_QR_FASTP=0 B200_SVD_QR_FUSED=0 B200_SVD_PHASES=1 timeout 900 python tools/qr_check.py oracle25 > gpurun_out/${TAG}_ph00.log 2>&1 ;;
+    ph10)      B200_SVD_QR_FASTP=768 B200_SVD_QR_FUSED=0 B200_SVD_PHASES=1 timeout 900 python tools/qr_check.py oracle25 > gpurun_out/${TAG}_ph10.log 2>&1 ;;
+    ph01)      B200_SVD_QR_FASTP=0 B200_SVD_QR_FUSED=1 B200_SVD_PHASES=1 timeout 900 python tools/qr_check.py oracle25 > gpurun_out/${TAG}_ph01.log 2>&1 ;;
     bench_ref) timeout 1500 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_ref.json 2> gpurun_out/${TAG}_bench_ref.err ;;
     bench_old) timeout 900 python bench.py --steps 20 --warmup 5 --preroll 0 > gpurun_out/${TAG}_bench_old.json 2> gpurun_out/${TAG}_bench_old.err ;;
     teacher)   timeout 1500 python tools/teacher_forced.py 7 26 > gpurun_out/${TAG}_teacher_7_26.json 2> gpurun_out/${TAG}_teacher.err ;;
