@@ -239,6 +239,9 @@ def build_member(ops, infl, args, torch, sync, snapshot=False):
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     sync()
+    cuprof = os.environ.get("B200_BENCH_CUPROF") == "1"     # ncu --profile-from-start off
+    if cuprof:
+        torch.cuda.cudart().cudaProfilerStart()
     t0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
@@ -247,6 +250,8 @@ def build_member(ops, infl, args, torch, sync, snapshot=False):
     e1.record()
     sync()
     wall = time.perf_counter() - t0
+    if cuprof:
+        torch.cuda.cudart().cudaProfilerStop()
     out = {"dev_ms": e0.elapsed_time(e1), "wall_ms": wall * 1e3, "sites": sites,
            "bond_hist": bond_hist,
            "launches": ops.launch_count() - l0, "h2d": ops.h2d_bytes - h0,

@@ -93,7 +93,7 @@ __host__ __device__ inline size_t align256(size_t x) { return (x + 255) & ~(size
 // Diagnostic knobs (environment, read ONCE: a getenv per SVD is host time on the critical
 // path of a dependent chain).  Defaults are the measured choices described in DESIGN.md.
 struct Knobs {
-  int max_slices, old_slices, npass, npass_minq, npass_all;
+  int max_slices, old_slices, npass, npass_minq, npass_all, xrows, wrows;
   double drop, kappa, negrel;      // < 0: not set
 };
 const Knobs& knobs() {
@@ -103,6 +103,10 @@ const Knobs& knobs() {
     v.max_slices = (e = getenv("B200_SVD_MAX_SLICES")) ? atoi(e) : 0;
     v.old_slices = getenv("B200_SVD_OLD_SLICES") ? 1 : 0;
     v.npass = (e = getenv("B200_SVD_NPASS")) ? atoi(e) : 1;
+    v.xrows = (e = getenv("B200_SVD_XROWS")) ? atoi(e) : X_SLICE_ROWS;
+    v.wrows = (e = getenv("B200_SVD_WROWS")) ? atoi(e) : W_SLICE_ROWS;
+    if (v.xrows < 4) v.xrows = 4;
+    if (v.wrows < 4) v.wrows = 4;
     v.npass_minq = (e = getenv("B200_SVD_NPASS_MINQ")) ? atoi(e) : (1 << 30);
     v.npass_all = getenv("B200_SVD_NPASS_ALL") ? 1 : 0;
     v.drop = (e = getenv("B200_SVD_DROP")) ? atof(e) : -1.0;
@@ -157,8 +161,8 @@ __host__ Layout make_layout(int m, int n) {
   if (max_r < 1) max_r = 1;
   // Row slices: X rows cost a Gram pass AND an apply pass, W rows only an apply pass,
   // so X slices are made smaller.  Slices never mix X and W rows (except R == 1).
-  const int want_x = (L.p + X_SLICE_ROWS - 1) / X_SLICE_ROWS;
-  const int want_w = (L.q + W_SLICE_ROWS - 1) / W_SLICE_ROWS;
+  const int want_x = (L.p + knobs().xrows - 1) / knobs().xrows;
+  const int want_w = (L.q + knobs().wrows - 1) / knobs().wrows;
   if (max_r == 1) {
     L.Rx = 1; L.Rw = 0;
   } else if (want_x + want_w <= max_r) {

@@ -17,12 +17,14 @@ def shard_indices(n_members, rank, world_size):
     return list(range(rank, n_members, world_size))
 
 
-def _run_concurrent(mine, run_member, concurrent, make_ops):
+def _run_concurrent(mine, run_member, concurrent, make_ops, background=False):
     """This rank's members on ``concurrent`` host threads, each with its own ops object and
     (on a GPU) its own CUDA stream: the C-ABI calls release the GIL, a TEMPO step is one C
     call, and the small cooperative SVD launches of different members overlap on the SMs
     (measured: 74 -> 832 aggregate TEMPO steps/s on one B200 with 16 members in flight,
-    profiles/r01_ensemble_one_gpu_v10.jsonl).  Results are bit-identical to serial runs."""
+    profiles/r01_ensemble_one_gpu_v10.jsonl).  Results are bit-identical to serial runs.
+    ``background=True`` returns at once with a ``join()`` callable that waits for the threads
+    and hands back the results."""
     import queue  # pylint: disable=import-outside-toplevel
     import threading  # pylint: disable=import-outside-toplevel
     todo = queue.Queue()
@@ -53,11 +55,14 @@ def _run_concurrent(mine, run_member, concurrent, make_ops):
     threads = [threading.Thread(target=worker) for _ in range(min(concurrent, len(mine)))]
     for th in threads:
         th.start()
-    for th in threads:
-        th.join()
-    if errors:
-        raise errors[0]
-    return results
+
+    def join():
+        for th in threads:
+            th.join()
+        if errors:
+            raise errors[0]
+        return results
+    return join if background else join()
 
 
 def run_ensemble(n_members, run_member, device=None, group=None, concurrent=1,
@@ -216,38 +221,65 @@ def tempo_grid(influences, initial_state, unitary, propagators, dkmax, epsrel, n
             be = BatchedTempoBackend(st0, infl[idx], unitary, propagators, np.ones(d2),
                                      np.ones(d2), dkmax, epsrel, chi_cap=chi_cap, ops=ops)
             _, s0 = be.initialize()
-            states = np.concatenate((s0[None], be.compute_steps(num_steps, strict=False)))
-            status = be.info()["status"]
-            states = np.swapaxes(states, 0, 1).reshape(len(idx), num_steps + 1, d, d).copy()
-            over = []
-            for k in np.nonzero(status)[0]:
-                if int(status[k]) != 2:
-                    raise RuntimeError(f"lock-step TEMPO member {idx[k]}: status {int(status[k])}")
-                over.append(int(k))
-            if over:        # the general device path, several members in flight at once
-                rerun.extend(int(idx[k]) for k in over)
+            cuda = getattr(ops, "name", "cuda") == "cuda"
+            dev_index = ops.device.index if (cuda and ops is not None) else 0
 
-                def member(pos, member_ops=None):
-                    k = over[pos]
-                    st = rho0 if rho0.ndim == 2 else rho0[idx[k]]
+            def member(k, member_ops=None):
+                st = rho0 if rho0.ndim == 2 else rho0[idx[k]]
 
-                    def member_props(step, pos_=k):
-                        return tuple(np.asarray(x)[pos_] if np.asarray(x).ndim == 3 else x
-                                     for x in propagators(step))
-                    return tempo_member(infl[idx[k]], member_props, st, dkmax, epsrel,
-                                        num_steps, unitary=unitary,
-                                        ops=member_ops if member_ops is not None else ops)
-                cuda = getattr(ops, "name", "cuda") == "cuda"
-                if cuda and len(over) > 1:
+                def member_props(step, pos_=k):
+                    return tuple(np.asarray(x)[pos_] if np.asarray(x).ndim == 3 else x
+                                 for x in propagators(step))
+                return tempo_member(infl[idx[k]], member_props, st, dkmax, epsrel,
+                                    num_steps, unitary=unitary,
+                                    ops=member_ops if member_ops is not None else ops)
+
+            def overflowed(done):
+                status = be.info()["status"]
+                over = []
+                for k in np.nonzero(status)[0]:
+                    if int(status[k]) != 2:
+                        raise RuntimeError(
+                            f"lock-step TEMPO member {idx[k]}: status {int(status[k])}")
+                    if int(k) not in done:
+                        over.append(int(k))
+                return over
+
+            def start(over):
+                """The general device path for members that outgrew shared memory: several
+                in flight at once, each on its own host thread and stream, WHILE the
+                lock-step engine carries on with the others."""
+                if cuda:
                     from ._lib import CudaOps  # pylint: disable=import-outside-toplevel
-                    dev_index = ops.device.index if ops is not None else 0
-                    redo = _run_concurrent(list(range(len(over))), member,
-                                           min(fallback_concurrency, len(over)),
-                                           lambda: CudaOps(dev_index))
-                else:
-                    redo = [member(pos) for pos in range(len(over))]
-                for pos, k in enumerate(over):
-                    states[k] = redo[pos]
+                    return _run_concurrent(over, member, min(fallback_concurrency, len(over)),
+                                           lambda: CudaOps(dev_index), background=True)
+                res = [member(k) for k in over]
+                return lambda: res
+
+            # bond dimensions saturate within a few memory times: look for members that left
+            # the lock-step path after 3 dkmax steps and start their re-runs right away
+            probe = min(num_steps, 3 * dkmax)
+            parts = [s0[None], be.compute_steps(probe, strict=False)]
+            redo = {}
+            pending = []
+            early = overflowed(redo)
+            if early:
+                for k in early:
+                    redo[k] = None
+                pending.append((early, start(early)))
+            if num_steps > probe:
+                parts.append(be.compute_steps(num_steps - probe, strict=False))
+            states = np.concatenate(parts)
+            states = np.swapaxes(states, 0, 1).reshape(len(idx), num_steps + 1, d, d).copy()
+            late = overflowed(redo)
+            if late:
+                for k in late:
+                    redo[k] = None
+                pending.append((late, start(late)))
+            for over, join in pending:
+                for k, res in zip(over, join()):
+                    states[k] = res
+            rerun.extend(int(idx[k]) for k in redo)
             out.extend(states)
         return out
 

@@ -97,6 +97,52 @@ def _compute_dynamics_factory(original, dynamics_cls):
     return compute_dynamics
 
 
+def _compute_gradient_factory(original, dynamics_cls):
+    """``oqupy.gradient.compute_gradient_and_dynamics`` (gradient.py:169-437) with the forward
+    pass, the back-propagation and the adjoint tensors on the device
+    (``oqupy_b200.gradient_device``: one or several environments, controls).  The reference's
+    own argument checks run first; ``state_gradient`` (gradient.py:32-111) looks the function
+    up in its module, so it takes the device path too and keeps its host ``_chain_rule``."""
+    import numpy as np  # pylint: disable=import-outside-toplevel
+    from .process_tensor import gradient_device  # pylint: disable=import-outside-toplevel
+
+    def compute_gradient_and_dynamics(system, initial_state, target_derivative,
+                                      process_tensors, parameters, start_time=0.0, dt=None,
+                                      num_steps=None, control=None, record_all=True,
+                                      progress_type=None):
+        def reference():
+            return original(system, initial_state, target_derivative, process_tensors,
+                            parameters, start_time=start_time, dt=dt, num_steps=num_steps,
+                            control=control, record_all=record_all,
+                            progress_type=progress_type)
+        if not _FORCE["dynamics"]:
+            return reference()
+        from oqupy.system import ParameterizedSystem  # pylint: disable=import-outside-toplevel
+        from oqupy.system_dynamics import _compute_dynamics_input_parse  # pylint: disable=import-outside-toplevel
+        from oqupy.util import check_isinstance  # pylint: disable=import-outside-toplevel
+        parsed = _compute_dynamics_input_parse(   # raises like the reference on bad input
+            False, system, initial_state, dt, num_steps, start_time, process_tensors, control,
+            record_all)
+        sys_, rho0, step, n, t0, pts, ctrl, rec_all, _ = parsed
+        check_isinstance(sys_, ParameterizedSystem, "system")
+        assert target_derivative is not None, "target state must be given explicitly"
+        devs = [_device_process_tensor(p) for p in pts]
+        if (not devs or any(d is None for d in devs) or n < 1
+                or any(d.transform_in is not None or d.transform_out is not None for d in devs)):
+            return reference()
+        props = sys_.get_propagators(step, parameters)
+        controls = [ctrl.get_controls(k, dt=step, start_time=t0) for k in range(n + 1)]
+        derivs, states = gradient_device(devs if len(devs) > 1 else devs[0], props,
+                                         np.asarray(rho0, dtype=complex), target_derivative,
+                                         num_steps=n, controls=controls)
+        if rec_all:
+            times = [t0 + step * k for k in range(n + 1)]
+            return derivs, dynamics_cls(times=times, states=list(states))
+        return derivs, dynamics_cls(times=[t0 + 1 * step], states=[states[-1]])
+    compute_gradient_and_dynamics.__doc__ = original.__doc__
+    return compute_gradient_and_dynamics
+
+
 def install(default=False, dynamics=True):
     """Rebind OQuPy's backend names.  With ``default=True`` the config dictionaries are
     also mutated in place so that every Tempo / PtTempo uses the B200 backend.
@@ -132,6 +178,15 @@ def install(default=False, dynamics=True):
     shim = _compute_dynamics_factory(_ORIGINALS["compute_dynamics"], oqupy.Dynamics)
     sdm.compute_dynamics = shim
     oqupy.compute_dynamics = shim
+    # oqupy.gradient.compute_gradient_and_dynamics (gradient.py:169-437), also reached by
+    # oqupy.state_gradient through its module
+    import oqupy.gradient as gm  # pylint: disable=import-outside-toplevel
+    if "compute_gradient_and_dynamics" not in _ORIGINALS:
+        _ORIGINALS["compute_gradient_and_dynamics"] = gm.compute_gradient_and_dynamics
+    gshim = _compute_gradient_factory(_ORIGINALS["compute_gradient_and_dynamics"],
+                                      oqupy.Dynamics)
+    gm.compute_gradient_and_dynamics = gshim
+    oqupy.compute_gradient_and_dynamics = gshim
     _FORCE["dynamics"] = bool(dynamics)
     if default:
         for name, cfg in (("TEMPO", oqupy.config.TEMPO_BACKEND_CONFIG),
@@ -155,6 +210,9 @@ def uninstall():
     import oqupy.system_dynamics as sdm  # pylint: disable=import-outside-toplevel
     sdm.compute_dynamics = _ORIGINALS["compute_dynamics"]
     oqupy.compute_dynamics = _ORIGINALS["compute_dynamics"]
+    import oqupy.gradient as gm  # pylint: disable=import-outside-toplevel
+    gm.compute_gradient_and_dynamics = _ORIGINALS["compute_gradient_and_dynamics"]
+    oqupy.compute_gradient_and_dynamics = _ORIGINALS["compute_gradient_and_dynamics"]
     tm.TempoBackend = _ORIGINALS["TempoBackend"]
     tb.BaseTempoBackend = _ORIGINALS["BaseTempoBackend"]
     tm.MeanFieldTempoBackend = _ORIGINALS["MeanFieldTempoBackend"]

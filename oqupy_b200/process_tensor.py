@@ -411,8 +411,167 @@ def _dynamics_multi_env(pts, propagators, initial_state, num_steps, ops):
     return ops.to_host(rho).reshape(num_steps + 1, d, d)
 
 
+def _gradient_multi_env(pts, propagators, initial_state, target_derivative, num_steps, ops,
+                        controls):
+    """gradient_device for m >= 2 environments (gradient.py:266-425 with one bond leg per
+    environment; adjoint tensor of system_dynamics.py:702-786 for MPOs that are diagonal in
+    the system leg):
+
+        D3[x][i, j] = sum F[l_1..l_m, i] prod_e T_e[l_e, r_e, x] B[r_1..r_m, j].
+
+    Every contraction is a strided, doubly batched GEMM (batches: the system index x and the
+    bond legs in front of the contracted one)."""
+    from ._lib import View  # pylint: disable=import-outside-toplevel
+    m = len(pts)
+    if num_steps is None:
+        num_steps = min(len(p) for p in pts)
+    for p_ in pts:
+        if p_.transform_in is not None or p_.transform_out is not None:
+            raise NotImplementedError(
+                "oqupy_b200: gradients through transformed process tensors are not supported")
+    propagators, rho0, controls = _fold_controls(propagators, controls, initial_state)
+    d = rho0.shape[0]
+    d2 = d * d
+    mats = {}
+
+    def dev(mat):
+        key = id(mat)
+        if key not in mats:
+            mats[key] = (ops.from_host(np.ascontiguousarray(np.asarray(mat, dtype=CDTYPE))), mat)
+        return mats[key][0]
+
+    def sys_leg(x, mat):                   # x[..., j] <- sum_i mat[j, i] x[..., i]
+        rows_ = int(x.numel()) // d2
+        out = ops.empty(rows_, d2)
+        ops.gemm(rows_, d2, d2, View(x, row=d2, col=1), View(dev(mat), row=1, col=d2),
+                 View(out, row=d2, col=1))
+        return out
+
+    def through(v, dims, step, swapped):
+        """v[a, l, b, x] -> sum_l T_e[l, r, x] v[a, l, b, x] for every environment e (or the
+        bond-swapped site, system_dynamics.py:588-628)."""
+        dims = list(dims)
+        for e in range(m):
+            t = pts[e].get_mpo_tensor_device(step)
+            chi_l, chi_r, _ = (int(x) for x in t.shape)
+            if swapped:
+                k_, n_ = chi_r, chi_l
+                ta = View(t, row=chi_r * d2, col=d2, b1=1)        # A[l][r] = T[l, r, x]
+            else:
+                k_, n_ = chi_l, chi_r
+                ta = View(t, row=d2, col=chi_r * d2, b1=1)        # A[r][l] = T[l, r, x]
+            assert dims[e] == k_
+            na = int(np.prod(dims[:e]))
+            nb = int(np.prod(dims[e + 1:]))
+            nxt = ops.empty(na * n_ * nb, d2)
+            ops.gemm(n_, nb, k_, ta,
+                     View(v, row=nb * d2, col=d2, b1=1, b2=k_ * nb * d2),
+                     View(nxt, row=nb * d2, col=d2, b1=1, b2=n_ * nb * d2), nb1=d2, nb2=na)
+            v = nxt
+            dims[e] = n_
+        return v, dims
+
+    def readout(v, dims, step, dst):
+        cur = v
+        rest = int(np.prod(dims)) * d2
+        for e in range(m):
+            rest //= dims[e]
+            cap = pts[e].get_cap_tensor_device(step)
+            out = dst if e == m - 1 else ops.empty(rest)
+            ops.gemm(1, rest, dims[e], View(cap, col=1), View(cur, row=rest, col=1),
+                     View(out, col=1))
+            cur = out
+
+    # ---- forward, every state kept
+    dims = [1] * m
+    v = ops.from_host(rho0.reshape(1, d2))
+    rho = ops.empty(num_steps + 1, d2)
+    forward, fdims = [], []
+    for step in range(num_steps):
+        readout(v, dims, step, rho[step])
+        forward.append(v)
+        fdims.append(list(dims))
+        p1, p2 = propagators(step)
+        v = sys_leg(v, p1)
+        v, dims = through(v, dims, step, False)
+        v = sys_leg(v, p2)
+    readout(v, dims, num_steps, rho[num_steps])
+    states = ops.to_host(rho).reshape(num_steps + 1, d, d)
+    target = target_derivative(states[-1]) if callable(target_derivative) \
+        else target_derivative
+    back = ops.from_host(np.asarray(target, dtype=CDTYPE).reshape(1, d2))
+    out = ops.empty(num_steps, d2, d2, d2)                    # D3[step][x][i][j]
+
+    def adjoint(step, b, bdims):
+        f = forward[step]
+        if controls is not None:
+            if controls[step][1] is not None:
+                f = sys_leg(f, controls[step][1])
+            if controls[step + 1][0] is not None:
+                b = sys_leg(b, np.asarray(controls[step + 1][0]).T)
+        cur, cdims, has_x = f, list(fdims[step]), False
+        for e in range(m):
+            t = pts[e].get_mpo_tensor_device(step)
+            chi_l, chi_r, _ = (int(x) for x in t.shape)
+            na = int(np.prod(cdims[:e]))
+            nc = int(np.prod(cdims[e + 1:])) * d2             # later bond legs and i
+            nxt = ops.empty(na * chi_r * nc, d2)              # G[a, r, c, x]
+            xs = d2 if has_x else 1                           # element stride of c in `cur`
+            ops.gemm(chi_r, nc, chi_l, View(t, row=d2, col=chi_r * d2, b1=1),
+                     View(cur, row=nc * xs, col=xs, b1=1 if has_x else 0,
+                          b2=chi_l * nc * xs),
+                     View(nxt, row=nc * d2, col=d2, b1=1, b2=chi_r * nc * d2),
+                     nb1=d2, nb2=na)
+            cur, has_x = nxt, True
+            cdims[e] = chi_r
+        assert cdims == list(bdims)
+        r_ = int(np.prod(cdims))
+        ops.gemm(d2, d2, r_, View(cur, row=d2, col=d2 * d2, b1=1),
+                 View(b, row=d2, col=1),
+                 View(out[step], row=d2, col=1, b1=d2 * d2), nb1=d2)
+
+    bdims = list(dims)
+    adjoint(num_steps - 1, back, bdims)
+    for step in range(num_steps - 1, 0, -1):
+        p1, p2 = propagators(step)
+        back = sys_leg(back, np.asarray(p2, dtype=CDTYPE).T)
+        back, bdims = through(back, bdims, step, True)
+        back = sys_leg(back, np.asarray(p1, dtype=CDTYPE).T)
+        adjoint(step - 1, back, bdims)
+    d3 = ops.to_host(out)
+    derivs = []
+    for step in range(num_steps):
+        full = np.zeros((d2, d2, d2, d2), dtype=CDTYPE)
+        for x in range(d2):
+            full[:, x, x, :] = d3[step, x]
+        derivs.append(full)
+    return derivs, states
+
+
+def _fold_controls(propagators, controls, initial_state):
+    """Controls (gradient.py:252-256, 287-301) folded into the half-step propagators:
+    P1'_k = P1_k C^post_k,  P2'_k = C^pre_{k+1} P2_k,  rho_0' = C^pre_0 rho_0.  The state
+    recorded at step k (after the pre-, before the post-measurement control) is then what
+    the folded loop reads out."""
+    rho0 = np.asarray(initial_state, dtype=CDTYPE)
+    if controls is None or all(c[0] is None and c[1] is None for c in controls):
+        return propagators, rho0, None
+    d = rho0.shape[0]
+    if controls[0][0] is not None:
+        rho0 = (np.asarray(controls[0][0], dtype=CDTYPE) @ rho0.reshape(d * d)).reshape(d, d)
+
+    def folded(step):
+        p1, p2 = propagators(step)
+        if controls[step][1] is not None:
+            p1 = np.asarray(p1, dtype=CDTYPE) @ np.asarray(controls[step][1], dtype=CDTYPE)
+        if controls[step + 1][0] is not None:
+            p2 = np.asarray(controls[step + 1][0], dtype=CDTYPE) @ np.asarray(p2, dtype=CDTYPE)
+        return p1, p2
+    return folded, rho0, controls
+
+
 def gradient_device(pt, propagators, initial_state, target_derivative, num_steps=None,
-                    ops=None):
+                    ops=None, controls=None):
     """compute_gradient_and_dynamics hot loops (oqupy/gradient.py:275-425): forward
     propagation through the process tensor keeping every intermediate state on the
     device, back-propagation of the target derivative through the bond-/leg-swapped
@@ -420,19 +579,36 @@ def gradient_device(pt, propagators, initial_state, target_derivative, num_steps
     ``D[i, x, x', j] = sum_{l,r} F[l, i] T[l, r, x] d_xx' B[r, j]``
     (system_dynamics.py:702-786; leg order of gradient.py:216-224).
 
-    One environment, no controls, rank-3 PT-MPO sites.  ``propagators(step)`` ->
-    (P1, P2) as (d2, d2) superoperators; ``target_derivative`` is a (d, d) array or a
-    callable of the final state.  Returns (propagator_derivatives, states): a list of
-    ``num_steps`` ndarrays (d2, d2, d2, d2) -- what ``oqupy.gradient._chain_rule`` takes
-    as ``adjoint_tensor`` -- and the (num_steps+1, d, d) dynamics.
+    ``pt``: one process tensor or a list of them (one bond leg per environment,
+    gradient.py:266-270); rank-3 PT-MPO sites.  ``propagators(step)`` -> (P1, P2) as
+    (d2, d2) superoperators; ``target_derivative`` is a (d, d) array or a callable of the
+    final state; ``controls``: optional list of (pre, post) measurement controls per step
+    0..num_steps ((d2, d2) superoperators or None, what ``Control.get_controls`` returns).
+    Returns (propagator_derivatives, states): a list of ``num_steps`` ndarrays
+    (d2, d2, d2, d2) -- what ``oqupy.gradient._chain_rule`` takes as ``adjoint_tensor`` --
+    and the (num_steps+1, d, d) dynamics.
     """
     from ._lib import View  # pylint: disable=import-outside-toplevel
     ops = default_ops() if ops is None else ops
-    rho0 = np.asarray(initial_state, dtype=CDTYPE)
-    d = rho0.shape[0]
-    d2 = d * d
+    if isinstance(pt, (list, tuple)):
+        if len(pt) > 1:
+            return _gradient_multi_env(list(pt), propagators, initial_state, target_derivative,
+                                       num_steps, ops, controls)
+        pt = pt[0]
     if num_steps is None:
         num_steps = len(pt)
+    propagators, rho0, controls = _fold_controls(propagators, controls, initial_state)
+    d = rho0.shape[0]
+    d2 = d * d
+
+    def sys_leg(x, mat):
+        """x[..., j] <- sum_i mat[j, i] x[..., i] on a (1, chi, d2) device tensor."""
+        dm = ops.from_host(np.ascontiguousarray(np.asarray(mat, dtype=CDTYPE)))
+        rows_ = int(x.numel()) // d2
+        out = ops.empty(*x.shape)
+        ops.gemm(rows_, d2, d2, View(x, row=d2, col=1), View(dm, row=1, col=d2),
+                 View(out, row=d2, col=1))
+        return out
     # ---- forward (gradient.py:275-316): the fused dynamics step, states kept
     v = ops.from_host(rho0.reshape(1, 1, d2))
     rho = ops.empty(num_steps + 1, 1, d2)
@@ -477,6 +653,13 @@ def gradient_device(pt, propagators, initial_state, target_derivative, num_steps
         t = pt.get_mpo_tensor_device(step)
         chi_l, chi_r, _ = t.shape
         f = forward[step]                                     # (1, chi_l, d2)
+        if controls is not None:
+            # the folded loop keeps F before the post-measurement control of its step and B
+            # before the pre-measurement control of the next one (gradient.py:299-303, 406-412)
+            if controls[step][1] is not None:
+                f = sys_leg(f, controls[step][1])
+            if controls[step + 1][0] is not None:
+                b = sys_leg(b, np.asarray(controls[step + 1][0]).T)
         frep = ops.empty(d2, chi_l, d2)                       # d2 copies of F
         ops.gemm(1, chi_l * d2, 1, View(ops.one), View(f, col=1),
                  View(frep, col=1, b1=chi_l * d2), nb1=d2)

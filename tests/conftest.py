@@ -125,3 +125,23 @@ def tebd_fixture(g):
         mpos = [g[f"pt_mpo_{k}"] for k in range(int(g["pt_len"]))]
         caps = [g[f"pt_cap_{k}"] for k in range(int(g["pt_len"]) + 1)]
     return gammas, lambdas, layers, pt_sites, mpos, caps
+
+
+def gradient_multi_setup(g, ops):
+    """Process tensors (device objects on `ops`), propagators and controls of
+    tests/golden/gradient_multi.npz (make_golden_gradient_multi.py)."""
+    import oqupy_b200 as ob  # pylint: disable=import-outside-toplevel
+    n = int(g["num_steps"])
+    pts = []
+    for e in range(2):
+        pt = ob.DeviceProcessTensor(int(g["dim"]), dt=float(g["dt"]), ops=ops)
+        for k in range(n):
+            pt.set_mpo_tensor(k, g[f"mpo_{e}_{k}"])
+        pt.compute_caps()
+        pts.append(pt)
+
+    def props(k):
+        return g["props_1"][k], g["props_2"][k]
+    controls = [(g["controls"][k, 0] if g["has_control"][k, 0] else None,
+                 g["controls"][k, 1] if g["has_control"][k, 1] else None) for k in range(n + 1)]
+    return pts, props, controls

@@ -124,3 +124,38 @@ def test_mean_field_lock_step_matches_oracle():
     for mine, ref in zip(be.get_bond_dimensions(), [n.bond_dimensions() for n in orc.networks]):
         diff = [abs(a - b) for a, b in zip(mine, ref)]
         assert len(mine) == len(ref) and max(diff) <= 1 and sum(diff) <= 3
+
+
+def test_tempo_grid_general_path_fallback():
+    """tempo_grid: members whose bond dimension outgrows the lock-step capacity are re-run on
+    the general device backend WHILE the others carry on; the result is what a single run of
+    that member gives, the others are untouched."""
+    from oqupy_b200.ensemble import tempo_grid, tempo_member
+    g = load_golden("tempo_c1_k20_eps7_n60")
+    dkmax, eps, steps = 6, 1e-7, 24
+    base = g["influences"][:dkmax + 1]
+    factors = [0.05, 1.0, 0.02, 2.5, 0.03]
+    infl = np.array([scaled(base, f) for f in factors])
+    props = lambda s: (g["prop_1"], g["prop_2"])  # noqa: E731
+    probe = ob.BatchedTempoBackend(np.array([g["initial_state"].reshape(-1)] * len(factors)),
+                                   infl, g["unitary"], props, np.ones(4), np.ones(4), dkmax, eps)
+    probe.initialize()
+    probe.compute_steps(steps)
+    max_chi = probe.info()["max_chi"]
+    assert max_chi.max() > max_chi.min()
+    cap = int(max_chi.min())           # the weakest coupling just fits, the strongest does not
+    expect = {k for k in range(len(factors)) if max_chi[k] > cap}
+    res, rerun = tempo_grid(infl, g["initial_state"], g["unitary"], props, dkmax, eps, steps,
+                            chi_cap=cap)
+    assert res.shape == (len(factors), steps + 1, 2, 2)
+    assert set(rerun) == expect and 0 < len(expect) < len(factors), (rerun, max_chi)
+    full, none = tempo_grid(infl, g["initial_state"], g["unitary"], props, dkmax, eps, steps)
+    assert not none
+    for k in range(len(factors)):
+        if k in rerun:
+            one = tempo_member(infl[k], props, g["initial_state"], dkmax, eps, steps,
+                               unitary=g["unitary"])
+            np.testing.assert_array_equal(res[k], one)
+            np.testing.assert_allclose(res[k], full[k], atol=TEMPO_STATE_ATOL(eps), rtol=0)
+        else:
+            np.testing.assert_array_equal(res[k], full[k])

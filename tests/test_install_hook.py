@@ -270,3 +270,59 @@ def test_install_compute_dynamics(monkeypatch):
     finally:
         install.uninstall()
     assert oqupy.compute_dynamics is install._ORIGINALS["compute_dynamics"]
+
+
+def test_install_compute_gradient_and_dynamics(monkeypatch):
+    """oqupy.compute_gradient_and_dynamics rebound (gradient.py:169-437): one and two
+    environments, controls, record_all=False, against the reference's own function on the
+    same reference-built process tensors."""
+    oqupy = load_reference()
+    np.vectorize = lambda f, *a, **k: f     # numpy-2: see tests/golden/make_golden_mean_field.py
+    from oqupy_b200 import backends, install, process_tensor
+    from host_model_ops import HostModelOps
+    ops = HostModelOps()
+    monkeypatch.setattr(backends, "default_ops", lambda: ops)
+    monkeypatch.setattr(process_tensor, "default_ops", lambda: ops)
+    sig = oqupy.operators.sigma
+    dt, n = 0.1, 8
+    pts = []
+    for alpha, temp in ((0.2, 0.5), (0.1, 1.3)):
+        corr = oqupy.PowerLawSD(alpha=alpha, zeta=1, cutoff=4.0, cutoff_type="exponential",
+                                temperature=temp)
+        pts.append(oqupy.pt_tempo_compute(
+            bath=oqupy.Bath(0.5 * sig("z"), corr), start_time=0.0, end_time=dt * n,
+            parameters=oqupy.TempoParameters(dt=dt, dkmax=4, epsrel=1e-6),
+            progress_type="silent"))
+    system = oqupy.ParameterizedSystem(hamiltonian=lambda hx: 0.5 * hx * sig("x") + 0.1 * sig("z"))
+    x0 = np.linspace(0.5, 1.5, 2 * n).reshape(-1, 1)
+    rho0 = oqupy.operators.spin_dm("z+")
+    target = oqupy.operators.spin_dm("x-").T
+    control = oqupy.Control(2)
+    control.add_single(2, oqupy.operators.left_super(sig("x")))
+    control.add_single(5, oqupy.operators.right_super(sig("y")), post=True)
+    control.add_single(n, oqupy.operators.left_right_super(sig("x"), sig("x")))
+    cases = [dict(process_tensors=[pts[0]]), dict(process_tensors=pts),
+             dict(process_tensors=[pts[0]], control=control),
+             dict(process_tensors=pts, control=control),
+             dict(process_tensors=[pts[1]], record_all=False)]
+    common = dict(system=system, initial_state=rho0, target_derivative=target, parameters=x0,
+                  dt=dt, progress_type="silent")
+    refs = [oqupy.compute_gradient_and_dynamics(**common, **c) for c in cases]
+    install.install()
+    try:
+        assert oqupy.gradient.compute_gradient_and_dynamics is not \
+            install._ORIGINALS["compute_gradient_and_dynamics"]
+        for case, (gref, dref) in zip(cases, refs):
+            launches = ops.launches
+            gnew, dnew = oqupy.compute_gradient_and_dynamics(**common, **case)
+            assert ops.launches > launches            # ran on the (model) device
+            np.testing.assert_allclose(dnew.times, dref.times, atol=1e-12)
+            np.testing.assert_allclose(dnew.states, dref.states, atol=1e-10)
+            ref_arr = np.array([np.asarray(getattr(t, "tensor", t)) for t in gref])
+            np.testing.assert_allclose(np.array(gnew), ref_arr, atol=1e-10)
+        with pytest.raises(ValueError):
+            oqupy.compute_gradient_and_dynamics(**{**common, "dt": 0.07}, process_tensors=pts)
+    finally:
+        install.uninstall()
+    assert oqupy.gradient.compute_gradient_and_dynamics is \
+        install._ORIGINALS["compute_gradient_and_dynamics"]

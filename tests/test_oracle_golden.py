@@ -174,3 +174,24 @@ def test_tempo_oracle_unique(tag):
     # floor at eps = 1e-7 (see test_tempo_oracle_matches_reference); exact before
     np.testing.assert_allclose(states, g["states"], atol=50 * float(g["epsrel"]), rtol=0)
     np.testing.assert_allclose(states[:3], g["states"][:3], atol=1e-9, rtol=0)
+
+
+def test_gradient_oracle_two_environments_and_controls():
+    """The oracle's general gradient (several environments, controls) against the reference's
+    own compute_gradient_and_dynamics (tests/golden/gradient_multi.npz)."""
+    g = load_golden("gradient_multi")
+    n = int(g["num_steps"])
+    mpos = [[g[f"mpo_{e}_{k}"] for k in range(n)] for e in range(2)]
+    caps = [[g[f"cap_{e}_{k}"] for k in range(n + 1)] for e in range(2)]
+    props = lambda k: (g["props_1"][k], g["props_2"][k])   # noqa: E731
+    derivs, states = onp.compute_gradient_and_dynamics_general(
+        mpos, caps, props, g["initial_state"], g["target_derivative"], n)
+    np.testing.assert_allclose(states, g["states_two_env"], atol=1e-12, rtol=0)
+    np.testing.assert_allclose(np.array(derivs), g["derivs_two_env"], atol=1e-12, rtol=0)
+    controls = [(g["controls"][k, 0] if g["has_control"][k, 0] else None,
+                 g["controls"][k, 1] if g["has_control"][k, 1] else None) for k in range(n + 1)]
+    derivs, states = onp.compute_gradient_and_dynamics_general(
+        mpos[:1], caps[:1], props, g["initial_state"], g["target_derivative"], n,
+        controls=controls)
+    np.testing.assert_allclose(states, g["states_controls"], atol=1e-12, rtol=0)
+    np.testing.assert_allclose(np.array(derivs), g["derivs_controls"], atol=1e-12, rtol=0)

@@ -14,6 +14,9 @@ for job in "$@"; do
     bench)     timeout 1500 python bench.py --steps 20 --warmup 5 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err ;;
     bench_noqr) B200_SVD_QR=0 timeout 1500 python bench.py --steps 20 --warmup 5 --no-cpu > gpurun_out/${TAG}_bench_noqr.json 2> gpurun_out/${TAG}_bench_noqr.err ;;
     bench_nopred) B200_SVD_PREDICT=0 timeout 1500 python bench.py --steps 20 --warmup 5 --no-cpu > gpurun_out/${TAG}_bench_nopred.json 2> gpurun_out/${TAG}_bench_nopred.err ;;
+    bench_x32) B200_SVD_XROWS=32 B200_SVD_WROWS=48 timeout 900 python bench.py --steps 20 --warmup 5 --no-cpu > gpurun_out/${TAG}_bench_x32.json 2> gpurun_out/${TAG}_bench_x32.err ;;
+    bench_x48) B200_SVD_XROWS=48 B200_SVD_WROWS=64 timeout 900 python bench.py --steps 20 --warmup 5 --no-cpu > gpurun_out/${TAG}_bench_x48.json 2> gpurun_out/${TAG}_bench_x48.err ;;
+    bench_x16) B200_SVD_XROWS=16 B200_SVD_WROWS=32 timeout 900 python bench.py --steps 20 --warmup 5 --no-cpu > gpurun_out/${TAG}_bench_x16.json 2> gpurun_out/${TAG}_bench_x16.err ;;
     svdstep)   timeout 900 python tools/svd_profile_step.py 40 > gpurun_out/${TAG}_svdstep.log 2>&1 ;;
     stepprof)  timeout 600 python tools/step_profile.py 50 300 > gpurun_out/${TAG}_stepprof.jsonl 2> gpurun_out/${TAG}_stepprof.err ;;
     stepprof_noqr) B200_SVD_QR=0 timeout 600 python tools/step_profile.py 50 300 > gpurun_out/${TAG}_stepprof_noqr.jsonl 2> gpurun_out/${TAG}_stepprof_noqr.err ;;
@@ -29,10 +32,15 @@ for job in "$@"; do
     batchbench) timeout 900 python tools/batch_bench.py 592 60 25 > gpurun_out/${TAG}_batchbench.json 2> gpurun_out/${TAG}_batchbench.err ;;
     ncu_svd)   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"qrcp_kernel|jacobi_kernel|apply_q_kernel" -c 6 -f -o gpurun_out/${TAG}_svd python tools/ncu_targets.py svd > gpurun_out/${TAG}_ncu_svd.log 2>&1 ;;
     ncu_batch) timeout 1200 ncu --set full --clock-control none --import-source on -k regex:tempo_batch_step_kernel -s 22 -c 1 -f -o gpurun_out/${TAG}_batch python tools/ncu_targets.py batch > gpurun_out/${TAG}_ncu_batch.log 2>&1 ;;
+    ncu_win)   B200_BENCH_CUPROF=1 timeout 2400 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 4000 --csv --log-file gpurun_out/${TAG}_launches_win.csv python bench.py --steps 2 --warmup 5 --preroll 25 --no-cpu > gpurun_out/${TAG}_ncu_win.log 2>&1 ;;
     ncu_list)  timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -s 43000 -c 3300 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/${TAG}_ncu_list.log 2>&1 ;;
     c5)        timeout 1500 python tools/c5_bench.py 64 200 > gpurun_out/${TAG}_c5_n1.json 2> gpurun_out/${TAG}_c5_n1.err ;;
     c5small)   timeout 900 python tools/c5_bench.py 24 100 > gpurun_out/${TAG}_c5small.json 2> gpurun_out/${TAG}_c5small.err ;;
     c5_n2)     timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/c5_bench.py 64 200 > gpurun_out/${TAG}_c5_n2.json 2> gpurun_out/${TAG}_c5_n2.err ;;
+    bench_n8)  timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_n8.json 2> gpurun_out/${TAG}_bench_n8.err ;;
+    bench_n4)  timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus 4 --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_n4.json 2> gpurun_out/${TAG}_bench_n4.err ;;
+    c5_n4)     timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29515 tools/c5_bench.py 64 200 > gpurun_out/${TAG}_c5_n4.json 2> gpurun_out/${TAG}_c5_n4.err ;;
+    c5_n8)     timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29519 tools/c5_bench.py 64 200 > gpurun_out/${TAG}_c5_n8.json 2> gpurun_out/${TAG}_c5_n8.err ;;
     bench_n2)  timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_n2.json 2> gpurun_out/${TAG}_bench_n2.err ;;
     *) echo "unknown job $job" ;;
   esac

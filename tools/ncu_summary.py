@@ -31,6 +31,8 @@ def main():
         print(f"## {path}")
         for r in rows[2:]:
             print("---")
+            if "Kernel Name" in head:
+                print(f"kernel = {r[head.index('Kernel Name')][:90]}")
             for i, name in enumerate(head):
                 if name in KEYS:
                     print(f"{name} [{unit[i]}] = {r[i]}")
