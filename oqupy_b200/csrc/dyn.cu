@@ -260,25 +260,59 @@ dyn_fused_kernel(int nvec, int chi_l, int chi_r, int d2, int lchunk, int cols_pe
   }
 }
 
-// cap_out[l] = sum_{r,x} T[l,r,x] cap_next[r] tr2[x] ; one warp per l
-__global__ void caps_kernel(int chi_l, int chi_r, int d2, const cplx* __restrict__ t,
-                            const cplx* __restrict__ cap_next,
-                            const cplx* __restrict__ tr2, cplx* __restrict__ cap_out) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= chi_l) return;
+// cap_out[l] = sum_{r,x} T[l,r,x] cap_next[r] tr2[x].  HBM-bound (T is read once): a CTA of
+// 8 warps takes CAP_ROWS rows x CAP_SEG column segments, every lane keeps 8 independent
+// 16-byte streaming loads in flight (the weights cap_next[r] tr2[x] are L1/L2 hits), the
+// segments of a row meet in shared memory in a fixed order.
+constexpr int CAP_ROWS = 2, CAP_SEG = 4, CAP_T = 32 * CAP_ROWS * CAP_SEG;
+__global__ void __launch_bounds__(CAP_T)
+caps_kernel(int chi_l, int chi_r, int d2, const cplx* __restrict__ t,
+            const cplx* __restrict__ cap_next, const cplx* __restrict__ tr2,
+            cplx* __restrict__ cap_out) {
+  __shared__ cplx s_part[CAP_ROWS][CAP_SEG];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rloc = warp / CAP_SEG, seg = warp % CAP_SEG;
+  const int l = blockIdx.x * CAP_ROWS + rloc;
   const int ncol = chi_r * d2;
-  const cplx* row = t + (size_t)warp * ncol;
-  cplx acc = make_double2(0.0, 0.0);
-  for (int c = lane; c < ncol; c += 32) {
-    const cplx w = b200::cmul(cap_next[c / d2], tr2[c % d2]);
-    acc = b200::cfma(row[c], w, acc);
+  cplx acc0 = make_double2(0.0, 0.0), acc1 = make_double2(0.0, 0.0);
+  if (l < chi_l) {
+    const cplx* row = t + (size_t)l * ncol;
+    // columns of this segment, in chunks of 8 x 32
+    const int per = (((ncol + CAP_SEG - 1) / CAP_SEG) + 255) & ~255;
+    const int cbeg = seg * per, cend = min(ncol, cbeg + per);
+    for (int c0 = cbeg; c0 < cend; c0 += 256) {
+      cplx tv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int c = c0 + u * 32 + lane;
+        tv[u] = (c < cend) ? __ldcs(reinterpret_cast<const double2*>(row + c))
+                           : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int c = c0 + u * 32 + lane;
+        if (c < cend) {
+          const cplx w = b200::cmul(cap_next[c / d2], tr2[c % d2]);
+          if (u & 1) acc1 = b200::cfma(tv[u], w, acc1); else acc0 = b200::cfma(tv[u], w, acc0);
+        }
+      }
+    }
   }
+  cplx acc = make_double2(acc0.x + acc1.x, acc0.y + acc1.y);
   for (int o = 16; o > 0; o >>= 1) {
     acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
     acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
   }
-  if (lane == 0) cap_out[warp] = acc;
+  if (lane == 0) s_part[rloc][seg] = acc;
+  __syncthreads();
+  if (threadIdx.x < CAP_ROWS) {
+    const int lo = blockIdx.x * CAP_ROWS + threadIdx.x;
+    if (lo < chi_l) {
+      cplx tot = s_part[threadIdx.x][0];
+      for (int q = 1; q < CAP_SEG; ++q) { tot.x += s_part[threadIdx.x][q].x; tot.y += s_part[threadIdx.x][q].y; }
+      cap_out[lo] = tot;
+    }
+  }
 }
 
 constexpr size_t kTicketBytes = 64 * 1024;   // >= nx * ne tickets (checked)
@@ -385,8 +419,8 @@ extern "C" int b200_caps_step(void* stream_, int chi_l, int chi_r, int d2,
     b200::set_error("b200_caps_step: invalid argument");
     return B200_EINVAL;
   }
-  const int blocks = (chi_l * 32 + 255) / 256;
-  caps_kernel<<<blocks, 256, 0, (cudaStream_t)stream_>>>(
+  const int blocks = (chi_l + CAP_ROWS - 1) / CAP_ROWS;
+  caps_kernel<<<blocks, CAP_T, 0, (cudaStream_t)stream_>>>(
       chi_l, chi_r, d2, (const cplx*)t, (const cplx*)cap_next, (const cplx*)tr2,
       (cplx*)cap_out);
   B200_LAUNCH_CHECK();

@@ -977,7 +977,10 @@ jacobi_kernel(const QrSrc qsrc, const cplx* __restrict__ theta, long long rs, lo
     PHASE(8)
     total_rot += rot;
     sweeps_done = sweep + 1;
-    if (rot == 0) { status = 0; break; }
+    // converged; status 2 when only the inflated floor (sweeps beyond FLOOR_GROW_AFTER) let
+    // the iteration end: such a factorisation is NOT within the accuracy contract and the
+    // host raises (b200_svd_factor*: B200_ENOCONV)
+    if (rot == 0) { status = (sweep > FLOOR_GROW_AFTER) ? 2 : 0; break; }
     // PREDICTED convergence (truncating mode only): every violation of this sweep was small
     // (|cos| <= 1e-7 or within 4x of the absolute floor) and has just been rotated away; what
     // the rotations leave behind is second order, n * 1e-14 in |cos| -- below the 1e-11 target.
@@ -1162,7 +1165,7 @@ using b200::qr::QrLayout;
 using b200::qr::QrHeader;
 
 struct QrKnobs {
-  int on, minq, cols, phases, panel, predict, fastp, fused;
+  int on, minq, cols, phases, panel, predict, fastp, fused, costol, tall, minq_rel;
   double theta;
 };
 QrKnobs& qr_knobs() {
@@ -1182,6 +1185,14 @@ QrKnobs& qr_knobs() {
     // panel factorisation with one warp per column up to this many rows (0: never)
     v.fastp = (e = getenv("B200_SVD_QR_FASTP")) ? atoi(e) : 768;
     v.fused = (e = getenv("B200_SVD_QR_FUSED")) ? atoi(e) : 1;
+    // the QR path in the relative-accuracy mode (cos_tol > 0: PT-TEBD splits), and the
+    // largest aspect ratio p/q it takes there (tall splits: the Jacobi passes then run over q
+    // rows instead of p)
+    // Measured on the config-4 PT-TEBD shape (profiles/r02_tebd_qr.jsonl): 0.83 -> 2.2
+    // steps/s, 5e-10 from the LAPACK oracle (= the plain path's and the oracle's own floor).
+    v.costol = (e = getenv("B200_SVD_QR_COSTOL")) ? atoi(e) : 1;
+    v.tall = (e = getenv("B200_SVD_QR_TALL")) ? atoi(e) : 16;
+    v.minq_rel = (e = getenv("B200_SVD_QR_MINQ_REL")) ? atoi(e) : 64;
     return v;
   }();
   return k;
@@ -1234,10 +1245,13 @@ QrLayout make_qr_layout(int m, int n) {
 }
 
 bool qr_eligible(int m, int n, double eps, double cos_tol) {
-  if (!qr_knobs().on || !(eps > 0.0) || cos_tol > 0.0) return false;
+  if (!qr_knobs().on || !(eps > 0.0)) return false;
+  if (cos_tol > 0.0 && !qr_knobs().costol) return false;
   const int p = (m < n) ? n : m, q = (m < n) ? m : n;
-  if (q < qr_knobs().minq || p > 4096) return false;
-  if ((long long)p > 2LL * q) return false;    // tall sweep operands are full rank at the stop level
+  if (q < ((cos_tol > 0.0) ? qr_knobs().minq_rel : qr_knobs().minq) || p > 4096) return false;
+  // tall sweep operands of TEMPO / PT-TEMPO are full rank at the stop level
+  const long long ratio = (cos_tol > 0.0) ? qr_knobs().tall : 2;
+  if ((long long)p > ratio * q) return false;
   const size_t fixed = 2 * (size_t)p * sizeof(cplx) + 4096 + (size_t)q;
   return fixed < (size_t)b200::qr::QR_SMEM_BYTES;
 }
@@ -1391,7 +1405,7 @@ int apply_q(cudaStream_t stream, const b200::qr::ApplyQArgs& A) {
 extern "C" size_t b200_svd_workspace_bytes(int m, int n) {
   if (m <= 0 || n <= 0) return 0;
   size_t need = make_layout(m, n).total;
-  if (qr_eligible(m, n, 1.0, 0.0)) {
+  if (qr_eligible(m, n, 1.0, 0.0) || qr_eligible(m, n, 1.0, 1.0)) {
     const size_t nq = make_qr_layout(m, n).total;
     if (nq > need) need = nq;
   }
@@ -1439,7 +1453,11 @@ extern "C" int b200_svd_factor2(void* stream_, const void* theta, int m, int n, 
     A.tauc = (cplx*)(base + Q.tau);
     A.hdr = (QrHeader*)(base + Q.header);
     A.info_host = info_host;
-    A.stop_rel = 1e-5 * eps;
+    // the discarded block perturbs theta by ~stop*sqrt(q)*||X||_F: negligible next to the
+    // eps-truncation in the absolute mode; the relative-accuracy mode (PT-TEBD: factors are
+    // multiplied by inverse singular values) stops 100x lower (measured on the config-4
+    // shape: 4.3e-9 from the LAPACK oracle at 1e-5*eps)
+    A.stop_rel = ((cos_tol > 0.0) ? 1e-7 : 1e-5) * eps;
     if (knobs().drop >= 0.0) A.stop_rel = knobs().drop * 1e-2 * eps;
     A.nc_res = Q.nc_res; A.ncmax = Q.NCmax;
     A.panel = Q.panel;
@@ -1662,6 +1680,9 @@ extern "C" int b200_svd_config(const char* key, double value) {
   else if (k == "qr_theta") qr_knobs().theta = value;
   else if (k == "predict") qr_knobs().predict = (value != 0.0);
   else if (k == "qr_fastp") qr_knobs().fastp = (int)value;
+  else if (k == "qr_costol") qr_knobs().costol = (value != 0.0);
+  else if (k == "qr_tall") qr_knobs().tall = (value < 1.0) ? 1 : (int)value;
+  else if (k == "qr_minq_rel") qr_knobs().minq_rel = (int)value;
   else { b200::set_error("b200_svd_config: unknown key %s", key); return B200_EINVAL; }
   return B200_OK;
 }

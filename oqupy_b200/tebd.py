@@ -40,8 +40,13 @@ def _isqrt(x):
 
 class PtTebdBackend:
     """PT-TEBD backend on the device: same constructor and methods as the reference
-    (pt_tebd_backend.py:46-445).  ``config['parallel']`` is accepted and ignored: the gates
-    of a layer are independent launches on one stream."""
+    (pt_tebd_backend.py:46-445).  The gates of a layer are independent
+    (pt_tebd_backend.py:134-155 maps them over a process / thread pool): with
+    ``config['parallel']`` set ('multithread' / 'multiprocess' as in the reference, or a number
+    of workers) -- or ``B200_TEBD_STREAMS`` > 1 -- they run on that many host threads, each with
+    its own ops object and CUDA stream, so that their dependent chains of small launches (three
+    truncated SVDs and six contractions per gate) overlap on the SMs; the results are
+    bit-identical to the serial order."""
 
     def __init__(self, gammas, lambdas, epsrel, config=None, ops=None):
         assert len(gammas) == len(lambdas) + 1                         # :71
@@ -63,20 +68,31 @@ class PtTebdBackend:
         self._lams = [ops.from_host(lam) for lam in host]
         self._inv_lams = [ops.from_host(1.0 / lam) for lam in host]
         self._gate_cache = {}
+        par = self._config.get("parallel") if isinstance(self._config, dict) else None
+        env = int(os.environ.get("B200_TEBD_STREAMS", "0"))
+        if isinstance(par, (int, np.integer)) and not isinstance(par, bool):
+            self._nworkers = int(par)
+        elif par in ("multithread", "multiprocess"):
+            self._nworkers = max(env, 4)
+        elif par is None or par is False:
+            self._nworkers = env
+        else:
+            raise NotImplementedError(f"Parallelisation method '{par}' is not implemented!")
+        self._pool = None
         self.clear_traces()
 
     # -------------------------------------------------------------- small helpers
-    def _scale_rows(self, x, lam, nrows, ncols):
+    def _scale_rows(self, x, lam, nrows, ncols, ops=None):
         """out[r, c] = lam[r] x[r, c]  (x contiguous, nrows x ncols)."""
-        ops = self._ops
+        ops = self._ops if ops is None else ops
         out = ops.empty(*x.shape)
         ops.gemm(1, ncols, 1, View(ops.one), View(x, col=1, b1=ncols),
                  View(out, col=1, b1=ncols), nb1=nrows, scale=View(lam, b1=1))
         return out
 
-    def _scale_cols(self, x, lam, nrows, ncols):
+    def _scale_cols(self, x, lam, nrows, ncols, ops=None):
         """out[r, c] = x[r, c] lam[c]."""
-        ops = self._ops
+        ops = self._ops if ops is None else ops
         out = ops.empty(*x.shape)
         ops.gemm(nrows, 1, 1, View(x, row=ncols, b1=1), View(ops.one),
                  View(out, row=ncols, b1=1), nb1=ncols, scale=View(lam, b1=1))
@@ -101,8 +117,56 @@ class PtTebdBackend:
 
     # -------------------------------------------------------------- gates
     def apply_nn_gate_layer(self, gate_layer):                         # :134-155
-        for gate in gate_layer.gates:
-            self.apply_nn_gate(gate)
+        gates = list(gate_layer.gates)
+        nw = min(self._nworkers, len(gates))
+        if nw <= 1 or getattr(self._ops, "name", "") != "cuda":
+            for gate in gates:
+                self.apply_nn_gate(gate)
+            return
+        self._apply_nn_gates_concurrently(gates, nw)
+
+    def _apply_nn_gates_concurrently(self, gates, nw):
+        """The gates of a layer touch disjoint site pairs (and only READ the outer lambdas):
+        worker w takes gates w, w + nw, ... on its own stream; all streams start after the
+        work already queued on the caller's stream and the caller's stream waits for all of
+        them; tensors that cross streams are registered with the caching allocator."""
+        import threading  # pylint: disable=import-outside-toplevel
+        import torch  # pylint: disable=import-outside-toplevel
+        from ._lib import CudaOps  # pylint: disable=import-outside-toplevel
+        dev = self._ops.device
+        if self._pool is None:
+            self._pool = []
+        while len(self._pool) < nw:
+            self._pool.append((CudaOps(dev.index), torch.cuda.Stream(device=dev)))
+        main = torch.cuda.current_stream(dev)
+        streams = [main] + [st for _, st in self._pool[:nw]]
+        for gate in gates:                    # gate matrices are uploaded on the main stream
+            self._gate_matrix(gate)
+        start = main.record_event()
+        results, errors, done = [None] * len(gates), [], [None] * nw
+
+        def work(w):
+            try:
+                wops, stream = self._pool[w]
+                with torch.cuda.stream(stream):
+                    stream.wait_event(start)
+                    for gi in range(w, len(gates), nw):
+                        results[gi] = self._nn_gate_compute(gates[gi], wops, streams)
+                    done[w] = stream.record_event()
+            except Exception as exc:  # pylint: disable=broad-except
+                errors.append(exc)
+
+        threads = [threading.Thread(target=work, args=(w,)) for w in range(nw)]
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
+        if errors:
+            raise errors[0]
+        for ev in done:
+            main.wait_event(ev)
+        for res in results:
+            self._nn_gate_commit(*res)
 
     def apply_site_gate_layer(self, gate_layer):                       # :233-236
         for gate in gate_layer.gates:
@@ -141,27 +205,46 @@ class PtTebdBackend:
 
     def apply_nn_gate(self, gate):
         """_apply_nn_gate (pt_tebd_backend.py:447-565), Figs. S2(c-h) of [Fux2023]."""
-        ops, eps = self._ops, self._epsrel
+        self._nn_gate_commit(*self._nn_gate_compute(gate, self._ops, None))
+
+    def _nn_gate_commit(self, sl, new_l, new_r, lam, inv_lam):         # :561-565
+        self._gammas[sl], self._gammas[sl + 1] = new_l, new_r
+        self._lams[sl + 1], self._inv_lams[sl + 1] = lam, inv_lam
+
+    def _nn_gate_compute(self, gate, ops, streams):
+        """The gate on (sl, sl + 1) with the kernels of `ops` on the current stream; returns
+        what :meth:`_nn_gate_commit` stores.  ``streams``: every stream that may touch the
+        chain (concurrent layers) -- inputs and outputs are registered with all of them."""
+        eps = self._epsrel
         sl, sr = gate.sites[0], gate.sites[1]
         assert sr == sl + 1
         gmat, na, nb, d2l, d2r = self._gate_matrix(gate)
         gam_l, gam_r = self._gammas[sl], self._gammas[sr]
+        lam_l, lam_m, lam_r = self._lams[sl], self._lams[sl + 1], self._lams[sr + 1]
+        inv_l, inv_r = self._inv_lams[sl], self._inv_lams[sr + 1]
+
+        def share(*tensors):
+            if streams is not None:
+                for t in tensors:
+                    for st in streams:
+                        t.record_stream(st)
+        share(gmat, gam_l, gam_r, lam_l, lam_m, lam_r, inv_l, inv_r)
         nl, _, pl, nm = gam_l.shape
         _, _, pr, nr = gam_r.shape
         assert gam_l.shape[1] == d2l and gam_r.shape[1] == d2r and gam_r.shape[0] == nm
         # -- split the process-tensor leg off the left site (:487-496):
         #    (lam_l Gam_l)[(L,b),(p,M)] = U1 [(L,b),k1] . S1 Vh1 [k1,(p,M)]
-        left = self._scale_rows(gam_l, self._lams[sl], nl, d2l * pl * nm)
+        left = self._scale_rows(gam_l, lam_l, nl, d2l * pl * nm, ops)
         h1 = ops.svd_factor(left, nl * pl, d2l * nm, d2l * pl * nm, pl * nm, eps,
                             rin=pl, rsi=nm, cin=nm, csi=1, cos_tol=COS_TOL)
         k1 = h1.keep
         u1 = ops.empty(nl, pl, k1)
         svh1 = ops.empty(k1, d2l, nm)
         ops.svd_emit(h1, u=u1, u_na=1, u_so=k1, u_sa=0, u_sj=1, svh=svh1)
-        left_mid = self._scale_cols(svh1, self._lams[sl + 1], k1 * d2l, nm)    # times lam_m
+        left_mid = self._scale_cols(svh1, lam_m, k1 * d2l, nm, ops)            # times lam_m
         # -- and off the right site (:498-507): (Gam_r lam_r)[(M,p),(b,R)] = U2 S2 . Vh2.
         #    The transposed matrix is factorised, so that U' = Vh2^T and S Vh' = (U2 S2)^T
-        right = self._scale_cols(gam_r, self._lams[sr + 1], nm * d2r * pr, nr)
+        right = self._scale_cols(gam_r, lam_r, nm * d2r * pr, nr, ops)
         h2 = ops.svd_factor(right, pr * nr, nm * d2r, 1, pr * nr, eps, cos_tol=COS_TOL)
         k2 = h2.keep
         right_temp = ops.empty(k2, pr, nr)
@@ -190,14 +273,14 @@ class PtTebdBackend:
         ops.gemm(pl, nj, k1, View(u1, row=k1, col=1, b1=pl * k1),
                  View(u3, row=na * nj, col=1, b2=nj),
                  View(new_l, row=nj, col=1, b1=na * pl * nj, b2=pl * nj), nb1=nl, nb2=na,
-                 scale=View(self._inv_lams[sl], b1=1))
-        rts = self._scale_cols(right_temp, self._inv_lams[sr + 1], k2 * pr, nr)
+                 scale=View(inv_l, b1=1))
+        rts = self._scale_cols(right_temp, inv_r, k2 * pr, nr, ops)
         new_r = ops.empty(nj, nb, pr, nr)
         ops.gemm(nj, pr * nr, k2, View(vh3, row=nb * k2, col=1, b1=k2),
                  View(rts, row=pr * nr, col=1),
                  View(new_r, row=nb * pr * nr, col=1, b1=pr * nr), nb1=nb)
-        self._gammas[sl], self._gammas[sr] = new_l, new_r
-        self._lams[sl + 1], self._inv_lams[sl + 1] = lam, inv_lam
+        share(new_l, new_r, lam, inv_lam)
+        return sl, new_l, new_r, lam, inv_lam
 
     # -------------------------------------------------------------- process tensors
     def apply_process_tensors(self, step, process_tensors):

@@ -217,6 +217,38 @@ def test_svd_split_strides_and_parts(shape, rows):
     np.testing.assert_allclose(hvh @ hvh.conj().T, np.eye(k), atol=1e-10)
 
 
+@pytest.mark.parametrize("m,n", [(300, 280), (1500, 96), (96, 1500), (700, 130)])
+def test_trunc_svd_relative_mode_qr_path(m, n):
+    """cos_tol > 0 (PT-TEBD): the rank-revealing QR front end in the RELATIVE-accuracy mode,
+    square and tall splits.  Graded operand over 12 decades, eps = 1e-5: same `keep` as
+    LAPACK, kept singular values to 1e-9 RELATIVE, orthonormal factors, and the product
+    lambda^-1-safe: U diag(lambda) Vh reproduces theta to 1e-12 s_0 beyond the truncation."""
+    ops = default_ops()
+    rng = np.random.default_rng(m + n)
+    q = min(m, n)
+    uu = np.linalg.qr(rnd(rng, m, q))[0]
+    vv = np.linalg.qr(rnd(rng, n, q))[0]
+    sv = np.logspace(0, -12, q)
+    a = (uu * sv) @ vv.conj().T
+    eps = 1e-5
+    h = ops.svd_factor(ops.from_host(a), m, n, n, 1, eps, cos_tol=1e-12)
+    assert ops.svd_plan(h)[0] == 1                       # the QR path ran
+    s_ref = np.linalg.svd(a, compute_uv=False)
+    k = h.keep
+    assert k == ref_keep(s_ref, eps)
+    u, vh = ops.empty(m, k), ops.empty(k, n)
+    lam, inv = ops.empty(k), ops.empty(k)
+    ops.svd_emit(h, u=u, u_na=1, u_so=k, u_sa=0, u_sj=1, vh=vh, lam=lam, inv_lam=inv)
+    hu, hvh, hl, hi = (ops.to_host(x) for x in (u, vh, lam, inv))
+    np.testing.assert_allclose(hl.real, s_ref[:k], rtol=1e-9)
+    np.testing.assert_allclose(hl * hi, np.ones(k), atol=1e-13)
+    np.testing.assert_allclose(hu.conj().T @ hu, np.eye(k), atol=1e-10)
+    np.testing.assert_allclose(hvh @ hvh.conj().T, np.eye(k), atol=1e-10)
+    trunc = np.linalg.norm(s_ref[k:])
+    err = np.linalg.norm((hu * hl) @ hvh - a)
+    assert err <= trunc * (1 + 1e-6) + 1e-12 * s_ref[0], (err, trunc)
+
+
 @pytest.mark.parametrize("m,n", [(1, 1), (1, 9), (9, 1), (2, 33), (33, 2)])
 def test_trunc_svd_degenerate_shapes(m, n):
     """Vectors and 1x1 operands (the first and last sites of a chain)."""

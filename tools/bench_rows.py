@@ -200,7 +200,8 @@ def tebd_row(n_sites=16):
                                           for s, t in layer]) for layer in big_layers]
 
     def run_device(steps=steps):
-        be = ob.PtTebdBackend(gam, lam, eps, {}, ops=ops)
+        par = int(os.environ.get("TEBD_PARALLEL", "0"))
+        be = ob.PtTebdBackend(gam, lam, eps, {"parallel": par} if par else {}, ops=ops)
         nsvd0 = ops.launch_count()
         for step in range(1, steps + 1):
             for layer in gate_layers:
@@ -238,8 +239,9 @@ def tebd_row(n_sites=16):
          bond_dims_gpu=[int(x) for x in be.get_bond_dimensions()],
          bond_dims_oracle=[int(x) for x in orc.get_bond_dimensions()],
          max_abs_err_vs_oracle=float(np.abs(rho - rho_ref).max()), gpu_launches=launches,
-         bound="latency (a chain of small dependent SVDs per gate; gates of a layer are "
-               "independent and could run on separate streams)")
+         parallel=int(os.environ.get("TEBD_PARALLEL", "0")),
+         bound="latency (a chain of dependent SVDs per gate; TEBD_PARALLEL=k runs the gates "
+               "of a layer on k streams)")
 
 
 if __name__ == "__main__":

@@ -17,6 +17,15 @@ for job in "$@"; do
     bench_x32) B200_SVD_XROWS=32 B200_SVD_WROWS=48 timeout 900 python bench.py --steps 20 --warmup 5 --no-cpu > gpurun_out/${TAG}_bench_x32.json 2> gpurun_out/${TAG}_bench_x32.err ;;
     bench_x48) B200_SVD_XROWS=48 B200_SVD_WROWS=64 timeout 900 python bench.py --steps 20 --warmup 5 --no-cpu > gpurun_out/${TAG}_bench_x48.json 2> gpurun_out/${TAG}_bench_x48.err ;;
     bench_x16) B200_SVD_XROWS=16 B200_SVD_WROWS=32 timeout 900 python bench.py --steps 20 --warmup 5 --no-cpu > gpurun_out/${TAG}_bench_x16.json 2> gpurun_out/${TAG}_bench_x16.err ;;
+    tebd0)     timeout 900 python tools/bench_rows.py tebd > gpurun_out/${TAG}_tebd0.jsonl 2> gpurun_out/${TAG}_tebd0.err ;;
+    tebd1)     B200_SVD_QR_COSTOL=1 timeout 900 python tools/bench_rows.py tebd > gpurun_out/${TAG}_tebd1.jsonl 2> gpurun_out/${TAG}_tebd1.err ;;
+    tebd2)     B200_SVD_QR_COSTOL=1 B200_SVD_QR_TALL=16 timeout 900 python tools/bench_rows.py tebd > gpurun_out/${TAG}_tebd2.jsonl 2> gpurun_out/${TAG}_tebd2.err ;;
+    tebdp4)    TEBD_PARALLEL=4 timeout 900 python tools/bench_rows.py tebd > gpurun_out/${TAG}_tebdp4.jsonl 2> gpurun_out/${TAG}_tebdp4.err ;;
+    tebdp8)    TEBD_PARALLEL=8 timeout 900 python tools/bench_rows.py tebd > gpurun_out/${TAG}_tebdp8.jsonl 2> gpurun_out/${TAG}_tebdp8.err ;;
+    tebd3)     B200_SVD_QR_COSTOL=1 B200_SVD_QR_TALL=16 B200_SVD_QR_MINQ=128 timeout 900 python tools/bench_rows.py tebd > gpurun_out/${TAG}_tebd3.jsonl 2> gpurun_out/${TAG}_tebd3.err ;;
+    tebd4)     B200_SVD_QR_COSTOL=1 B200_SVD_QR_TALL=16 B200_SVD_QR_MINQ=64 timeout 900 python tools/bench_rows.py tebd > gpurun_out/${TAG}_tebd4.jsonl 2> gpurun_out/${TAG}_tebd4.err ;;
+    tebdtest2) B200_SVD_QR_COSTOL=1 B200_SVD_QR_TALL=16 timeout 900 python -m pytest tests/test_parity_gpu.py -x -q -k tebd > gpurun_out/${TAG}_tebdtest2.log 2>&1 ;;
+    rows)      timeout 1500 python tools/bench_rows.py > gpurun_out/${TAG}_rows.jsonl 2> gpurun_out/${TAG}_rows.err ;;
     svdstep)   timeout 900 python tools/svd_profile_step.py 40 > gpurun_out/${TAG}_svdstep.log 2>&1 ;;
     stepprof)  timeout 600 python tools/step_profile.py 50 300 > gpurun_out/${TAG}_stepprof.jsonl 2> gpurun_out/${TAG}_stepprof.err ;;
     stepprof_noqr) B200_SVD_QR=0 timeout 600 python tools/step_profile.py 50 300 > gpurun_out/${TAG}_stepprof_noqr.jsonl 2> gpurun_out/${TAG}_stepprof_noqr.err ;;
