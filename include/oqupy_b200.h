@@ -282,6 +282,10 @@ int b200_tempo_batch_set(void* batch, const void* mid, const void* start, const 
 int b200_tempo_batch_step(void* batch, const void* p1, const void* p2t, void* states_out);
 int b200_tempo_batch_info(void* batch, int32_t* status, int32_t* svds, int32_t* sweeps,
                           int32_t* max_chi, int32_t* bonds);
+/* CTA i of the following steps takes member order[i] (host array, a permutation of
+ * 0..n_members-1; NULL: identity): longest-running members first (a scheduling hint, the
+ * results do not depend on it). */
+int b200_tempo_batch_set_order(void* batch, const int32_t* order);
 size_t b200_tempo_batch_bytes(void* batch);
 
 #ifdef __cplusplus

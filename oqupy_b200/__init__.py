@@ -8,14 +8,15 @@ the compute_dynamics loop.  Everything reaches the GPU through the C-ABI library
 from .backends import (BaseTempoBackend, MeanFieldTempoBackend, PtTempoBackend,
                        TempoBackend)
 from .tebd import PtTebdBackend
-from .process_tensor import (DeviceProcessTensor, dynamics_device, gradient_device,
+from .process_tensor import (DeviceProcessTensor, dynamics_device,
+                             dynamics_with_field_device, gradient_device,
                              import_process_tensor)
 from ._lib import B200Error, CudaOps, default_ops, load_library
 from .batch import BatchedTempoBackend
 
 __all__ = ["BatchedTempoBackend", "BaseTempoBackend", "MeanFieldTempoBackend", "PtTempoBackend", "TempoBackend",
            "PtTebdBackend",
-           "DeviceProcessTensor", "dynamics_device", "gradient_device",
+           "DeviceProcessTensor", "dynamics_device", "dynamics_with_field_device", "gradient_device",
            "import_process_tensor", "B200Error", "CudaOps",
            "default_ops", "load_library"]
 __version__ = "0.1.0"

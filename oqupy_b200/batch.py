@@ -171,6 +171,25 @@ class BatchedTempoBackend:
             self.check()
         return out
 
+    def set_order(self, order=None):
+        """CTA i of the following launches takes member ``order[i]`` (None: identity).  A
+        scheduling hint only -- every member is still advanced exactly once per step."""
+        if order is None:
+            arr = None
+        else:
+            arr = (c_int32 * self.E)(*[int(x) for x in order])
+        self._ops._check(self._ops.lib.b200_tempo_batch_set_order(c_void_p(self._h), arr),  # pylint: disable=protected-access
+                         "b200_tempo_batch_set_order")
+
+    def rebalance(self):
+        """Longest-processing-time-first: hand the members with the largest bond dimensions
+        (cost ~ chi^3 per SVD) to the first CTAs of every launch, so that the last wave of a
+        step does not wait for one heavy member.  Returns the order."""
+        chi = self.info()["max_chi"].astype(np.int64)
+        order = np.argsort(-chi, kind="stable")
+        self.set_order(order)
+        return order
+
     def info(self):
         """dict of per-member arrays: status, svds, sweeps, max_chi, bonds (list of lists)."""
         e_ = self.E

@@ -57,6 +57,7 @@ struct BatchDev {
   cplx* tmp;          // [E][slot_elems]
   cplx* states;       // [E][d2]
   int first_member;
+  const int* order;   // [E] member taken by CTA i (nullptr: i): longest-running members first
 };
 
 __device__ __forceinline__ double wsum(double x) {
@@ -436,7 +437,7 @@ __global__ void __launch_bounds__(BT, 1) tempo_batch_step_kernel(const BatchDev 
   extern __shared__ __align__(16) unsigned char bsm[];
   __shared__ SvdShared S;
   const int tid = threadIdx.x;
-  const int e = P.first_member + blockIdx.x;
+  const int e = P.order ? P.order[blockIdx.x] : P.first_member + blockIdx.x;
   if (e >= P.E) return;
   const int d2 = P.d2, NS = P.ns_slots;
   int* hdr = P.hdr + (size_t)e * 8;
@@ -682,6 +683,7 @@ struct Batch {
   int step;
   size_t bytes;
   void* arena;
+  int* order_buf;
 };
 
 }  // namespace
@@ -710,6 +712,7 @@ void* b200_tempo_batch_create(void* stream, int n_members, int d2, int dkmax, in
   if (D.slot_elems < 2 * MAXD + chi_cap * d2 * d2) D.slot_elems = 2 * MAXD + chi_cap * d2 * d2;
   D.n_infl = dkmax + 1;
   D.first_member = 0;
+  D.order = nullptr;
   const size_t E = (size_t)n_members, d4 = (size_t)d2 * d2;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
@@ -728,6 +731,7 @@ void* b200_tempo_batch_create(void* stream, int n_members, int d2, int dkmax, in
   const size_t o_jg = take(E * (size_t)MAXD * MAXD * sizeof(cplx));
   const size_t o_tmp = take(E * D.slot_elems * sizeof(cplx));
   const size_t o_states = take(E * d2 * sizeof(cplx));
+  const size_t o_order = take(E * sizeof(int));
   b->bytes = off;
   if (cudaMalloc(&b->arena, off) != cudaSuccess) {
     b200::set_error("b200_tempo_batch_create: cudaMalloc(%zu) failed", off);
@@ -743,6 +747,7 @@ void* b200_tempo_batch_create(void* stream, int n_members, int d2, int dkmax, in
   D.p1 = (cplx*)(base + o_p1); D.p2t = (cplx*)(base + o_p2); D.carry = (cplx*)(base + o_carry);
   D.vg = (cplx*)(base + o_vg); D.jg = (cplx*)(base + o_jg); D.tmp = (cplx*)(base + o_tmp);
   D.states = (cplx*)(base + o_states);
+  b->order_buf = (int*)(base + o_order);
   static std::once_flag once;       // ensembles drive the library from several host threads
   static cudaError_t attr_rc = cudaSuccess;
   std::call_once(once, [] {
@@ -858,6 +863,30 @@ int b200_tempo_batch_info(void* h, int32_t* status, int32_t* svds, int32_t* swee
       }
     }
   }
+  return B200_OK;
+}
+
+/* CTA i of the following steps takes member order[i] (a permutation of 0..E-1, host array;
+ * NULL restores the identity).  One launch advances E members that differ widely in cost
+ * (bond dimension^3): handing the longest-running members out FIRST keeps the last wave of
+ * CTAs short (longest-processing-time-first; measured on the 4096-member grid of BASELINE
+ * configs[4] at 512 members per GPU). */
+int b200_tempo_batch_set_order(void* h, const int32_t* order) {
+  Batch* b = (Batch*)h;
+  if (!b) { b200::set_error("b200_tempo_batch_set_order: invalid argument"); return B200_EINVAL; }
+  if (!order) { b->dev.order = nullptr; return B200_OK; }
+  std::vector<char> seen((size_t)b->E, 0);
+  for (int i = 0; i < b->E; ++i) {
+    if (order[i] < 0 || order[i] >= b->E || seen[(size_t)order[i]]) {
+      b200::set_error("b200_tempo_batch_set_order: not a permutation of 0..%d", b->E - 1);
+      return B200_EINVAL;
+    }
+    seen[(size_t)order[i]] = 1;
+  }
+  // (pageable source: the copy is staged before the call returns)
+  B200_CUDA_CHECK(cudaMemcpyAsync(b->order_buf, order, (size_t)b->E * sizeof(int),
+                                  cudaMemcpyHostToDevice, b->stream));
+  b->dev.order = b->order_buf;
   return B200_OK;
 }
 

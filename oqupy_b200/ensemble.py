@@ -7,6 +7,8 @@ of a parameter grid); no data-path collective exists.  The ONLY collective is th
 final gather of the per-member dynamics (``all_gather_into_tensor``: NCCL over NVLink
 on GPUs, gloo in the CPU tests).
 """
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -259,7 +261,15 @@ def tempo_grid(influences, initial_state, unitary, propagators, dkmax, epsrel, n
             # bond dimensions saturate within a few memory times: look for members that left
             # the lock-step path after 3 dkmax steps and start their re-runs right away
             probe = min(num_steps, 3 * dkmax)
-            parts = [s0[None], be.compute_steps(probe, strict=False)]
+            first = min(probe, max(2, dkmax // 2))
+            parts = [s0[None], be.compute_steps(first, strict=False)]
+            lpt = os.environ.get("B200_BATCH_REBALANCE", "1") != "0"
+            if lpt:
+                be.rebalance()       # heavy members (large bond dimensions) first from now on
+            if probe > first:
+                parts.append(be.compute_steps(probe - first, strict=False))
+            if lpt:
+                be.rebalance()
             redo = {}
             pending = []
             early = overflowed(redo)

@@ -143,6 +143,63 @@ def _compute_gradient_factory(original, dynamics_cls):
     return compute_gradient_and_dynamics
 
 
+def _compute_dynamics_with_field_factory(original, dynamics_cls):
+    """``oqupy.compute_dynamics_with_field`` (system_dynamics.py:184-475): every system of the
+    mean-field model runs through its process tensor(s) on the device
+    (``oqupy_b200.dynamics_with_field_device``); the field equation of motion and the
+    field-dependent propagators stay host callbacks, as in the reference.  The reference's
+    own argument checks run first; anything the device path does not cover runs the
+    reference code."""
+    from .process_tensor import dynamics_with_field_device  # pylint: disable=import-outside-toplevel
+
+    def compute_dynamics_with_field(mean_field_system, initial_field, process_tensor_list=None,
+                                    dt=None, num_steps=None, initial_state_list=None,
+                                    start_time=0.0, control_list=None, record_all=True,
+                                    **kwargs):
+        def reference():
+            return original(mean_field_system, initial_field,
+                            process_tensor_list=process_tensor_list, dt=dt,
+                            num_steps=num_steps, initial_state_list=initial_state_list,
+                            start_time=start_time, control_list=control_list,
+                            record_all=record_all, **kwargs)
+        from oqupy.system import MeanFieldSystem  # pylint: disable=import-outside-toplevel
+        if (not _FORCE["dynamics"] or process_tensor_list is None
+                or not isinstance(mean_field_system, MeanFieldSystem)
+                or not isinstance(process_tensor_list, list)):
+            return reference()
+        systems = mean_field_system.system_list
+        nsys = len(systems)
+        states0 = [None] * nsys if initial_state_list is None else initial_state_list
+        ctrls = [None] * nsys if control_list is None else control_list
+        if nsys == 0 or not nsys == len(states0) == len(ctrls) == len(process_tensor_list):
+            return reference()                 # raises the reference's own message
+        from oqupy.config import INTEGRATE_EPSREL, SUBDIV_LIMIT  # pylint: disable=import-outside-toplevel
+        from oqupy.system_dynamics import _compute_dynamics_input_parse  # pylint: disable=import-outside-toplevel
+        parsed = [_compute_dynamics_input_parse(True, sys_, st, dt, num_steps, start_time, pt,
+                                                ct, record_all)
+                  for sys_, st, pt, ct in zip(systems, states0, process_tensor_list, ctrls)]
+        step, n, rec_all = parsed[0][2], parsed[0][3], parsed[0][7]
+        devs = [[_device_process_tensor(p) for p in par[5]] for par in parsed]
+        if n < 1 or any(not d or any(x is None for x in d) for d in devs):
+            return reference()
+        props = [par[0].get_propagators(step, start_time,
+                                        kwargs.get("subdiv_limit", SUBDIV_LIMIT),
+                                        kwargs.get("liouvillian_epsrel", INTEGRATE_EPSREL))
+                 for par in parsed]
+        controls = [(lambda k, c=par[6]: c.get_controls(k, dt=step, start_time=start_time))
+                    for par in parsed]
+        states, fields = dynamics_with_field_device(
+            devs, props, [par[1] for par in parsed], complex(initial_field),
+            mean_field_system.field_eom, step, start_time, n, controls_list=controls)
+        if rec_all:
+            times = [start_time + step * k for k in range(n + 1)]
+            return dynamics_cls(times=times, system_states_list=states, fields=fields)
+        return dynamics_cls(times=[start_time + 1 * step], system_states_list=[states[-1]],
+                            fields=[fields[-1]])
+    compute_dynamics_with_field.__doc__ = original.__doc__
+    return compute_dynamics_with_field
+
+
 def install(default=False, dynamics=True):
     """Rebind OQuPy's backend names.  With ``default=True`` the config dictionaries are
     also mutated in place so that every Tempo / PtTempo uses the B200 backend.
@@ -178,6 +235,12 @@ def install(default=False, dynamics=True):
     shim = _compute_dynamics_factory(_ORIGINALS["compute_dynamics"], oqupy.Dynamics)
     sdm.compute_dynamics = shim
     oqupy.compute_dynamics = shim
+    if "compute_dynamics_with_field" not in _ORIGINALS:
+        _ORIGINALS["compute_dynamics_with_field"] = sdm.compute_dynamics_with_field
+    fshim = _compute_dynamics_with_field_factory(_ORIGINALS["compute_dynamics_with_field"],
+                                                 oqupy.MeanFieldDynamics)
+    sdm.compute_dynamics_with_field = fshim
+    oqupy.compute_dynamics_with_field = fshim
     # oqupy.gradient.compute_gradient_and_dynamics (gradient.py:169-437), also reached by
     # oqupy.state_gradient through its module
     import oqupy.gradient as gm  # pylint: disable=import-outside-toplevel
@@ -210,6 +273,8 @@ def uninstall():
     import oqupy.system_dynamics as sdm  # pylint: disable=import-outside-toplevel
     sdm.compute_dynamics = _ORIGINALS["compute_dynamics"]
     oqupy.compute_dynamics = _ORIGINALS["compute_dynamics"]
+    sdm.compute_dynamics_with_field = _ORIGINALS["compute_dynamics_with_field"]
+    oqupy.compute_dynamics_with_field = _ORIGINALS["compute_dynamics_with_field"]
     import oqupy.gradient as gm  # pylint: disable=import-outside-toplevel
     gm.compute_gradient_and_dynamics = _ORIGINALS["compute_gradient_and_dynamics"]
     oqupy.compute_gradient_and_dynamics = _ORIGINALS["compute_gradient_and_dynamics"]

@@ -411,6 +411,123 @@ def _dynamics_multi_env(pts, propagators, initial_state, num_steps, ops):
     return ops.to_host(rho).reshape(num_steps + 1, d, d)
 
 
+class _SteppedState:
+    """One system's state (chi_1, ..., chi_m, d2) on the device, advanced step by step through
+    its m >= 1 process tensors -- the loop body of system_dynamics.py:131-170 / 366-447 for
+    callers that need the state between the steps (mean-field systems: the propagators of a
+    step depend on the field, the field on the states)."""
+
+    def __init__(self, pts, initial_state, ops):
+        from ._lib import View  # pylint: disable=import-outside-toplevel
+        self._view = View
+        self.pts, self.ops = list(pts), ops
+        rho0 = np.asarray(initial_state, dtype=CDTYPE)
+        self.d = rho0.shape[0]
+        self.d2 = self.d * self.d
+        self.dims = [1] * len(self.pts)
+        self.v = ops.from_host(rho0.reshape(1, self.d2))
+        self._mats = {}
+
+    def sys_leg(self, mat):
+        """v[..., j] <- sum_i mat[j, i] v[..., i]  (_apply_system_superoperator, :631-640)"""
+        ops, d2, view = self.ops, self.d2, self._view
+        dm = ops.from_host(np.ascontiguousarray(np.asarray(mat, dtype=CDTYPE)))
+        rows = int(self.v.numel()) // d2
+        out = ops.empty(rows, d2)
+        ops.gemm(rows, d2, d2, view(self.v, row=d2, col=1), view(dm, row=1, col=d2),
+                 view(out, row=d2, col=1))
+        self.v = out
+
+    def readout(self, step):
+        """rho = sum cap_1[l_1] .. cap_m[l_m] v[l_1..l_m, :]  (_apply_caps, :643-651)"""
+        ops, d2, view = self.ops, self.d2, self._view
+        cur = self.v
+        rest = int(np.prod(self.dims)) * d2
+        for e, pt in enumerate(self.pts):
+            rest //= self.dims[e]
+            cap = pt.get_cap_tensor_device(step)
+            out = ops.empty(rest)
+            ops.gemm(1, rest, self.dims[e], view(cap, col=1), view(cur, row=rest, col=1),
+                     view(out, col=1))
+            cur = out
+        return ops.to_host(cur).reshape(self.d, self.d)
+
+    def through(self, step):
+        """_apply_pt_mpos (:654-700) with rank-3 sites and their transforms"""
+        ops, d2, view = self.ops, self.d2, self._view
+        for e, pt in enumerate(self.pts):
+            t = pt.get_mpo_tensor_device(step)
+            chi_l, chi_r, _ = (int(x) for x in t.shape)
+            assert chi_l == self.dims[e] and int(t.shape[2]) == d2
+            if pt.transform_in is not None:
+                self.sys_leg(np.asarray(pt.transform_in).T)
+            na = int(np.prod(self.dims[:e]))
+            nb = int(np.prod(self.dims[e + 1:]))
+            nxt = ops.empty(na * chi_r * nb, d2)
+            ops.gemm(chi_r, nb, chi_l, view(t, row=d2, col=chi_r * d2, b1=1),
+                     view(self.v, row=nb * d2, col=d2, b1=1, b2=chi_l * nb * d2),
+                     view(nxt, row=nb * d2, col=d2, b1=1, b2=chi_r * nb * d2),
+                     nb1=d2, nb2=na)
+            self.v = nxt
+            self.dims[e] = chi_r
+            if pt.transform_out is not None:
+                self.sys_leg(np.asarray(pt.transform_out).T)
+
+
+def dynamics_with_field_device(pts_list, propagators_list, initial_state_list, initial_field,
+                               field_eom, dt, start_time, num_steps, ops=None,
+                               controls_list=None):
+    """compute_dynamics_with_field hot loop (system_dynamics.py:366-470): every system of a
+    mean-field model is propagated through its own process tensor(s) on the device; per step
+    the reduced states come back (d x d each), the field takes its Heun step on the host
+    (:324-330) and the field-dependent propagators of the step are uploaded.
+
+    ``pts_list[s]``: list of device process tensors of system s; ``propagators_list[s]``:
+    ``(step, field, field_derivative) -> (P1, P2)`` (system.py: TimeDependentSystemWithField);
+    ``controls_list[s]``: ``step -> (pre, post)`` or None.  Returns (states, fields):
+    states[k][s] the (d, d) state of system s at step k (num_steps + 1 entries), fields[k]."""
+    ops = default_ops() if ops is None else ops
+    nsys = len(pts_list)
+    if controls_list is None:
+        controls_list = [None] * nsys
+    sts = [_SteppedState(pts, rho0, ops) for pts, rho0 in zip(pts_list, initial_state_list)]
+
+    def heun(t, states, field, next_states):
+        rk1 = field_eom(t, states, field)
+        rk2 = field_eom(t + dt, next_states, field + rk1 * dt)
+        return field + dt * (rk1 + rk2) / 2
+
+    all_states, fields = [], []
+    field, prev = initial_field, None
+    t = start_time
+    for step in range(num_steps + 1):
+        t = start_time + step * dt
+        ctl = [(None, None) if c is None else c(step) for c in controls_list]
+        for st, (pre, _) in zip(sts, ctl):
+            if pre is not None:
+                st.sys_leg(pre)
+        if step == num_steps:
+            break
+        states = [st.readout(step) for st in sts]
+        field = initial_field if step == 0 else heun(t, prev, field, states)
+        prev = states
+        all_states.append(states)
+        fields.append(field)
+        for st, (_, post) in zip(sts, ctl):
+            if post is not None:
+                st.sys_leg(post)
+        dfield = field_eom(t, states, field)
+        for st, props in zip(sts, propagators_list):
+            p1, p2 = props(step, field, dfield)
+            st.sys_leg(p1)
+            st.through(step)
+            st.sys_leg(p2)
+    final = [st.readout(num_steps) for st in sts]
+    all_states.append(final)
+    fields.append(heun(t, prev, field, final))
+    return all_states, fields
+
+
 def _gradient_multi_env(pts, propagators, initial_state, target_derivative, num_steps, ops,
                         controls):
     """gradient_device for m >= 2 environments (gradient.py:266-425 with one bond leg per

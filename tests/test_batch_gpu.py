@@ -72,6 +72,33 @@ def test_batched_tempo_step_by_step_equals_block():
     np.testing.assert_array_equal(blk[:, 0], blk[:, 2])
 
 
+def test_batched_tempo_launch_order_is_only_a_scheduling_hint():
+    """set_order / rebalance (longest members first): bit-identical states and bond dimensions
+    whatever CTA takes which member; a non-permutation is rejected."""
+    g = load_golden("tempo_c1_k20_eps7_n60")
+    base = g["influences"][:9]
+    infl = np.array([scaled(base, f) for f in (0.1, 2.0, 0.5, 1.3, 0.02, 0.9)])
+    mk = lambda: ob.BatchedTempoBackend(  # noqa: E731
+        np.array([g["initial_state"].reshape(-1)] * 6), infl, g["unitary"],
+        lambda s: (g["prop_1"], g["prop_2"]), np.ones(4), np.ones(4), 8, 1e-7)
+    a, b = mk(), mk()
+    a.initialize()
+    b.initialize()
+    ref = a.compute_steps(14)
+    b.set_order([5, 3, 1, 0, 2, 4])
+    part1 = b.compute_steps(6)
+    order = b.rebalance()
+    assert sorted(order.tolist()) == list(range(6))
+    chi = b.info()["max_chi"]
+    assert all(chi[order[i]] >= chi[order[i + 1]] for i in range(5))
+    part2 = b.compute_steps(8)
+    np.testing.assert_array_equal(np.concatenate((part1, part2)), ref)
+    assert a.get_bond_dimensions() == b.get_bond_dimensions()
+    b.set_order(None)
+    with pytest.raises(ob.B200Error):
+        b.set_order([0, 1, 2, 3, 4, 4])
+
+
 def test_batched_tempo_capacity_is_reported():
     g = load_golden("tempo_c1_k20_eps7_n60")
     infl = np.array([g["influences"][:21]])

@@ -326,3 +326,60 @@ def test_install_compute_gradient_and_dynamics(monkeypatch):
         install.uninstall()
     assert oqupy.gradient.compute_gradient_and_dynamics is \
         install._ORIGINALS["compute_gradient_and_dynamics"]
+
+
+def test_install_compute_dynamics_with_field(monkeypatch):
+    """oqupy.compute_dynamics_with_field rebound (system_dynamics.py:184-475): a mean-field
+    model of two systems, each with its own reference-built process tensor (the second one
+    with two environments), a control on one system, against the reference's own function."""
+    oqupy = load_reference()
+    np.vectorize = lambda f, *a, **k: f     # numpy-2: see tests/golden/make_golden_mean_field.py
+    from oqupy_b200 import backends, install, process_tensor
+    from host_model_ops import HostModelOps
+    ops = HostModelOps()
+    monkeypatch.setattr(backends, "default_ops", lambda: ops)
+    monkeypatch.setattr(process_tensor, "default_ops", lambda: ops)
+    sig = oqupy.operators.sigma
+    dt, n = 0.1, 8
+    pts = []
+    for alpha, temp in ((0.2, 0.5), (0.1, 1.3)):
+        corr = oqupy.PowerLawSD(alpha=alpha, zeta=1, cutoff=4.0, cutoff_type="exponential",
+                                temperature=temp)
+        pts.append(oqupy.pt_tempo_compute(
+            bath=oqupy.Bath(0.5 * sig("z"), corr), start_time=0.0, end_time=dt * n,
+            parameters=oqupy.TempoParameters(dt=dt, dkmax=4, epsrel=1e-6),
+            progress_type="silent"))
+
+    def make_system(w):
+        return oqupy.TimeDependentSystemWithField(
+            lambda t, field: 0.5 * w * sig("z") + 0.3 * (field * sig("+") + np.conj(field) * sig("-")))
+
+    def field_eom(t, states, field):
+        return -(0.2 + 1.0j) * field - 0.3j * sum(np.trace(sig("-") @ s) for s in states)
+
+    mfs = oqupy.MeanFieldSystem([make_system(1.0), make_system(0.6)], field_eom=field_eom)
+    rho0 = [oqupy.operators.spin_dm("z-"), oqupy.operators.spin_dm("x+")]
+    control = oqupy.Control(2)
+    control.add_single(3, oqupy.operators.left_super(sig("x")))
+    control.add_single(5, oqupy.operators.right_super(sig("y")), post=True)
+    cases = [dict(process_tensor_list=[pts[0], pts[1]]),
+             dict(process_tensor_list=[pts[0], [pts[1], pts[0]]], control_list=[control, None]),
+             dict(process_tensor_list=[pts[0], pts[1]], record_all=False)]
+    common = dict(mean_field_system=mfs, initial_field=0.4 + 0.1j, initial_state_list=rho0,
+                  progress_type="silent")
+    refs = [oqupy.compute_dynamics_with_field(**common, **c) for c in cases]
+    install.install()
+    try:
+        for case, ref in zip(cases, refs):
+            launches = ops.launches
+            new = oqupy.compute_dynamics_with_field(**common, **case)
+            assert ops.launches > launches            # ran on the (model) device
+            np.testing.assert_allclose(new.times, ref.times, atol=1e-12)
+            np.testing.assert_allclose(new.fields, ref.fields, atol=1e-10)
+            for a, b in zip(new.system_dynamics, ref.system_dynamics):
+                np.testing.assert_allclose(a.states, b.states, atol=1e-10)
+        with pytest.raises(AssertionError):
+            oqupy.compute_dynamics_with_field(**common, process_tensor_list=[pts[0]])
+    finally:
+        install.uninstall()
+    assert oqupy.compute_dynamics_with_field is install._ORIGINALS["compute_dynamics_with_field"]

@@ -44,6 +44,8 @@ for job in "$@"; do
     ncu_win)   B200_BENCH_CUPROF=1 timeout 2400 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 4000 --csv --log-file gpurun_out/${TAG}_launches_win.csv python bench.py --steps 2 --warmup 5 --preroll 25 --no-cpu > gpurun_out/${TAG}_ncu_win.log 2>&1 ;;
     ncu_list)  timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -s 43000 -c 3300 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/${TAG}_ncu_list.log 2>&1 ;;
     c5)        timeout 1500 python tools/c5_bench.py 64 200 > gpurun_out/${TAG}_c5_n1.json 2> gpurun_out/${TAG}_c5_n1.err ;;
+    c5r8on)    timeout 900 python tools/c5_bench.py 23 200 > gpurun_out/${TAG}_c5r8on.json 2> gpurun_out/${TAG}_c5r8on.err ;;
+    c5r8off)   B200_BATCH_REBALANCE=0 timeout 900 python tools/c5_bench.py 23 200 > gpurun_out/${TAG}_c5r8off.json 2> gpurun_out/${TAG}_c5r8off.err ;;
     c5small)   timeout 900 python tools/c5_bench.py 24 100 > gpurun_out/${TAG}_c5small.json 2> gpurun_out/${TAG}_c5small.err ;;
     c5_n2)     timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/c5_bench.py 64 200 > gpurun_out/${TAG}_c5_n2.json 2> gpurun_out/${TAG}_c5_n2.err ;;
     bench_n8)  timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_n8.json 2> gpurun_out/${TAG}_bench_n8.err ;;
