@@ -409,6 +409,15 @@ class NativeChain:
             raise B200Error("b200_chain_create failed: "
                             f"{self.lib.b200_last_error().decode()}")
         self._shape = (c_int32 * 3)()
+        self._stream_id = ops._stream().value
+
+    def _same_stream(self):
+        """The engine launches on the stream it was created with; torch allocations and the
+        other ops calls use the CURRENT stream.  Both must be the same stream (create and
+        drive a backend inside one ``torch.cuda.stream(...)`` context, or outside of any)."""
+        if self.ops._stream().value != self._stream_id:
+            raise B200Error("NativeChain was created on another CUDA stream than the current "
+                            "one: create and step a backend under the same torch stream")
 
     def __del__(self):
         try:
@@ -423,6 +432,7 @@ class NativeChain:
 
     def push(self, tensor):
         """Append a (chi_l, a, chi_r) complex128 device tensor (copied)."""
+        self._same_stream()
         t = tensor.contiguous()
         dl, da, dr = (int(x) for x in t.shape)
         self.ops._check(self.lib.b200_chain_push(c_void_p(self.h), t.data_ptr(), dl, da, dr),
@@ -435,17 +445,20 @@ class NativeChain:
 
     def site(self, i):
         """Copy of site i as a torch tensor (chi_l, a, chi_r)."""
+        self._same_stream()
         out = self.ops.empty(*self.shape(i))
         self.ops._check(self.lib.b200_chain_read(c_void_p(self.h), i, out.data_ptr()),
                         "b200_chain_read")
         return out
 
     def svd_sweep(self, from_index, to_index, eps):
+        self._same_stream()
         self.ops._check(self.lib.b200_chain_svd_sweep(c_void_p(self.h), from_index, to_index,
                                                       float(eps)), "b200_chain_svd_sweep")
 
     def pt_zip_up_left(self, mpo, eps):
         """mpo: list of chain.PtSite (kind, device matrix)."""
+        self._same_stream()
         arr = (_PtSite * len(mpo))()
         keep = []           # host map arrays stay alive for the call
         for k, site in enumerate(mpo):
@@ -468,6 +481,7 @@ class NativeChain:
 
     def tempo_step(self, mpo, p1, p2site, sum_north, d2, eps, state_out):
         """One whole TEMPO time step (b200_chain_tempo_step); mpo: list of chain.TempoSite."""
+        self._same_stream()
         arr = (_TempoSite * len(mpo))()
         for k, site in enumerate(mpo):
             arr[k].kind = TEMPO_KINDS[site.kind]

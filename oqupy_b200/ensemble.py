@@ -38,7 +38,11 @@ def _run_concurrent(mine, run_member, concurrent, make_ops, background=False):
         try:
             ops = make_ops() if make_ops is not None else None
             on_gpu = ops is not None and getattr(ops, "name", "") == "cuda"
-            stream = torch.cuda.Stream(device=ops.device) if on_gpu else None
+            # background work (members re-run next to a lock-step batch that fills every SM)
+            # goes on a HIGH-PRIORITY stream: its short cooperative launches take the SMs that
+            # free up first instead of queueing behind the batch's remaining CTAs
+            stream = torch.cuda.Stream(device=ops.device, priority=-1 if background else 0) \
+                if on_gpu else None
             while True:
                 try:
                     k, i = todo.get_nowait()
@@ -68,7 +72,7 @@ def _run_concurrent(mine, run_member, concurrent, make_ops, background=False):
 
 
 def run_ensemble(n_members, run_member, device=None, group=None, concurrent=1,
-                 make_ops=None, run_batch=None):
+                 make_ops=None, run_batch=None, timings=None):
     """Run ``run_member(i)`` (-> real or complex ndarray, same shape for all i) for the
     members of this rank and gather everything on every rank.
 
@@ -86,6 +90,8 @@ def run_ensemble(n_members, run_member, device=None, group=None, concurrent=1,
         world, rank = dist.get_world_size(group), dist.get_rank(group)
     else:
         world, rank = 1, 0
+    import time  # pylint: disable=import-outside-toplevel
+    t_run = time.perf_counter()
     mine = shard_indices(n_members, rank, world)
     if run_batch is not None:
         results = [np.asarray(r) for r in run_batch(mine)]
@@ -94,8 +100,11 @@ def run_ensemble(n_members, run_member, device=None, group=None, concurrent=1,
         results = _run_concurrent(mine, run_member, concurrent, make_ops)
     else:
         results = [np.asarray(run_member(i)) for i in mine]
+    if timings is not None:
+        timings["members_s"] = time.perf_counter() - t_run
     if world == 1:
         return np.stack(results) if results else np.zeros((0,))
+    t_gather = time.perf_counter()
     # every rank learns shape/dtype from rank 0 (which always owns member 0)
     meta = [None]
     if rank == 0:
@@ -122,6 +131,8 @@ def run_ensemble(n_members, run_member, device=None, group=None, concurrent=1,
     for r in range(world):
         for k, i in enumerate(shard_indices(n_members, r, world)):
             out[i] = allr[r, k]
+    if timings is not None:
+        timings["gather_s"] = time.perf_counter() - t_gather
     return out
 
 
@@ -195,7 +206,7 @@ def broadcast_process_tensor(pt, src=0, device=None, group=None, ops=None):
 
 def tempo_grid(influences, initial_state, unitary, propagators, dkmax, epsrel, num_steps,
                device=None, group=None, ops=None, chunk=4096, chi_cap=None,
-               fallback_concurrency=12):
+               fallback_concurrency=12, timings=None, check_every=10):
     """BASELINE configs[4]: an ensemble of independent TEMPO runs (one per parameter point)
     sharded over the ranks and, on every rank, advanced in LOCK-STEP by the batched engine
     (:class:`oqupy_b200.batch.BatchedTempoBackend`: one kernel launch per time step for all
@@ -220,9 +231,14 @@ def tempo_grid(influences, initial_state, unitary, propagators, dkmax, epsrel, n
             idx = list(indices[c0:c0 + chunk])
             st0 = np.broadcast_to(rho0.reshape(-1, d2), (len(idx), d2)) if rho0.ndim == 2 \
                 else rho0[idx].reshape(len(idx), d2)
+            import time  # pylint: disable=import-outside-toplevel
+            t_0 = time.perf_counter()
             be = BatchedTempoBackend(st0, infl[idx], unitary, propagators, np.ones(d2),
                                      np.ones(d2), dkmax, epsrel, chi_cap=chi_cap, ops=ops)
             _, s0 = be.initialize()
+            if timings is not None:
+                timings["setup_s"] = timings.get("setup_s", 0.0) + time.perf_counter() - t_0
+                t_0 = time.perf_counter()
             cuda = getattr(ops, "name", "cuda") == "cuda"
             dev_index = ops.device.index if (cuda and ops is not None) else 0
 
@@ -277,10 +293,24 @@ def tempo_grid(influences, initial_state, unitary, propagators, dkmax, epsrel, n
                 for k in early:
                     redo[k] = None
                 pending.append((early, start(early)))
-            if num_steps > probe:
-                parts.append(be.compute_steps(num_steps - probe, strict=False))
+            # the rest in chunks: a member that leaves the lock-step path late is noticed
+            # within `check_every` steps and re-run next to the batch instead of after it
+            done_steps = probe
+            while done_steps < num_steps:
+                nxt = min(check_every, num_steps - done_steps)
+                parts.append(be.compute_steps(nxt, strict=False))
+                done_steps += nxt
+                if done_steps < num_steps:
+                    more = overflowed(redo)
+                    if more:
+                        for k in more:
+                            redo[k] = None
+                        pending.append((more, start(more)))
             states = np.concatenate(parts)
             states = np.swapaxes(states, 0, 1).reshape(len(idx), num_steps + 1, d, d).copy()
+            if timings is not None:
+                timings["steps_s"] = timings.get("steps_s", 0.0) + time.perf_counter() - t_0
+                t_0 = time.perf_counter()
             late = overflowed(redo)
             if late:
                 for k in late:
@@ -290,8 +320,12 @@ def tempo_grid(influences, initial_state, unitary, propagators, dkmax, epsrel, n
                 for k, res in zip(over, join()):
                     states[k] = res
             rerun.extend(int(idx[k]) for k in redo)
+            if timings is not None:
+                timings["general_path_wait_s"] = (timings.get("general_path_wait_s", 0.0)
+                                                  + time.perf_counter() - t_0)
             out.extend(states)
         return out
 
-    res = run_ensemble(n_members, None, device=device, group=group, run_batch=run_batch)
+    res = run_ensemble(n_members, None, device=device, group=group, run_batch=run_batch,
+                       timings=timings)
     return res, rerun

@@ -383,3 +383,36 @@ def test_install_compute_dynamics_with_field(monkeypatch):
     finally:
         install.uninstall()
     assert oqupy.compute_dynamics_with_field is install._ORIGINALS["compute_dynamics_with_field"]
+
+
+def test_install_compute_correlations(monkeypatch):
+    """oqupy.compute_correlations / compute_correlations_nt (system_dynamics.py:791-1095) call
+    compute_dynamics with controls once per operator ordering: with the hook installed they
+    run through the device loop unchanged and return what the reference returns."""
+    oqupy = load_reference()
+    from oqupy_b200 import backends, install, process_tensor
+    from host_model_ops import HostModelOps
+    ops = HostModelOps()
+    monkeypatch.setattr(backends, "default_ops", lambda: ops)
+    monkeypatch.setattr(process_tensor, "default_ops", lambda: ops)
+    sig = oqupy.operators.sigma
+    corr = oqupy.PowerLawSD(alpha=0.1, zeta=1, cutoff=4.0, cutoff_type="exponential",
+                            temperature=0.5)
+    pt = oqupy.pt_tempo_compute(bath=oqupy.Bath(0.5 * sig("z"), corr), start_time=0.0,
+                                end_time=0.8, progress_type="silent",
+                                parameters=oqupy.TempoParameters(dt=0.1, dkmax=5, epsrel=1e-6))
+    system = oqupy.System(0.5 * sig("x") + 0.2 * sig("z"))
+    args = dict(system=system, process_tensor=pt, operator_a=sig("x"), operator_b=sig("z"),
+                times_a=0.2, times_b=(0.2, 0.7), time_order="ordered",
+                initial_state=oqupy.operators.spin_dm("z+"), progress_type="silent")
+    t_ref, c_ref = oqupy.compute_correlations(**args)
+    install.install()
+    try:
+        launches = ops.launches
+        t_new, c_new = oqupy.compute_correlations(**args)
+        assert ops.launches > launches            # ran on the (model) device
+        for a, b in zip(t_new, t_ref):
+            np.testing.assert_allclose(a, b, atol=1e-12)
+        np.testing.assert_allclose(c_new, c_ref, atol=1e-10, equal_nan=True)
+    finally:
+        install.uninstall()

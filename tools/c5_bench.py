@@ -49,12 +49,19 @@ def main():
                      for a in alphas for t in ti])              # member = (alpha, T) pair
     n = infl.shape[0]
     if world > 1:
+        # warm-up of the collectives the gather uses (NCCL sets its rings / trees up on the first
+        # call of every collective type: a per-process cost, not a per-job one)
+        from oqupy_b200.ensemble import run_ensemble
+        run_ensemble(world * 2, lambda i: np.zeros((3, 2, 2), dtype=complex) + i,
+                     device=ops.device)
         dist.barrier()
     torch.cuda.synchronize()
+    timings = {}
     t0 = time.perf_counter()
     res, rerun = tempo_grid(infl, g["initial_state"], g["unitary"],
                             lambda s: (g["prop_1"], g["prop_2"]), int(g["dkmax"]),
-                            float(g["epsrel"]), steps, device=ops.device, ops=ops)
+                            float(g["epsrel"]), steps, device=ops.device, ops=ops,
+                            timings=timings)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     tt = torch.tensor([wall], dtype=torch.float64, device=ops.device)
@@ -84,6 +91,7 @@ def main():
             "member_steps_per_s": n * steps / float(tt[0]),
             "runs_per_s": n / float(tt[0]), "seconds": float(tt[0]),
             "members_on_general_path": len(rerun),
+            "rank0_phase_seconds": {k: round(v, 3) for k, v in timings.items()},
             "cpu_oracle_steps_per_s_one_thread": len(sample) * steps / cpu_s,
             "host_cores": os.cpu_count(),
             "max_dev_vs_oracle_sample": dev,

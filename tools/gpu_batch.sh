@@ -25,6 +25,7 @@ for job in "$@"; do
     tebd3)     B200_SVD_QR_COSTOL=1 B200_SVD_QR_TALL=16 B200_SVD_QR_MINQ=128 timeout 900 python tools/bench_rows.py tebd > gpurun_out/${TAG}_tebd3.jsonl 2> gpurun_out/${TAG}_tebd3.err ;;
     tebd4)     B200_SVD_QR_COSTOL=1 B200_SVD_QR_TALL=16 B200_SVD_QR_MINQ=64 timeout 900 python tools/bench_rows.py tebd > gpurun_out/${TAG}_tebd4.jsonl 2> gpurun_out/${TAG}_tebd4.err ;;
     tebdtest2) B200_SVD_QR_COSTOL=1 B200_SVD_QR_TALL=16 timeout 900 python -m pytest tests/test_parity_gpu.py -x -q -k tebd > gpurun_out/${TAG}_tebdtest2.log 2>&1 ;;
+    smoke)     timeout 600 python -c 'import __graft_entry__ as g; g.smoke()' > gpurun_out/${TAG}_smoke.log 2>&1 ;;
     rows)      timeout 1500 python tools/bench_rows.py > gpurun_out/${TAG}_rows.jsonl 2> gpurun_out/${TAG}_rows.err ;;
     svdstep)   timeout 900 python tools/svd_profile_step.py 40 > gpurun_out/${TAG}_svdstep.log 2>&1 ;;
     stepprof)  timeout 600 python tools/step_profile.py 50 300 > gpurun_out/${TAG}_stepprof.jsonl 2> gpurun_out/${TAG}_stepprof.err ;;
