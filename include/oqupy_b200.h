@@ -135,7 +135,9 @@ int b200_svd_plan(const void* work, int m, int n, int32_t* out4);
  * stage's y, singular values, column order} */
 int b200_svd_qr_layout(int m, int n, int k, int64_t* out16);
 /* runtime switches (tests, A/B measurements): "qr" (0/1: rank-revealing QR front end),
- * "qr_minq" (smallest min(m,n) that takes it), "qr_cols" (columns per CTA of the QR grid) */
+ * "qr_minq" (smallest min(m,n) that takes it), "qr_cols" (columns per CTA of the QR grid);
+ * "max_slices" (CALLING THREAD only; < 0 clears it): cap of the row slices per pair slot, i.e.
+ * of the cooperative grid, for runs that share the GPU with a persistent kernel */
 int b200_svd_config(const char* key, double value);
 /* diagnostics: SM-clock cycles CTA 0 (leader of pair slot 0) spent per phase of the
  * Jacobi kernel: {0 wait for input blocks, 1 load + partial Gram, 2 publish, 3 wait
@@ -286,6 +288,10 @@ int b200_tempo_batch_info(void* batch, int32_t* status, int32_t* svds, int32_t* 
  * 0..n_members-1; NULL: identity): longest-running members first (a scheduling hint, the
  * results do not depend on it). */
 int b200_tempo_batch_set_order(void* batch, const int32_t* order);
+/* The following steps leave n SMs to other streams (0: none): members that outgrow shared
+ * memory are re-run on the general backend NEXT TO the batch and need free SMs for their
+ * cooperative launches. */
+int b200_tempo_batch_reserve_sms(void* batch, int n);
 size_t b200_tempo_batch_bytes(void* batch);
 
 #ifdef __cplusplus

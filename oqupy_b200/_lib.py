@@ -27,7 +27,7 @@ EXPORTS = [
     "b200_chain_log",
     "b200_tempo_batch_create", "b200_tempo_batch_destroy", "b200_tempo_batch_set",
     "b200_tempo_batch_step", "b200_tempo_batch_info", "b200_tempo_batch_bytes",
-    "b200_tempo_batch_set_order",
+    "b200_tempo_batch_set_order", "b200_tempo_batch_reserve_sms",
 ]
 
 
@@ -161,6 +161,8 @@ def load_library():
     lib.b200_tempo_batch_info.argtypes = [c_void_p] + [POINTER(c_int32)] * 5
     lib.b200_tempo_batch_set_order.restype = c_int
     lib.b200_tempo_batch_set_order.argtypes = [c_void_p, POINTER(c_int32)]
+    lib.b200_tempo_batch_reserve_sms.restype = c_int
+    lib.b200_tempo_batch_reserve_sms.argtypes = [c_void_p, c_int]
     lib.b200_tempo_batch_bytes.restype = c_size_t
     lib.b200_tempo_batch_bytes.argtypes = [c_void_p]
     _lib = lib

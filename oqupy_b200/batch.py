@@ -166,7 +166,7 @@ class BatchedTempoBackend:
         buf = self._ops.empty(num_steps, self.E, self.d2)
         for k in range(num_steps):
             self._launch(buf[k])
-        out = self._ops.to_host(buf)
+        out = self._read_back(buf)
         if strict:
             self.check()
         return out
@@ -181,6 +181,11 @@ class BatchedTempoBackend:
         self._ops._check(self._ops.lib.b200_tempo_batch_set_order(c_void_p(self._h), arr),  # pylint: disable=protected-access
                          "b200_tempo_batch_set_order")
 
+    def reserve_sms(self, n):
+        """Leave ``n`` SMs to other streams in the following steps (0: none)."""
+        self._ops._check(self._ops.lib.b200_tempo_batch_reserve_sms(c_void_p(self._h), int(n)),  # pylint: disable=protected-access
+                         "b200_tempo_batch_reserve_sms")
+
     def rebalance(self):
         """Longest-processing-time-first: hand the members with the largest bond dimensions
         (cost ~ chi^3 per SVD) to the first CTAs of every launch, so that the last wave of a
@@ -189,6 +194,26 @@ class BatchedTempoBackend:
         order = np.argsort(-chi, kind="stable")
         self.set_order(order)
         return order
+
+    def _read_back(self, buf):
+        """Device -> host WITHOUT holding the interpreter lock while the launches drain (an
+        asynchronous copy into pinned memory, then a sleeping poll on an event): members that
+        are re-run on the general backend in other host threads of this process (tempo_grid)
+        keep stepping while the batch runs.  A blocking ``tensor.cpu()`` starved them: measured
+        on the 4096-member grid, the 5.3 s re-run of one member made no progress during 17-37 s
+        of batch time."""
+        import time  # pylint: disable=import-outside-toplevel
+        import torch  # pylint: disable=import-outside-toplevel
+        if getattr(self._ops, "name", "") != "cuda":
+            return self._ops.to_host(buf)
+        host = torch.empty(buf.shape, dtype=buf.dtype, pin_memory=True)
+        host.copy_(buf, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream(buf.device))
+        while not done.query():
+            time.sleep(0.0005)
+        self._ops.d2h_bytes += buf.numel() * buf.element_size()
+        return host.numpy().copy()
 
     def info(self):
         """dict of per-member arrays: status, svds, sweeps, max_chi, bonds (list of lists)."""

@@ -57,7 +57,8 @@ struct BatchDev {
   cplx* tmp;          // [E][slot_elems]
   cplx* states;       // [E][d2]
   int first_member;
-  const int* order;   // [E] member taken by CTA i (nullptr: i): longest-running members first
+  const int* order;   // [E] i-th member drawn from the work queue (nullptr: i): longest first
+  int* counter;       // work queue head (zeroed before every launch)
 };
 
 __device__ __forceinline__ double wsum(double x) {
@@ -433,11 +434,8 @@ __device__ int cta_svd(SvdShared& S, cplx* X, int ld, cplx* Jsm, int jsm_elems, 
 }
 
 // ---------------------------------------------------------------- one member, one time step
-__global__ void __launch_bounds__(BT, 1) tempo_batch_step_kernel(const BatchDev P) {
-  extern __shared__ __align__(16) unsigned char bsm[];
-  __shared__ SvdShared S;
+__device__ void member_step(const BatchDev& P, const int e, SvdShared& S, unsigned char* bsm) {
   const int tid = threadIdx.x;
-  const int e = P.order ? P.order[blockIdx.x] : P.first_member + blockIdx.x;
   if (e >= P.E) return;
   const int d2 = P.d2, NS = P.ns_slots;
   int* hdr = P.hdr + (size_t)e * 8;
@@ -676,6 +674,24 @@ __global__ void __launch_bounds__(BT, 1) tempo_batch_step_kernel(const BatchDev 
   if (tid == 0) { hdr[0] = n_sites; hdr[1] = head; }
 }
 
+// PERSISTENT launch: gridDim.x CTAs (at most one per SM, fewer when SMs are kept free for
+// members that are re-run on the general path next to the batch) draw members from a work
+// queue in the order of P.order (longest-running first).  All exits of member_step are
+// CTA-uniform (they depend on the member's shapes only).
+__global__ void __launch_bounds__(BT, 1) tempo_batch_step_kernel(const BatchDev P) {
+  extern __shared__ __align__(16) unsigned char bsm[];
+  __shared__ SvdShared S;
+  __shared__ int s_next;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_next = atomicAdd(P.counter, 1);
+    __syncthreads();
+    const int i = s_next;
+    if (i >= P.E) break;
+    member_step(P, P.order ? P.order[i] : P.first_member + i, S, bsm);
+  }
+}
+
 struct Batch {
   BatchDev dev;
   cudaStream_t stream;
@@ -684,6 +700,8 @@ struct Batch {
   size_t bytes;
   void* arena;
   int* order_buf;
+  int reserve_sms;    // SMs the persistent launch leaves to other streams
+  int sms;
 };
 
 }  // namespace
@@ -732,6 +750,7 @@ void* b200_tempo_batch_create(void* stream, int n_members, int d2, int dkmax, in
   const size_t o_tmp = take(E * D.slot_elems * sizeof(cplx));
   const size_t o_states = take(E * d2 * sizeof(cplx));
   const size_t o_order = take(E * sizeof(int));
+  const size_t o_counter = take(sizeof(int));
   b->bytes = off;
   if (cudaMalloc(&b->arena, off) != cudaSuccess) {
     b200::set_error("b200_tempo_batch_create: cudaMalloc(%zu) failed", off);
@@ -748,6 +767,17 @@ void* b200_tempo_batch_create(void* stream, int n_members, int d2, int dkmax, in
   D.vg = (cplx*)(base + o_vg); D.jg = (cplx*)(base + o_jg); D.tmp = (cplx*)(base + o_tmp);
   D.states = (cplx*)(base + o_states);
   b->order_buf = (int*)(base + o_order);
+  D.counter = (int*)(base + o_counter);
+  b->reserve_sms = 0;
+  {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
+      (void)cudaGetLastError();
+      sms = 148;
+    }
+    b->sms = sms;
+  }
   static std::once_flag once;       // ensembles drive the library from several host threads
   static cudaError_t attr_rc = cudaSuccess;
   std::call_once(once, [] {
@@ -826,7 +856,11 @@ int b200_tempo_batch_step(void* h, const void* p1, const void* p2t, void* states
   b->step += 1;
   D.n_mpo = (b->step <= b->dkmax) ? b->step : b->dkmax + 1;
   b200::profile_begin(s, 3);
-  tempo_batch_step_kernel<<<b->E, BT, BATCH_SMEM, s>>>(D);
+  B200_CUDA_CHECK(cudaMemsetAsync(D.counter, 0, sizeof(int), s));
+  int grid = b->sms - b->reserve_sms;
+  if (grid < 1) grid = 1;
+  if (grid > b->E) grid = b->E;
+  tempo_batch_step_kernel<<<grid, BT, BATCH_SMEM, s>>>(D);
   B200_LAUNCH_CHECK();
   b200::profile_end(s, 3, 0.0, nullptr);
   if (states_out)
@@ -887,6 +921,16 @@ int b200_tempo_batch_set_order(void* h, const int32_t* order) {
   B200_CUDA_CHECK(cudaMemcpyAsync(b->order_buf, order, (size_t)b->E * sizeof(int),
                                   cudaMemcpyHostToDevice, b->stream));
   b->dev.order = b->order_buf;
+  return B200_OK;
+}
+
+/* The following steps leave `n` SMs to other streams (0: none): work that runs NEXT TO the
+ * batch -- members re-run on the general backend -- needs free SMs for its cooperative
+ * launches, which a launch that fills the GPU never yields. */
+int b200_tempo_batch_reserve_sms(void* h, int n) {
+  Batch* b = (Batch*)h;
+  if (!b || n < 0) { b200::set_error("b200_tempo_batch_reserve_sms: invalid argument"); return B200_EINVAL; }
+  b->reserve_sms = (n >= b->sms) ? b->sms - 1 : n;
   return B200_OK;
 }
 

@@ -117,6 +117,11 @@ const Knobs& knobs() {
   return k;
 }
 
+// per-thread override of B200_SVD_MAX_SLICES (b200_svd_config("max_slices", n) from the thread
+// that drives a backend): a run that shares the GPU with a persistent kernel keeps its
+// cooperative grids small enough for the SMs left free.  < 0: not set.
+thread_local int t_max_slices = -1;
+
 int device_sms() {
   static int sms = 0;
   if (!sms) {
@@ -152,7 +157,7 @@ __host__ Layout make_layout(int m, int n) {
   int max_r = sms / L.S;
   {   // throughput mode for ensembles of small problems: fewer row slices per SVD leave
       // SMs to the SVDs of other members running on their own streams
-    const int cap = knobs().max_slices;
+    const int cap = (t_max_slices >= 0) ? t_max_slices : knobs().max_slices;
     if (cap > 0 && max_r > cap) max_r = cap;
   }
   // narrow operands (<= 6 column blocks) are pure latency: three slices per slot are faster
@@ -1680,6 +1685,7 @@ extern "C" int b200_svd_config(const char* key, double value) {
   else if (k == "qr_theta") qr_knobs().theta = value;
   else if (k == "predict") qr_knobs().predict = (value != 0.0);
   else if (k == "qr_fastp") qr_knobs().fastp = (int)value;
+  else if (k == "max_slices") t_max_slices = (int)value;      // calling thread only
   else if (k == "qr_costol") qr_knobs().costol = (value != 0.0);
   else if (k == "qr_tall") qr_knobs().tall = (value < 1.0) ? 1 : (int)value;
   else if (k == "qr_minq_rel") qr_knobs().minq_rel = (int)value;

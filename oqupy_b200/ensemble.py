@@ -19,7 +19,8 @@ def shard_indices(n_members, rank, world_size):
     return list(range(rank, n_members, world_size))
 
 
-def _run_concurrent(mine, run_member, concurrent, make_ops, background=False):
+def _run_concurrent(mine, run_member, concurrent, make_ops, background=False,
+                    thread_init=None):
     """This rank's members on ``concurrent`` host threads, each with its own ops object and
     (on a GPU) its own CUDA stream: the C-ABI calls release the GIL, a TEMPO step is one C
     call, and the small cooperative SVD launches of different members overlap on the SMs
@@ -37,6 +38,8 @@ def _run_concurrent(mine, run_member, concurrent, make_ops, background=False):
     def worker():
         try:
             ops = make_ops() if make_ops is not None else None
+            if thread_init is not None:
+                thread_init(ops)
             on_gpu = ops is not None and getattr(ops, "name", "") == "cuda"
             # background work (members re-run next to a lock-step batch that fills every SM)
             # goes on a HIGH-PRIORITY stream: its short cooperative launches take the SMs that
@@ -68,6 +71,7 @@ def _run_concurrent(mine, run_member, concurrent, make_ops, background=False):
         if errors:
             raise errors[0]
         return results
+    join.alive = lambda: any(th.is_alive() for th in threads)
     return join if background else join()
 
 
@@ -206,7 +210,7 @@ def broadcast_process_tensor(pt, src=0, device=None, group=None, ops=None):
 
 def tempo_grid(influences, initial_state, unitary, propagators, dkmax, epsrel, num_steps,
                device=None, group=None, ops=None, chunk=4096, chi_cap=None,
-               fallback_concurrency=12, timings=None, check_every=10):
+               fallback_concurrency=12, timings=None, check_every=10, reserve=24):
     """BASELINE configs[4]: an ensemble of independent TEMPO runs (one per parameter point)
     sharded over the ranks and, on every rank, advanced in LOCK-STEP by the batched engine
     (:class:`oqupy_b200.batch.BatchedTempoBackend`: one kernel launch per time step for all
@@ -269,10 +273,17 @@ def tempo_grid(influences, initial_state, unitary, propagators, dkmax, epsrel, n
                 lock-step engine carries on with the others."""
                 if cuda:
                     from ._lib import CudaOps  # pylint: disable=import-outside-toplevel
+                    # the persistent batch launch leaves `reserve` SMs free from now on, and the
+                    # re-runs keep their cooperative SVD grids within them (<= 5 pair slots x
+                    # 4 slices for operands up to 160 columns)
+                    be.reserve_sms(reserve)
                     return _run_concurrent(over, member, min(fallback_concurrency, len(over)),
-                                           lambda: CudaOps(dev_index), background=True)
+                                           lambda: CudaOps(dev_index), background=True,
+                                           thread_init=lambda o: o.svd_config("max_slices", 4))
                 res = [member(k) for k in over]
-                return lambda: res
+                join_ = lambda: res      # noqa: E731
+                join_.alive = lambda: False
+                return join_
 
             # bond dimensions saturate within a few memory times: look for members that left
             # the lock-step path after 3 dkmax steps and start their re-runs right away
@@ -300,6 +311,8 @@ def tempo_grid(influences, initial_state, unitary, propagators, dkmax, epsrel, n
                 nxt = min(check_every, num_steps - done_steps)
                 parts.append(be.compute_steps(nxt, strict=False))
                 done_steps += nxt
+                if pending and cuda and not any(j.alive() for _, j in pending):
+                    be.reserve_sms(0)
                 if done_steps < num_steps:
                     more = overflowed(redo)
                     if more:

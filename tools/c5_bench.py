@@ -61,7 +61,8 @@ def main():
     res, rerun = tempo_grid(infl, g["initial_state"], g["unitary"],
                             lambda s: (g["prop_1"], g["prop_2"]), int(g["dkmax"]),
                             float(g["epsrel"]), steps, device=ops.device, ops=ops,
-                            timings=timings)
+                            timings=timings,
+                            reserve=int(os.environ.get("B200_BATCH_RESERVE", "24")))
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     tt = torch.tensor([wall], dtype=torch.float64, device=ops.device)

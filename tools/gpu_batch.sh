@@ -47,11 +47,15 @@ for job in "$@"; do
     c5)        timeout 1500 python tools/c5_bench.py 64 200 > gpurun_out/${TAG}_c5_n1.json 2> gpurun_out/${TAG}_c5_n1.err ;;
     c5r8on)    timeout 900 python tools/c5_bench.py 23 200 > gpurun_out/${TAG}_c5r8on.json 2> gpurun_out/${TAG}_c5r8on.err ;;
     c5r8off)   B200_BATCH_REBALANCE=0 timeout 900 python tools/c5_bench.py 23 200 > gpurun_out/${TAG}_c5r8off.json 2> gpurun_out/${TAG}_c5r8off.err ;;
+    c5m_res)   timeout 900 python tools/c5_bench.py 32 200 > gpurun_out/${TAG}_c5m_res.json 2> gpurun_out/${TAG}_c5m_res.err ;;
+    c5m_nores) B200_BATCH_RESERVE=0 timeout 900 python tools/c5_bench.py 32 200 > gpurun_out/${TAG}_c5m_nores.json 2> gpurun_out/${TAG}_c5m_nores.err ;;
+    c5probe)   timeout 600 python tools/c5_overflow_probe.py 32 200 32 > gpurun_out/${TAG}_c5probe.json 2> gpurun_out/${TAG}_c5probe.err ;;
     c5small)   timeout 900 python tools/c5_bench.py 24 100 > gpurun_out/${TAG}_c5small.json 2> gpurun_out/${TAG}_c5small.err ;;
     c5_n2)     timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/c5_bench.py 64 200 > gpurun_out/${TAG}_c5_n2.json 2> gpurun_out/${TAG}_c5_n2.err ;;
     bench_n8)  timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_n8.json 2> gpurun_out/${TAG}_bench_n8.err ;;
     bench_n4)  timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus 4 --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_n4.json 2> gpurun_out/${TAG}_bench_n4.err ;;
     c5_n4)     timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29515 tools/c5_bench.py 64 200 > gpurun_out/${TAG}_c5_n4.json 2> gpurun_out/${TAG}_c5_n4.err ;;
+    c5_n8r)    B200_BATCH_RESERVE=24 timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29520 tools/c5_bench.py 64 200 > gpurun_out/${TAG}_c5_n8r.json 2> gpurun_out/${TAG}_c5_n8r.err ;;
     c5_n8)     timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29519 tools/c5_bench.py 64 200 > gpurun_out/${TAG}_c5_n8.json 2> gpurun_out/${TAG}_c5_n8.err ;;
     bench_n2)  timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_n2.json 2> gpurun_out/${TAG}_bench_n2.err ;;
     *) echo "unknown job $job" ;;
