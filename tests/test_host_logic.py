@@ -257,3 +257,35 @@ def test_process_tensor_file_round_trip(tmp_path):
     host = pt.export_to(HostPt())
     assert len(host.mpo) == len(pt) and len(host.cap) == len(pt) + 1
     np.testing.assert_array_equal(host.mpo[3], pt.get_mpo_tensor(3))
+
+
+def test_run_concurrent_background_mode():
+    """ensemble._run_concurrent(background=True): returns at once, join() hands back the
+    results in member order, alive() reports the threads, thread_init runs once per thread,
+    errors of a member surface at join()."""
+    import threading
+    import time
+    from oqupy_b200.ensemble import _run_concurrent
+    seen, gate = [], threading.Event()
+
+    def member(i, ops):
+        gate.wait(5.0)
+        return np.full(3, float(i))
+
+    join = _run_concurrent([4, 7, 9], member, 2, None, background=True,
+                           thread_init=lambda ops: seen.append(threading.get_ident()))
+    assert join.alive()
+    gate.set()
+    res = join()
+    assert not join.alive()
+    assert [float(r[0]) for r in res] == [4.0, 7.0, 9.0]
+    assert len(seen) == 2 and len(set(seen)) == 2
+
+    def bad(i, ops):
+        raise ValueError(f"member {i}")
+    join = _run_concurrent([1], bad, 1, None, background=True)
+    time.sleep(0.05)
+    with pytest.raises(ValueError):
+        join()
+    # blocking mode returns the list directly
+    assert [float(r[0]) for r in _run_concurrent([2, 3], member, 2, None)] == [2.0, 3.0]
