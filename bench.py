@@ -228,8 +228,13 @@ def build_member(ops, infl, args, torch, sync, snapshot=False):
     for _ in range(args.warmup):
         be.compute_step()
     sites = None
+    snap_s = snap_bytes = None
     if snapshot:     # start state of the CPU sample (device -> host, before the timed region)
+        torch.cuda.synchronize(ops.device)
+        t0 = time.perf_counter()
         sites = [ops.to_host(be._site(k)) for k in range(be._num_sites())]  # pylint: disable=protected-access
+        snap_s = time.perf_counter() - t0
+        snap_bytes = int(sum(x.nbytes for x in sites))
     bond_hist = []
     ops.profile_enable(True)
     ops.profile_read_kinds()
@@ -256,7 +261,8 @@ def build_member(ops, infl, args, torch, sync, snapshot=False):
            "bond_hist": bond_hist,
            "launches": ops.launch_count() - l0, "h2d": ops.h2d_bytes - h0,
            "d2h": ops.d2h_bytes - d0 + be.chain_stats()[2],
-           "initialize_s": init_s, "preroll_s": pre_s}
+           "initialize_s": init_s, "preroll_s": pre_s,
+           "snapshot_s": snap_s, "snapshot_bytes": snap_bytes}
     kinds, flops, sweeps = ops.profile_read_kinds()
     ops.profile_enable(False)
     out.update({"kinds": kinds, "flops": flops, "sweeps": sweeps,
@@ -375,8 +381,16 @@ def gpu_arm(args):
             "max_bond": max(be.get_bond_dimensions()),
             "initialize_s": round(out["initialize_s"], 3),
             "preroll_s": round(out["preroll_s"], 2),
-            "update_process_tensor": "not in the timed loop (pt_tempo.py:275-278); measured "
-                                     "by tools/bench_rows.py",
+            "update_process_tensor": {
+                "note": ("not in the timed loop (the reference reads the sites out once, after "
+                         "the last step: pt_tempo.py:275-278).  What it costs with a HOST "
+                         "process tensor is one device->host copy of every site; measured here "
+                         "as the read-back of the whole chain at the start of the timed window "
+                         "(untimed; null when the CPU sample is off).  With a "
+                         "DeviceProcessTensor nothing leaves the device."),
+                "chain_readback_s": (None if out["snapshot_s"] is None
+                                     else round(out["snapshot_s"], 4)),
+                "chain_bytes": out["snapshot_bytes"]},
             "per_rank": per_rank,
         },
         "e2e": {"value": e2e, "unit": "steps/s",
