@@ -289,3 +289,66 @@ def test_run_concurrent_background_mode():
         join()
     # blocking mode returns the list directly
     assert [float(r[0]) for r in _run_concurrent([2, 3], member, 2, None)] == [2.0, 3.0]
+
+
+def test_tempo_grid_orchestration_with_a_model_backend(monkeypatch):
+    """tempo_grid's host logic (chunked stepping, early / late detection of members that
+    leave the lock-step path, their re-run, assembly of the result) against a stand-in for the
+    CUDA-only BatchedTempoBackend: every state encodes (member, step), members 2 and 5 leave
+    the lock-step path at steps 7 and 33 of 40."""
+    import oqupy_b200.batch as batch_mod
+    import oqupy_b200.ensemble as ens
+    fail_at = {2: 7, 5: 33}
+    calls = {"rebalance": 0, "chunks": []}
+
+    class ModelBatch:
+        def __init__(self, st0, infl, unitary, props, sn, sw, dkmax, eps, chi_cap=None,
+                     ops=None):
+            self.E, self.d2, self.step = len(st0), st0.shape[1], 0
+            self.members = [int(round(m[0, 0, 0].real)) for m in infl]
+
+        def initialize(self):
+            return 0, np.array([[m, 0, 0, 0] for m in self.members], dtype=complex)
+
+        def compute_steps(self, n, strict=True):
+            calls["chunks"].append(n)
+            out = np.zeros((n, self.E, self.d2), dtype=complex)
+            for k in range(n):
+                self.step += 1
+                for e, m in enumerate(self.members):
+                    ok = m not in fail_at or self.step < fail_at[m]
+                    out[k, e] = [m, self.step, 0, 0] if ok else np.nan
+            return out
+
+        def info(self):
+            st = np.array([2 if (m in fail_at and self.step >= fail_at[m]) else 0
+                           for m in self.members])
+            return {"status": st, "max_chi": np.arange(self.E)}
+
+        def rebalance(self):
+            calls["rebalance"] += 1
+
+        def reserve_sms(self, n):
+            raise AssertionError("no reservation without a CUDA device")
+
+    def model_member(infl, props, st, dkmax, eps, num_steps, unitary=None, ops=None):
+        m = int(round(infl[0, 0, 0].real))
+        return np.array([[[m, s], [0, -1]] for s in range(num_steps + 1)], dtype=complex)
+
+    monkeypatch.setattr(batch_mod, "BatchedTempoBackend", ModelBatch)
+    monkeypatch.setattr(ens, "tempo_member", model_member)
+    n, steps, dkmax = 8, 40, 4
+    infl = np.zeros((n, dkmax + 1, 4, 4), dtype=complex)
+    infl[:, :, 0, 0] = np.arange(n)[:, None]
+    ops = HostModelOps()
+    res, rerun = ens.tempo_grid(infl, np.eye(2), np.eye(2), lambda s: (None, None), dkmax,
+                                1e-7, steps, ops=ops, check_every=10)
+    assert sorted(rerun) == [2, 5]
+    assert sum(calls["chunks"]) == steps and calls["rebalance"] == 2
+    assert res.shape == (n, steps + 1, 2, 2)
+    for m in range(n):
+        for s in range(steps + 1):
+            if m in fail_at:
+                np.testing.assert_array_equal(res[m, s], [[m, s], [0, -1]])   # the re-run
+            else:
+                np.testing.assert_array_equal(res[m, s].reshape(-1), [m, s, 0, 0])
