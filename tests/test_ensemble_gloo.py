@@ -120,3 +120,48 @@ def test_broadcast_process_tensor_two_ranks(tmp_path):
     assert r0.shape == (5, 11, 2, 2)
     np.testing.assert_array_equal(r0, r1)
     assert np.abs(r0[1] - r0[0]).max() > 1e-6
+
+
+def _grad_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from conftest import gradient_multi_setup, load_golden
+    from host_model_ops import HostModelOps
+    import oqupy_b200 as ob
+    from oqupy_b200.ensemble import run_ensemble
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = load_golden("gradient_multi")
+    ops = HostModelOps()
+    pts, props, _ = gradient_multi_setup(g, ops)
+    n = int(g["num_steps"])
+    rng = np.random.default_rng(0)              # the same perturbation directions on every rank
+    direction = rng.normal(size=(6, n))
+
+    def member(i):      # BASELINE configs[4]: control-gradient perturbations, base +- 1e-3 * unit
+        def perturbed(step):
+            p1, p2 = props(step)
+            return p1 * (1.0 + 1e-3 * direction[i, step]), p2
+        derivs, states = ob.gradient_device(pts, perturbed, g["initial_state"],
+                                            g["target_derivative"], num_steps=n, ops=ops)
+        return np.concatenate((np.array(derivs).reshape(-1), np.array(states).reshape(-1)))
+
+    res = run_ensemble(6, member)
+    if rank == 0:
+        serial = np.array([member(i) for i in range(6)])
+        np.testing.assert_array_equal(res, serial)
+    np.save(os.path.join(out_dir, f"gr{rank}.npy"), res)
+    dist.destroy_process_group()
+
+
+def test_gradient_perturbation_panel_two_ranks(tmp_path):
+    """BASELINE configs[4], second half: a panel of control-gradient evaluations (two
+    environments) sharded over the ranks, adjoint tensors and dynamics gathered everywhere."""
+    port = _free_port()
+    mp.spawn(_grad_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = np.load(tmp_path / "gr0.npy"), np.load(tmp_path / "gr1.npy")
+    assert r0.shape[0] == 6
+    np.testing.assert_array_equal(r0, r1)
+    assert np.abs(r0[1] - r0[0]).max() > 1e-6
